@@ -1,0 +1,97 @@
+// Shared helpers for the eds_b200 CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+
+#include "../../include/eds_b200.h"
+
+namespace eds {
+
+// ---- error plumbing -------------------------------------------------------
+// eds_last_error() returns the thread-local message of the last failing call.
+void set_error(const char* fmt, ...);
+int  check_launch(const char* what);   // cudaGetLastError -> EDS_ERR_CUDA
+
+#define EDS_REQUIRE(cond, ...)                                   \
+    do {                                                         \
+        if (!(cond)) {                                           \
+            ::eds::set_error(__VA_ARGS__);                       \
+            return EDS_ERR_INVALID;                              \
+        }                                                        \
+    } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- activation element access (bf16 or fp32 storage, fp32 math) ----------
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+    static __device__ __forceinline__ float ld(const float* p) { return *p; }
+    static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+};
+template <> struct Elem<__nv_bfloat16> {
+    static __device__ __forceinline__ float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+    static __device__ __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+// 8 consecutive channels as one vector access (16 B for bf16, 32 B for fp32).
+template <typename T> struct Vec8;
+template <> struct Vec8<__nv_bfloat16> {
+    static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[8]) {
+        uint4 raw = *reinterpret_cast<const uint4*>(p);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float2 f = __bfloat1622float2(h[i]);
+            v[2 * i] = f.x;
+            v[2 * i + 1] = f.y;
+        }
+    }
+    static __device__ __forceinline__ void st(__nv_bfloat16* p, const float (&v)[8]) {
+        uint4 raw;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        *reinterpret_cast<uint4*>(p) = raw;
+    }
+};
+template <> struct Vec8<float> {
+    static __device__ __forceinline__ void ld(const float* p, float (&v)[8]) {
+        float4 a = *reinterpret_cast<const float4*>(p);
+        float4 b = *reinterpret_cast<const float4*>(p + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    static __device__ __forceinline__ void st(float* p, const float (&v)[8]) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+};
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Dispatch a templated launcher on the activation dtype code.
+#define EDS_DISPATCH_DTYPE(dtype, T, ...)                              \
+    do {                                                               \
+        if ((dtype) == EDS_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+        else if ((dtype) == EDS_F32) { using T = float; __VA_ARGS__; } \
+        else { ::eds::set_error("unknown dtype code %d", (int)(dtype)); return EDS_ERR_INVALID; } \
+    } while (0)
+
+}  // namespace eds

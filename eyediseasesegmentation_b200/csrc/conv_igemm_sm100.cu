@@ -1,0 +1,424 @@
+// Implicit-GEMM convolution for sm_100a: TMA-staged NHWC bf16 tiles, tcgen05.mma with the
+// fp32 accumulator in tensor memory, fused bias / residual / ReLU epilogue.
+//
+// Replaces the cuDNN convolutions behind Conv2dReLU (src/main/archs/unetplusplusstar.py:22-63),
+// the SENet / ResNet bottleneck convolutions, the axial block's in/out 1x1 convolutions and
+// 3x3 stride-2 shortcut (axial_attention_v2.py:243-255) and the attention projections
+// (Conv1d k=1 == 1x1 convolution, axial_attention_v2.py:49-52).  BatchNorm is folded into
+// w / bias on the host (eval-mode affine).
+//
+// GEMM view:  D[M = 128 output pixels][N = block_n couts] += A[M][K] * B[N][K]^T,
+//             K = taps * C walked as (tap, 64-channel chunk).
+//   A tile : one TMA box [block_k ch][TW][TH][TN] of the NHWC input, shifted by the tap's
+//            (dh, dw); out-of-bounds elements are zero-filled by TMA = the conv padding.
+//            Rows land 128 B apart with the 128B swizzle = the canonical K-major UMMA layout.
+//            Stride-2 convolutions read one of four parity planes of the input (plain strided
+//            tensor maps), so every tap is still a dense box.
+//   B tile : TMA box [block_k][block_n] of the [Cout][taps*C] weight matrix.
+//   D      : 128 TMEM lanes x block_n fp32 columns.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2-5 = epilogue (TMEM -> registers -> bias/residual/ReLU -> bf16 -> global).
+#include "common.cuh"
+#include <cuda.h>
+#include <algorithm>
+#include <climits>
+#include <cstring>
+#include <mutex>
+
+namespace eds {
+
+constexpr int kIgemmThreads = 192;
+constexpr int kMaxTaps = 9;
+constexpr int kMaxStages = 8;
+constexpr int kTileM = 128;
+
+struct IgemmParams {
+    CUtensorMap a_map[4];
+    CUtensorMap b_map;
+    const float* bias;
+    const __nv_bfloat16* residual;
+    __nv_bfloat16* y;
+    int taps, C, block_k, k_chunks, block_n, n_tiles;
+    int tw_log2, th_log2, TW, TH, TN;
+    int tiles_w, tiles_h;
+    int N, Ho, Wo, Cout, relu;
+    int stages, a_stage_bytes, b_stage_bytes, tmem_cols;
+    uint32_t idesc;
+    uint32_t desc_hi;  // upper 32 bits of the smem descriptor (SBO, version, swizzle mode)
+    int8_t tap_plane[kMaxTaps], tap_dh[kMaxTaps], tap_dw[kMaxTaps];
+};
+
+// ---- PTX wrappers ------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug becomes a trap (an error the host sees) instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("eds conv_igemm: mbarrier timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major swizzled operand descriptor: start address (>>4) | LBO=1 | SBO | version 1 | layout.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t desc_hi) {
+    return (uint64_t)(((saddr & 0x3FFFFu) >> 4) | (1u << 16)) | ((uint64_t)desc_hi << 32);
+}
+
+__global__ void __launch_bounds__(kIgemmThreads, 1)
+conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // operand stages need 1024 B alignment for the 128B swizzle atom
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tmem_full_bar = empty_bar + kMaxStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tile = blockIdx.x % p.n_tiles;
+    int m_tile = blockIdx.x / p.n_tiles;
+    const int tile_w = m_tile % p.tiles_w;
+    m_tile /= p.tiles_w;
+    const int tile_h = m_tile % p.tiles_h;
+    const int tile_n = m_tile / p.tiles_h;
+    const int w0 = tile_w * p.TW, h0 = tile_h * p.TH, n0 = tile_n * p.TN;
+    const int num_k_iters = p.taps * p.k_chunks;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&p.b_map);
+        prefetch_tmap(&p.a_map[0]);
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < num_k_iters; ++it) {
+                const int tap = it / p.k_chunks, kc = it - tap * p.k_chunks;
+                mbar_wait(&empty_bar[stage], phase ^ 1u);
+                mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(kTileM * p.block_k * 2 + p.block_n * p.block_k * 2));
+                uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                uint8_t* sb = sa + p.a_stage_bytes;
+                tma_load_4d(sa, &p.a_map[p.tap_plane[tap]], &full_bar[stage], kc * p.block_k, w0 + p.tap_dw[tap],
+                            h0 + p.tap_dh[tap], n0);
+                tma_load_2d(sb, &p.b_map, &full_bar[stage], tap * p.C + kc * p.block_k, n_tile * p.block_n);
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            int stage = 0;
+            uint32_t phase = 0;
+            const int k_steps = p.block_k / 16;
+            for (int it = 0; it < num_k_iters; ++it) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint32_t sb = sa + (uint32_t)p.a_stage_bytes;
+                for (int k = 0; k < k_steps; ++k)
+                    umma_bf16(tmem_base, make_desc(sa + k * 32, p.desc_hi), make_desc(sb + k * 32, p.desc_hi), p.idesc,
+                              (it > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&empty_bar[stage]);  // frees the stage once these MMAs have read it
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+            umma_commit(tmem_full_bar);
+        }
+    } else {
+        // ===== epilogue: warp q owns TMEM lanes [32q, 32q+32) =====
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const int tw = m & (p.TW - 1);
+        const int th = (m >> p.tw_log2) & (p.TH - 1);
+        const int tn = m >> (p.tw_log2 + p.th_log2);
+        const int ow = w0 + tw, oh = h0 + th, on = n0 + tn;
+        const bool valid = ow < p.Wo && oh < p.Ho && on < p.N;
+        const int co0 = n_tile * p.block_n;
+        const int64_t off = (((int64_t)on * p.Ho + oh) * p.Wo + ow) * p.Cout + co0;
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int c = 0; c < p.block_n; c += 16) {
+            uint32_t r[16];
+            tmem_ld16(taddr + (uint32_t)c, r);
+            if (valid) {
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+                if (p.bias) {
+                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + co0 + c);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 b = __ldg(b4 + i);
+                        v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+                    }
+                }
+                if (p.residual) {
+                    float r0[8], r1[8];
+                    Vec8<__nv_bfloat16>::ld(p.residual + off + c, r0);
+                    Vec8<__nv_bfloat16>::ld(p.residual + off + c + 8, r1);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { v[i] += r0[i]; v[8 + i] += r1[i]; }
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+                }
+                float o0[8], o1[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { o0[i] = v[i]; o1[i] = v[8 + i]; }
+                Vec8<__nv_bfloat16>::st(p.y + off + c, o0);
+                Vec8<__nv_bfloat16>::st(p.y + off + c + 8, o1);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ---- host side -----------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static std::once_flag g_igemm_once;
+static int g_igemm_init_rc = EDS_OK;
+
+static void igemm_init_once() {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        set_error("conv_igemm: cuTensorMapEncodeTiled entry point unavailable (%s)",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "driver too old");
+        g_igemm_init_rc = EDS_ERR_CUDA;
+        return;
+    }
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+        set_error("conv_igemm: cannot opt in to 227 KB shared memory: %s", cudaGetErrorString(e));
+        g_igemm_init_rc = EDS_ERR_CUDA;
+    }
+}
+
+int igemm_init() {
+    std::call_once(g_igemm_once, igemm_init_once);
+    return g_igemm_init_rc;
+}
+
+static int ilog2(int v) {
+    int l = 0;
+    while ((1 << l) < v) ++l;
+    return l;
+}
+static int pow2_ceil(int v) { return 1 << ilog2(v); }
+
+static int encode(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                  const cuuint32_t* box, CUtensorMapSwizzle swz, const char* what) {
+    cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+                          strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("conv_igemm: cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+        return EDS_ERR_CUDA;
+    }
+    return EDS_OK;
+}
+
+}  // namespace eds
+
+using namespace eds;
+
+extern "C" int eds_conv2d_igemm_bf16(const void* x, int N, int H, int W, int C, const void* w, const float* bias,
+                                     int Cout, int R, int S, int stride, int pad, int relu, const void* residual,
+                                     void* y, void* stream) {
+    EDS_REQUIRE(x && w && y, "conv2d_igemm: null pointer");
+    EDS_REQUIRE(N > 0 && H > 0 && W > 0, "conv2d_igemm: bad shape N=%d H=%d W=%d", N, H, W);
+    EDS_REQUIRE(C >= 16 && C % 16 == 0, "conv2d_igemm: C=%d must be a multiple of 16", C);
+    EDS_REQUIRE(Cout >= 16 && Cout % 16 == 0, "conv2d_igemm: Cout=%d must be a multiple of 16", Cout);
+    EDS_REQUIRE(R == S && (R == 1 || R == 3), "conv2d_igemm: filter %dx%d not supported (1x1, 3x3)", R, S);
+    EDS_REQUIRE(stride == 1 || stride == 2, "conv2d_igemm: stride=%d not supported", stride);
+    EDS_REQUIRE(pad >= 0 && pad <= R / 2, "conv2d_igemm: pad=%d", pad);
+    EDS_REQUIRE((((uintptr_t)x | (uintptr_t)w | (uintptr_t)y | (uintptr_t)residual) & 15) == 0 &&
+                    (((uintptr_t)bias) & 15) == 0,
+                "conv2d_igemm: pointers must be 16-byte aligned");
+    if (int rc = igemm_init()) return rc;
+    const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+    EDS_REQUIRE(Ho > 0 && Wo > 0, "conv2d_igemm: empty output");
+
+    IgemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.bias = bias;
+    p.residual = (const __nv_bfloat16*)residual;
+    p.y = (__nv_bfloat16*)y;
+    p.taps = R * S;
+    p.C = C;
+    p.block_k = (C % 64 == 0) ? 64 : (C % 32 == 0 ? 32 : 16);
+    p.k_chunks = C / p.block_k;
+    // cout tile: the largest multiple of 16 that divides Cout and is <= 256
+    int bn = 256;
+    while (bn > 16 && Cout % bn != 0) bn -= 16;
+    p.block_n = bn;
+    p.n_tiles = Cout / bn;
+    p.N = N; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.relu = relu;
+
+    // pixel tile TN x TH x TW = 128 minimising the number of tiles (ties -> wider rows)
+    int best_tiles = INT32_MAX, best_tw = 8;
+    for (int tw = 8; tw <= 128; tw *= 2) {
+        const int th = std::min(kTileM / tw, pow2_ceil(Ho));
+        const int tn = kTileM / (tw * th);
+        const int tiles = ceil_div(Wo, tw) * ceil_div(Ho, th) * ceil_div(N, tn);
+        if (tiles <= best_tiles) { best_tiles = tiles; best_tw = tw; }
+    }
+    p.TW = best_tw;
+    p.TH = std::min(kTileM / p.TW, pow2_ceil(Ho));
+    p.TN = kTileM / (p.TW * p.TH);
+    p.tw_log2 = ilog2(p.TW);
+    p.th_log2 = ilog2(p.TH);
+    p.tiles_w = ceil_div(Wo, p.TW);
+    p.tiles_h = ceil_div(Ho, p.TH);
+    const int tiles_n = ceil_div(N, p.TN);
+    const int64_t n_ctas = (int64_t)p.tiles_w * p.tiles_h * tiles_n * p.n_tiles;
+    EDS_REQUIRE(n_ctas < (1ll << 31), "conv2d_igemm: grid too large");
+
+    const CUtensorMapSwizzle swz = p.block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : p.block_k == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    const uint32_t layout = p.block_k == 64 ? 2u : (p.block_k == 32 ? 4u : 6u);
+    const uint32_t sbo = (uint32_t)(8 * p.block_k * 2) >> 4;
+    p.desc_hi = sbo | (1u << 14) | (layout << 29);
+    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    p.a_stage_bytes = kTileM * p.block_k * 2;                          // 16 / 8 / 4 KB
+    p.b_stage_bytes = (p.block_n * p.block_k * 2 + 1023) & ~1023;
+    const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+    const int budget = stage_bytes >= 40 * 1024 ? 200 * 1024 : 100 * 1024;
+    p.stages = std::max(2, std::min(kMaxStages, budget / stage_bytes));
+    p.tmem_cols = std::max(32, pow2_ceil(p.block_n));
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + (2 * kMaxStages + 1) * 8 + 16;
+
+    // input tensor maps: one per (row parity, col parity) plane that a tap touches
+    bool plane_used[4] = {false, false, false, false};
+    for (int r = 0; r < R; ++r)
+        for (int s = 0; s < S; ++s) {
+            const int t = r * S + s;
+            const int qh = r - pad, qw = s - pad;
+            if (stride == 1) {
+                p.tap_plane[t] = 0; p.tap_dh[t] = (int8_t)qh; p.tap_dw[t] = (int8_t)qw;
+            } else {
+                const int ph = qh & 1, pw = qw & 1;  // parity (two's complement: -1 & 1 == 1)
+                p.tap_plane[t] = (int8_t)(ph * 2 + pw);
+                p.tap_dh[t] = (int8_t)((qh - ph) / 2);
+                p.tap_dw[t] = (int8_t)((qw - pw) / 2);
+            }
+            plane_used[p.tap_plane[t]] = true;
+        }
+    const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
+    for (int pl = 0; pl < 4; ++pl) {
+        if (!plane_used[pl]) continue;
+        const int ph = stride == 1 ? 0 : pl >> 1, pw = stride == 1 ? 0 : pl & 1;
+        const int Wp = (W - pw + stride - 1) / stride, Hp = (H - ph + stride - 1) / stride;
+        EDS_REQUIRE(Wp > 0 && Hp > 0, "conv2d_igemm: empty parity plane");
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)stride * C * 2, (cuuint64_t)stride * W * C * 2, (cuuint64_t)H * W * C * 2};
+        cuuint32_t box[4] = {(cuuint32_t)p.block_k, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TN};
+        if (int rc = encode(&p.a_map[pl], xb + ((int64_t)ph * W + pw) * C, 4, dims, strides, box, swz, "input"))
+            return rc;
+    }
+    if (!plane_used[0]) p.a_map[0] = p.a_map[p.tap_plane[0]];  // keep the prefetch target valid
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)p.taps * C, (cuuint64_t)Cout};
+        cuuint64_t strides[1] = {(cuuint64_t)p.taps * C * 2};
+        cuuint32_t box[2] = {(cuuint32_t)p.block_k, (cuuint32_t)p.block_n};
+        if (int rc = encode(&p.b_map, w, 2, dims, strides, box, swz, "weights")) return rc;
+    }
+    conv_igemm_kernel<<<(unsigned)n_ctas, kIgemmThreads, smem, as_stream(stream)>>>(p);
+    return check_launch("conv_igemm_kernel");
+}

@@ -1,0 +1,280 @@
+"""Torch-tensor wrappers around the C ABI.
+
+PyTorch is used for device memory and streams only; every operation here is one call
+into ``libeds_b200.so``.  Activations are NHWC tensors ``[N, H, W, C]`` (bf16 or fp32).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import EDS_BF16, EDS_F32, check
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.bfloat16:
+        return EDS_BF16
+    if t.dtype == torch.float32:
+        return EDS_F32
+    raise TypeError(f"unsupported activation dtype {t.dtype}")
+
+
+def _chk(*tensors: Optional[torch.Tensor]) -> None:
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise ValueError("libeds_b200 kernels need CUDA tensors (there is no CPU path)")
+        if not t.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------ scoring
+def pr_hist(prob: torch.Tensor, gt: torch.Tensor, hist: Optional[torch.Tensor] = None,
+            straddle: Optional[torch.Tensor] = None, splits: int = 0):
+    """prob [n_img, n_px] fp32, gt [n_img, n_px] u8 -> (hist [n_img,2,BINS] i32, straddle [n_img,19,2] i32)."""
+    _chk(prob, gt)
+    assert prob.dtype == torch.float32 and gt.dtype == torch.uint8 and prob.shape == gt.shape and prob.dim() == 2
+    n_img, n_px = prob.shape
+    if hist is None:
+        hist = torch.zeros((n_img, 2, _lib.PR_BINS), dtype=torch.int32, device=prob.device)
+    if straddle is None:
+        straddle = torch.zeros((n_img, _lib.PR_NTHRESH, 2), dtype=torch.int32, device=prob.device)
+    check(_lib.lib().eds_pr_hist_f32(_p(prob), _p(gt), n_px, n_img, _p(hist), _p(straddle), splits, _stream()))
+    return hist, straddle
+
+
+def pr_scan(hist: torch.Tensor, straddle: torch.Tensor):
+    """-> ap [n] f64, roc [n] f64, counts [n,19,2] i64 (tp, pp), totals [n,2] i64 (n_pos, n_neg)."""
+    _chk(hist, straddle)
+    n = hist.shape[0]
+    dev = hist.device
+    ap = torch.empty(n, dtype=torch.float64, device=dev)
+    roc = torch.empty(n, dtype=torch.float64, device=dev)
+    counts = torch.empty((n, _lib.PR_NTHRESH, 2), dtype=torch.int64, device=dev)
+    totals = torch.empty((n, 2), dtype=torch.int64, device=dev)
+    check(_lib.lib().eds_pr_scan(_p(hist), _p(straddle), n, _p(ap), _p(roc), _p(counts), _p(totals), _stream()))
+    return ap, roc, counts, totals
+
+
+# ------------------------------------------------------------- TTA and paste
+def tta_merge(logits: torch.Tensor, deaug_maps: Sequence[Sequence[int]], apply_sigmoid: bool = True,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """logits [V,B,S,S] fp32 -> prob [B,S,S] fp32."""
+    _chk(logits, out)
+    V, B, S, S2 = logits.shape
+    assert S == S2 and logits.dtype == torch.float32 and len(deaug_maps) == V
+    if out is None:
+        out = torch.empty((B, S, S), dtype=torch.float32, device=logits.device)
+    flat = _lib.int_array([v for m in deaug_maps for v in m])
+    check(_lib.lib().eds_tta_merge(_p(logits), V, B, S, flat, int(apply_sigmoid), _p(out), _stream()))
+    return out
+
+
+def resize_paste(src: torch.Tensor, dst: torch.Tensor, crop, dst_yx, out_hw) -> None:
+    """Bilinear resize of src[crop] (y, x, h, w) to out_hw, written over dst at dst_yx."""
+    _chk(src, dst)
+    assert src.dtype == torch.float32 and dst.dtype == torch.float32 and src.dim() == 2 and dst.dim() == 2
+    cy, cx, ch, cw = crop
+    check(_lib.lib().eds_resize_paste_f32(_p(src), src.shape[0], src.shape[1], cy, cx, ch, cw, _p(dst), dst.shape[0],
+                                          dst.shape[1], dst_yx[0], dst_yx[1], out_hw[0], out_hw[1], _stream()))
+
+
+def preprocess_tile(img: torch.Tensor, y0: int, x0: int, S: int, mean, std,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """img [H,W,3] u8 -> normalised half-resolution window [3,S,S] fp32."""
+    _chk(img, out)
+    assert img.dtype == torch.uint8 and img.dim() == 3 and img.shape[2] == 3
+    if out is None:
+        out = torch.empty((3, S, S), dtype=torch.float32, device=img.device)
+    m = (C.c_double * 3)(*[float(v) for v in mean])
+    s = (C.c_double * 3)(*[float(v) for v in std])
+    check(_lib.lib().eds_preprocess_tile_u8(_p(img), img.shape[0], img.shape[1], y0, x0, S, m, s, _p(out), _stream()))
+    return out
+
+
+# -------------------------------------------------------------- network ops
+def stem_conv(x: torch.Tensor, aug_maps, w: torch.Tensor, bias: torch.Tensor, dtype: torch.dtype,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [B,3,H,W] fp32 NCHW -> [V*B, H/2, W/2, 64]."""
+    _chk(x, w, bias, out)
+    B, Cin, H, W = x.shape
+    assert Cin == 3 and x.dtype == torch.float32 and w.shape == (7, 7, 3, 64) and w.dtype == torch.float32
+    V = len(aug_maps)
+    if out is None:
+        out = torch.empty((V * B, H // 2, W // 2, 64), dtype=dtype, device=x.device)
+    flat = _lib.int_array([v for m in aug_maps for v in m])
+    check(_lib.lib().eds_stem_conv7x7s2(_p(x), B, H, W, V, flat, _p(w), _p(bias), _p(out), _dt(out), _stream()))
+    return out
+
+
+def conv_out_hw(H: int, W: int, R: int, stride: int, pad: int):
+    return (H + 2 * pad - R) // stride + 1, (W + 2 * pad - R) // stride + 1
+
+
+def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], stride: int = 1, pad: int = 0,
+           relu: bool = False, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+           impl: str = "auto") -> torch.Tensor:
+    """x [N,H,W,C], w [Cout,R,S,C] (same dtype as x) -> [N,Ho,Wo,Cout].
+
+    impl: "tc" = tcgen05 implicit GEMM (bf16 only), "simt" = CUDA-core kernel,
+    "auto" = tc for bf16 activations, simt for fp32 (the fp32 parity mode).
+    """
+    _chk(x, w, bias, residual, out)
+    N, H, W_, Cin = x.shape
+    Cout, R, S, Cw = w.shape
+    assert Cw == Cin and w.dtype == x.dtype
+    Ho, Wo = conv_out_hw(H, W_, R, stride, pad)
+    if out is None:
+        out = torch.empty((N, Ho, Wo, Cout), dtype=x.dtype, device=x.device)
+    if impl == "auto":
+        impl = "tc" if x.dtype == torch.bfloat16 else "simt"
+    if impl == "tc":
+        if x.dtype != torch.bfloat16:
+            raise TypeError("the tcgen05 kernel takes bf16 activations")
+        check(_lib.lib().eds_conv2d_igemm_bf16(_p(x), N, H, W_, Cin, _p(w), _p(bias), Cout, R, S, stride, pad,
+                                               int(relu), _p(residual), _p(out), _stream()))
+    elif impl == "simt":
+        check(_lib.lib().eds_conv2d_simt(_p(x), N, H, W_, Cin, _p(w), _p(bias), Cout, R, S, stride, pad, int(relu),
+                                         _p(residual), _p(out), _dt(x), _stream()))
+    else:
+        raise ValueError(impl)
+    return out
+
+
+def head_conv3x3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor],
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [N,H,W,C], w [classes,3,3,C] fp32 -> logits [N,classes,H,W] fp32."""
+    _chk(x, w, bias, out)
+    N, H, W_, Cin = x.shape
+    classes = w.shape[0]
+    assert w.dtype == torch.float32 and w.shape[1:] == (3, 3, Cin)
+    if out is None:
+        out = torch.empty((N, classes, H, W_), dtype=torch.float32, device=x.device)
+    check(_lib.lib().eds_head_conv3x3(_p(x), N, H, W_, Cin, _p(w), _p(bias), classes, _p(out), _dt(x), _stream()))
+    return out
+
+
+def pool_out(size: int, k: int, stride: int, pad: int, ceil_mode: bool) -> int:
+    num = size + 2 * pad - k
+    o = (-(-num // stride) if ceil_mode else num // stride) + 1
+    if ceil_mode and (o - 1) * stride >= size + pad:
+        o -= 1
+    return o
+
+
+def maxpool2d(x: torch.Tensor, k: int, stride: int, pad: int = 0, ceil_mode: bool = False,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk(x, out)
+    N, H, W_, Cc = x.shape
+    Ho, Wo = pool_out(H, k, stride, pad, ceil_mode), pool_out(W_, k, stride, pad, ceil_mode)
+    if out is None:
+        out = torch.empty((N, Ho, Wo, Cc), dtype=x.dtype, device=x.device)
+    check(_lib.lib().eds_maxpool2d(_p(x), N, H, W_, Cc, k, stride, pad, int(ceil_mode), _p(out), _dt(x), _stream()))
+    return out
+
+
+def avgpool2_affine(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, relu: bool,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk(x, scale, shift, out)
+    N, H, W_, Cc = x.shape
+    if out is None:
+        out = torch.empty((N, H // 2, W_ // 2, Cc), dtype=x.dtype, device=x.device)
+    check(_lib.lib().eds_avgpool2_affine(_p(x), N, H, W_, Cc, _p(scale), _p(shift), int(relu), _p(out), _dt(x),
+                                         _stream()))
+    return out
+
+
+def channel_mean(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk(x, out)
+    N, H, W_, Cc = x.shape
+    if out is None:
+        out = torch.empty((N, Cc), dtype=torch.float32, device=x.device)
+    check(_lib.lib().eds_channel_mean(_p(x), N, H * W_, Cc, _p(out), _dt(x), _stream()))
+    return out
+
+
+def se_gate(mean: torch.Tensor, w1, b1, w2, b2, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk(mean, w1, b1, w2, b2, out)
+    N, Cc = mean.shape
+    Cr = w1.shape[0]
+    assert w1.shape == (Cr, Cc) and w2.shape == (Cc, Cr)
+    if out is None:
+        out = torch.empty((N, Cc), dtype=torch.float32, device=mean.device)
+    check(_lib.lib().eds_se_gate(_p(mean), N, Cc, Cr, _p(w1), _p(b1), _p(w2), _p(b2), _p(out), _stream()))
+    return out
+
+
+def se_scale_add_relu(x: torch.Tensor, gate: torch.Tensor, residual: torch.Tensor,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk(x, gate, residual, out)
+    N, H, W_, Cc = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.lib().eds_se_scale_add_relu(_p(x), _p(gate), _p(residual), N, H * W_, Cc, _p(out), _dt(x), _stream()))
+    return out
+
+
+def scse_apply(x: torch.Tensor, cgate: torch.Tensor, w_sse: torch.Tensor, b_sse: float,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk(x, cgate, w_sse, out)
+    N, H, W_, Cc = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.lib().eds_scse_apply(_p(x), _p(cgate), _p(w_sse), float(b_sse), N, H * W_, Cc, _p(out), _dt(x),
+                                    _stream()))
+    return out
+
+
+def upsample2x_concat(x0: torch.Tensor, skips: Sequence[torch.Tensor], mode: int,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk(x0, out, *skips)
+    N, h, w, C0 = x0.shape
+    ctot = C0 + sum(s.shape[3] for s in skips)
+    for s in skips:
+        assert s.shape[:3] == (N, 2 * h, 2 * w) and s.dtype == x0.dtype
+    if out is None:
+        out = torch.empty((N, 2 * h, 2 * w, ctot), dtype=x0.dtype, device=x0.device)
+    n = len(skips)
+    ptrs = (C.c_void_p * max(n, 1))(*[s.data_ptr() for s in skips])
+    chans = (C.c_int * max(n, 1))(*[s.shape[3] for s in skips])
+    check(_lib.lib().eds_upsample2x_concat(_p(x0), N, h, w, C0, mode, ptrs, chans, n, _p(out), _dt(x0), _stream()))
+    return out
+
+
+def axial_attention(qk: torch.Tensor, v: Optional[torch.Tensor], axis: int, heads: int, dqk: int, dv: int,
+                    rel: torch.Tensor, sim_scale: torch.Tensor, out_scale: torch.Tensor, out_shift: torch.Tensor,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk(qk, v, rel, sim_scale, out_scale, out_shift, out)
+    N, H, W_, Cq = qk.shape
+    L = H if axis == 0 else W_
+    assert rel.shape == (2 * dqk + dv, 2 * L - 1) and rel.dtype == torch.float32
+    assert Cq == heads * (2 * dqk + (0 if v is not None else dv))
+    if v is not None:
+        assert v.shape == (N, H, W_, heads * dv) and v.dtype == qk.dtype
+    if out is None:
+        out = torch.empty((N, H, W_, heads * dv), dtype=qk.dtype, device=qk.device)
+    check(_lib.lib().eds_axial_attention(_p(qk), Cq, _p(v), heads * dv, N, H, W_, axis, heads, dqk, dv, _p(rel),
+                                         _p(sim_scale), _p(out_scale), _p(out_shift), _p(out), _dt(qk), _stream()))
+    return out
+
+
+def mhca_gate(ori: torch.Tensor, att: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk(ori, att, out)
+    N, h, w, Cc = att.shape
+    assert ori.shape == (N, 2 * h, 2 * w, Cc)
+    if out is None:
+        out = torch.empty_like(ori)
+    check(_lib.lib().eds_mhca_gate(_p(ori), _p(att), N, h, w, Cc, _p(out), _dt(ori), _stream()))
+    return out

@@ -1,0 +1,203 @@
+/*
+ * eds_b200.h -- C ABI of libeds_b200.so, the B200 (sm_100a) hot path of
+ * duylebkHCM/EyeDiseaseSegmentation's inference-and-scoring pipeline.
+ *
+ * The reference is 100 % Python and has no FFI of its own; every entry point below
+ * replaces a span of reference Python (cited as file:line relative to the reference
+ * root) that the Python shim in eyediseasesegmentation_b200/ calls through ctypes.
+ * INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 (EDS_OK) or a negative error code; the message of the
+ *     last failure on the calling thread is eds_last_error();
+ *   - all tensor pointers are caller-owned DEVICE pointers unless the parameter
+ *     name ends in _host; nothing is allocated, freed or synchronised inside;
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it and the
+ *     call returns immediately;
+ *   - activations are NHWC (channels innermost) with storage type `dtype`
+ *     (EDS_BF16 or EDS_F32); arithmetic is fp32 (tensor-core convs: bf16 inputs,
+ *     fp32 accumulate);
+ *   - there is no CPU fallback: without a CUDA device every compute entry fails.
+ */
+#ifndef EDS_B200_H
+#define EDS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define EDS_API __attribute__((visibility("default")))
+#else
+#define EDS_API
+#endif
+
+#define EDS_OK 0
+#define EDS_ERR_INVALID (-1)
+#define EDS_ERR_CUDA (-2)
+#define EDS_ERR_UNSUPPORTED (-3)
+
+#define EDS_BF16 0
+#define EDS_F32 1
+
+/* PR/ROC histogram geometry (see DESIGN.md "score key").  A probability p (fp32) is
+ * mapped to key = clamp((int)(bits(p) >> 13) - EDS_PR_KEY_BIAS, 0, EDS_PR_BINS-1):
+ * bin 0 = p < 2^-24 (and negatives), then 10 mantissa bits per binade for
+ * 2^-24 <= p < 1 (24 * 1024 bins), and a last bin for p >= 1. */
+#define EDS_PR_KEY_SHIFT 13
+#define EDS_PR_KEY_BIAS ((103 << 10) - 1)
+#define EDS_PR_BINS (24 * 1024 + 2)
+/* thresholds of aucpr.py:53,128: 0,1e-5,1e-4,1e-3,1e-2,.1,...,.9,.99,.999,.9999,.99999,1 */
+#define EDS_PR_NTHRESH 19
+
+/* interpolation of the x2 decoder upsample */
+#define EDS_UP_NEAREST 0   /* deep_supunetplusplus.py:49, smp Unet decoder */
+#define EDS_UP_BILINEAR 1  /* unetplusplusstar.py:128 (align_corners=False) */
+
+EDS_API int eds_version(void);
+EDS_API const char* eds_last_error(void);
+/* 1 if a CUDA device with compute capability 10.x is present, else 0. */
+EDS_API int eds_device_ok(void);
+/* One-time per-process setup on the current device (constant tables, shared-memory
+ * opt-ins, driver entry points).  Must be called once before any entry point is
+ * used under CUDA-graph capture; otherwise the first call of each entry does it. */
+EDS_API int eds_init(void);
+
+/* ------------------------------------------------------------------ scoring
+ * Replaces sklearn average_precision_score / roc_auc_score as called from
+ * src/main/aucpr.py:24,38 and the 19-threshold loops of aucpr.py:60-81,136-170. */
+
+/* Per-image score histograms.  prob: [n_images][n_pixels] fp32, gt: same shape u8
+ * (non-zero = positive).  hist: [n_images][2][EDS_PR_BINS] u32 (class 0 = negatives),
+ * straddle: [n_images][EDS_PR_NTHRESH][2] u32 = pixels that share the key of
+ * threshold k and are strictly above it.  Both are ACCUMULATED into (caller zeroes).
+ * `splits` CTAs cooperate on one image (0 = pick). */
+EDS_API int eds_pr_hist_f32(const float* prob, const uint8_t* gt, int64_t n_pixels, int n_images,
+                    uint32_t* hist, uint32_t* straddle, int splits, void* stream);
+
+/* Scan of the histograms.  Per image: ap[i] (sklearn AP on key-quantised scores),
+ * roc[i] (trapezoid ROC-AUC), counts[i][k] = {tp, pp} at threshold k (strict >,
+ * aucpr.py:63-66), totals[i] = {n_pos, n_neg}.  NaN when a class is empty. */
+EDS_API int eds_pr_scan(const uint32_t* hist, const uint32_t* straddle, int n_images, double* ap,
+                double* roc, uint64_t* counts, uint64_t* totals, void* stream);
+
+/* --------------------------------------------------------------- TTA + paste
+ * Replaces ttach.SegmentationTTAWrapper's de-augment + Merger('mean') (tta.py:92-99,
+ * 173-180), the sigmoid (tta.py:114,210), the cv2.resize of the tile and the
+ * overwrite paste (tta.py:211-213) / center-crop + resize (tta.py:117-119). */
+
+/* logits: [V][B][S][S] fp32 (view-major).  view_maps_host: V*6 ints, de-augment map
+ * of view v: out[i][j] += logits_v[a*i+b*j+c][d*i+e*j+f].  prob: [B][S][S] fp32 =
+ * sigmoid((((l0+l1)+l2)+...)/V) in view order, or the raw mean when apply_sigmoid=0. */
+EDS_API int eds_tta_merge(const float* logits, int V, int B, int S, const int* view_maps_host,
+                  int apply_sigmoid, float* prob, void* stream);
+
+/* Bilinear (half-pixel centres, edge clamp == cv2.INTER_LINEAR on fp32 ==
+ * F.interpolate(align_corners=False)) resize of the crop
+ * src[crop_y:crop_y+crop_h, crop_x:crop_x+crop_w] to out_h x out_w, written over
+ * dst[dst_y:dst_y+out_h, dst_x:dst_x+out_w] (clipped to the dst extent). */
+EDS_API int eds_resize_paste_f32(const float* src, int src_h, int src_w, int crop_y, int crop_x,
+                         int crop_h, int crop_w, float* dst, int dst_h, int dst_w, int dst_y,
+                         int dst_x, int out_h, int out_w, void* stream);
+
+/* Sliding-window tile fetch (tta.py:201-204): window [y0,y0+2S) x [x0,x0+2S) of an
+ * HWC u8 RGB image -> 2x2 box mean with round-half-up (== cv2.resize of uint8 by
+ * exactly 1/2) -> x/255, -mean, /std (archs/__init__.py:88-97) -> out [3][S][S] fp32. */
+EDS_API int eds_preprocess_tile_u8(const uint8_t* img, int img_h, int img_w, int y0, int x0, int S,
+                           const double* mean3_host, const double* std3_host, float* out,
+                           void* stream);
+
+/* ------------------------------------------------------------- network ops */
+
+/* Encoder stem: 7x7 stride-2 pad-3 conv 3->64 + folded BN + ReLU (SENet layer0 /
+ * ResNet conv1,bn1,relu).  x: [B][3][H][W] fp32 NCHW as the reference feeds it.
+ * The V TTA views are folded into the loader: view v reads x through
+ * aug_maps_host (V*6 ints, aug_v(x)[i][j] = x[a*i+b*j+c][d*i+e*j+f]); output image
+ * index is v*B+b.  w: [7][7][3][64] fp32 (cout innermost, BN folded), bias: [64] fp32.
+ * y: [V*B][H/2][W/2][64]. */
+EDS_API int eds_stem_conv7x7s2(const float* x, int B, int H, int W, int V, const int* aug_maps_host,
+                       const float* w, const float* bias, void* y, int dtype, void* stream);
+
+/* Implicit-GEMM convolution on the tcgen05 tensor cores (bf16 in, fp32 accumulate in
+ * TMEM, TMA-staged NHWC tiles).  x: [N][H][W][C] bf16, w: [Cout][R][S][C] bf16 (BN
+ * folded), bias: [Cout] fp32 or NULL, residual: [N][Ho][Wo][Cout] bf16 or NULL (added
+ * before the ReLU), y: [N][Ho][Wo][Cout] bf16.  R=S in {1,3}, stride in {1,2},
+ * C % 16 == 0, Cout % 16 == 0.  Replaces cuDNN for unetplusplusstar.py:40-63 and the
+ * SENet / ResNet / axial-block convolutions. */
+EDS_API int eds_conv2d_igemm_bf16(const void* x, int N, int H, int W, int C, const void* w,
+                          const float* bias, int Cout, int R, int S, int stride, int pad,
+                          int relu, const void* residual, void* y, void* stream);
+
+/* Same contract on CUDA cores with fp32 accumulate for either storage type; used for
+ * the fp32 parity mode and as the cross-check of the tensor-core kernel.  w has the
+ * activation dtype. */
+EDS_API int eds_conv2d_simt(const void* x, int N, int H, int W, int C, const void* w, const float* bias,
+                    int Cout, int R, int S, int stride, int pad, int relu, const void* residual,
+                    void* y, int dtype, void* stream);
+
+/* Segmentation head: 3x3 pad-1 conv C->classes with bias, fp32 logits out
+ * ([N][classes][H][W], NCHW like the reference output).  w: [classes][3][3][C] fp32. */
+EDS_API int eds_head_conv3x3(const void* x, int N, int H, int W, int C, const float* w, const float* bias,
+                     int classes, float* logits, int dtype, void* stream);
+
+/* MaxPool2d(k, stride, pad, ceil_mode): SENet layer0.pool (3,2,0,ceil), ResNet
+ * maxpool (3,2,1), MHCA init_conv pool (2,2,0). */
+EDS_API int eds_maxpool2d(const void* x, int N, int H, int W, int C, int k, int stride, int pad,
+                  int ceil_mode, void* y, int dtype, void* stream);
+
+/* AvgPool2d(2) followed by a per-channel affine (folded BN) and optional ReLU
+ * (axial_attention_v2.py:256-259,277-279). */
+EDS_API int eds_avgpool2_affine(const void* x, int N, int H, int W, int C, const float* scale,
+                        const float* shift, int relu, void* y, int dtype, void* stream);
+
+/* Global average pool: x [N][HW][C] -> mean [N][C] fp32. */
+EDS_API int eds_channel_mean(const void* x, int N, int HW, int C, float* mean, int dtype, void* stream);
+
+/* Squeeze-excite MLP on pooled features: gate = sigmoid(w2 * relu(w1 * mean + b1) + b2).
+ * mean/gate: [N][C] fp32, w1: [Cr][C], w2: [C][Cr] fp32. */
+EDS_API int eds_se_gate(const float* mean, int N, int C, int Cr, const float* w1, const float* b1,
+                const float* w2, const float* b2, float* gate, void* stream);
+
+/* y = relu(x * gate[n][c] + residual): tail of a SENet bottleneck. */
+EDS_API int eds_se_scale_add_relu(const void* x, const float* gate, const void* residual, int N, int HW,
+                          int C, void* y, int dtype, void* stream);
+
+/* SCSE (smp SCSEModule): y = x * (cgate[n][c] + sigmoid(sum_c x*w_sse[c] + b_sse)). */
+EDS_API int eds_scse_apply(const void* x, const float* cgate, const float* w_sse, float b_sse, int N,
+                   int HW, int C, void* y, int dtype, void* stream);
+
+/* Decoder concat: y[N][2h][2w][C0 + sum Ci] = cat(up2x(x0), skip_1 .. skip_n) with
+ * nearest or bilinear(align_corners=False) upsampling of x0 [N][h][w][C0].
+ * skips_host / skip_channels_host: n_skips (<= 5) device pointers / channel counts. */
+EDS_API int eds_upsample2x_concat(const void* x0, int N, int h, int w, int C0, int mode,
+                          const void* const* skips_host, const int* skip_channels_host,
+                          int n_skips, void* y, int dtype, void* stream);
+
+/* Axial attention core (axial_attention_v2.py:100-135,178-213) for one axis.
+ * qk: per pixel `heads` groups of [q(dqk) | k(dqk) | (v(dv) if v == NULL)] channels,
+ * pixel stride qk_cstride elements; v: optional separate tensor with `heads` groups
+ * of dv channels (MHCA), pixel stride v_cstride.  Tensors are [N][H][W][*]; axis 0
+ * attends along H (one sequence per (n,w)), axis 1 along W.  L = length of that axis.
+ * rel: [2*dqk+dv][2L-1] fp32 relative table; sim_scale: [heads][3] (qr, kr, dots BN
+ * scales); out_scale/out_shift: [2][heads*dv] (kv part, out part) folded out_norm.
+ * y: [N][H][W][heads*dv]. */
+EDS_API int eds_axial_attention(const void* qk, int qk_cstride, const void* v, int v_cstride, int N, int H,
+                        int W, int axis, int heads, int dqk, int dv, const float* rel,
+                        const float* sim_scale, const float* out_scale, const float* out_shift,
+                        void* y, int dtype, void* stream);
+
+/* MHCA gate (unetplusplusstar.py:146-147): y = ori * up2x_bilinear(sigmoid(att)),
+ * ori/y: [N][2h][2w][C], att: [N][h][w][C]. */
+EDS_API int eds_mhca_gate(const void* ori, const void* att, int N, int h, int w, int C, void* y, int dtype,
+                  void* stream);
+
+/* dtype conversion helpers for weights / debugging (n elements). */
+EDS_API int eds_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
+EDS_API int eds_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EDS_B200_H */

@@ -1,0 +1,405 @@
+"""Per-kernel numerics: every C-ABI entry point against a plain PyTorch fp32 statement of
+the same op (integer outputs bit-exact, floating point within the tolerance written in
+each test).  Network-level parity against the oracle lives in test_parity_gpu.py."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from eyediseasesegmentation_b200 import _lib, kernels as K  # noqa: E402
+
+DEV = "cuda"
+
+
+def setup_module(module):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def nhwc(x):  # NCHW -> NHWC contiguous
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+# ------------------------------------------------------------------ convolutions
+CONV_CASES = [
+    # N, H, W, C, Cout, R, stride, pad, relu, residual
+    (2, 32, 32, 64, 64, 3, 1, 1, True, False),
+    (1, 64, 64, 128, 256, 3, 1, 1, True, False),
+    (2, 16, 16, 256, 512, 1, 1, 0, False, True),
+    (1, 32, 32, 64, 128, 3, 2, 1, False, False),
+    (2, 32, 32, 128, 64, 1, 2, 0, True, False),
+    (1, 19, 19, 64, 64, 3, 1, 1, True, False),
+    (3, 8, 8, 64, 32, 3, 1, 1, True, False),
+    (1, 64, 64, 32, 16, 3, 1, 1, True, False),
+    (1, 64, 64, 16, 16, 3, 1, 1, True, False),
+    (1, 16, 16, 512, 640, 1, 1, 0, False, False),
+    (1, 38, 38, 64, 64, 3, 2, 1, True, False),
+    (1, 128, 128, 320, 32, 3, 1, 1, True, False),
+]
+
+
+def conv_ref(x, w, bias, stride, pad, relu, residual):
+    y = F.conv2d(nchw(x.float()), w.float().permute(0, 3, 1, 2), bias, stride=stride, padding=pad)
+    if residual is not None:
+        y = y + nchw(residual.float())
+    if relu:
+        y = F.relu(y)
+    return nhwc(y)
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_simt_fp32(case):
+    N, H, W, C, Cout, R, stride, pad, relu, use_res = case
+    x = rnd(N, H, W, C, seed=1)
+    w = rnd(Cout, R, R, C, seed=2, scale=1.0 / math.sqrt(R * R * C))
+    b = rnd(Cout, seed=3)
+    Ho, Wo = K.conv_out_hw(H, W, R, stride, pad)
+    res = rnd(N, Ho, Wo, Cout, seed=4) if use_res else None
+    y = K.conv2d(x, w, b, stride, pad, relu, res, impl="simt")
+    ref = conv_ref(x, w, b, stride, pad, relu, res)
+    assert y.shape == ref.shape
+    err = (y - ref).abs().max().item()
+    assert err < 2e-4, f"simt fp32 conv max abs err {err}"
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_tcgen05_bf16(case):
+    N, H, W, C, Cout, R, stride, pad, relu, use_res = case
+    x = rnd(N, H, W, C, seed=1).bfloat16()
+    w = rnd(Cout, R, R, C, seed=2, scale=1.0 / math.sqrt(R * R * C)).bfloat16()
+    b = rnd(Cout, seed=3)
+    Ho, Wo = K.conv_out_hw(H, W, R, stride, pad)
+    res = rnd(N, Ho, Wo, Cout, seed=4).bfloat16() if use_res else None
+    y = K.conv2d(x, w, b, stride, pad, relu, res, impl="tc")
+    torch.cuda.synchronize()
+    ref = conv_ref(x, w, b, stride, pad, relu, res)
+    # inputs are identical bf16 values; only the output rounding (2^-9 relative) and the fp32
+    # accumulation order differ
+    err = (y.float() - ref).abs().max().item()
+    tol = 1e-2 * max(1.0, ref.abs().max().item())
+    assert err < tol, f"tcgen05 conv max abs err {err} (tol {tol}), rel {rel_err(y, ref)}"
+    assert rel_err(y, ref) < 4e-3
+    # and against the CUDA-core kernel on the same bf16 data
+    y2 = K.conv2d(x, w, b, stride, pad, relu, res, impl="simt")
+    assert (y.float() - y2.float()).abs().max().item() < tol
+
+
+def test_conv_tcgen05_large_k():
+    # decoder-sized reduction: K = 9 * 1024
+    x = rnd(1, 32, 32, 1024, seed=5).bfloat16()
+    w = rnd(256, 3, 3, 1024, seed=6, scale=1.0 / 96).bfloat16()
+    y = K.conv2d(x, w, None, 1, 1, True, None, impl="tc")
+    ref = conv_ref(x, w, None, 1, 1, True, None)
+    assert rel_err(y, ref) < 4e-3
+
+
+# --------------------------------------------------------------------------- stem
+def d4_maps(S):
+    from eyediseasesegmentation_b200 import ttach_compat as tta
+    return tta.view_maps(tta.aliases.d4_transform(), S, S)
+
+
+def test_stem_conv_views():
+    from eyediseasesegmentation_b200 import ttach_compat as tta
+    B, S = 2, 64
+    x = rnd(B, 3, S, S, seed=7)
+    w = rnd(64, 3, 7, 7, seed=8, scale=0.1)
+    b = rnd(64, seed=9)
+    tfm = tta.aliases.d4_transform()
+    aug, _ = tta.view_maps(tfm, S, S)
+    y = K.stem_conv(x, aug, w.permute(2, 3, 1, 0).contiguous(), b, torch.float32)
+    refs = []
+    for t in tfm:
+        refs.append(nhwc(F.relu(F.conv2d(t.augment_image(x), w, b, stride=2, padding=3))))
+    ref = torch.cat(refs, 0)
+    assert y.shape == ref.shape
+    assert (y - ref).abs().max().item() < 1e-4
+    yb = K.stem_conv(x, aug, w.permute(2, 3, 1, 0).contiguous(), b, torch.bfloat16)
+    assert rel_err(yb, ref) < 5e-3
+
+
+# -------------------------------------------------------------------- pointwise
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_maxpool_variants(dtype):
+    x = rnd(2, 33, 33, 64, seed=10).to(dtype)
+    for k, s, p, ceil in [(3, 2, 0, True), (3, 2, 1, False), (2, 2, 0, False)]:
+        y = K.maxpool2d(x, k, s, p, ceil)
+        ref = nhwc(F.max_pool2d(nchw(x.float()), k, s, p, ceil_mode=ceil))
+        assert y.shape == ref.shape, (k, s, p, ceil)
+        assert torch.equal(y.float(), ref)
+    x = rnd(1, 32, 32, 16, seed=11).to(dtype)
+    y = K.maxpool2d(x, 3, 2, 0, True)
+    assert y.shape == (1, 16, 16, 16)
+    assert torch.equal(y.float(), nhwc(F.max_pool2d(nchw(x.float()), 3, 2, 0, ceil_mode=True)))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_avgpool2_affine(dtype):
+    x = rnd(2, 16, 16, 64, seed=12).to(dtype)
+    sc, sh = rnd(64, seed=13), rnd(64, seed=14)
+    y = K.avgpool2_affine(x, sc, sh, True)
+    ref = nhwc(F.relu(F.avg_pool2d(nchw(x.float()), 2) * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)))
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    assert (y.float() - ref).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("C", [16, 64, 320, 1024, 3072])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_channel_mean(C, dtype):
+    x = rnd(3, 20, 12, C, seed=15).to(dtype)
+    m = K.channel_mean(x)
+    ref = x.float().mean(dim=(1, 2))
+    assert (m - ref).abs().max().item() < 1e-5
+
+
+def test_se_gate():
+    N, C, Cr = 3, 256, 16
+    mean = rnd(N, C, seed=16)
+    w1, b1, w2, b2 = rnd(Cr, C, seed=17, scale=0.1), rnd(Cr, seed=18), rnd(C, Cr, seed=19, scale=0.2), rnd(C, seed=20)
+    g = K.se_gate(mean, w1, b1, w2, b2)
+    ref = torch.sigmoid(F.relu(mean @ w1.t() + b1) @ w2.t() + b2)
+    assert (g - ref).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_se_scale_add_relu(dtype):
+    x, r = rnd(2, 8, 8, 64, seed=21).to(dtype), rnd(2, 8, 8, 64, seed=22).to(dtype)
+    g = torch.rand(2, 64, device=DEV)
+    y = K.se_scale_add_relu(x, g, r)
+    ref = F.relu(x.float() * g.view(2, 1, 1, 64) + r.float())
+    assert (y.float() - ref).abs().max().item() < (1e-6 if dtype == torch.float32 else 3e-2)
+
+
+@pytest.mark.parametrize("C", [16, 32, 320, 896])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_scse_apply(C, dtype):
+    x = rnd(2, 9, 7, C, seed=23).to(dtype)
+    cg = torch.rand(2, C, device=DEV)
+    w = rnd(C, seed=24, scale=0.1)
+    b = 0.3
+    y = K.scse_apply(x, cg, w, b)
+    xf = x.float()
+    s = torch.sigmoid((xf * w).sum(-1, keepdim=True) + b)
+    ref = xf * cg.view(2, 1, 1, C) + xf * s
+    assert (y.float() - ref).abs().max().item() < (2e-5 if dtype == torch.float32 else 4e-2)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_upsample2x_concat(mode, dtype):
+    x0 = rnd(2, 5, 7, 32, seed=25).to(dtype)
+    skips = [rnd(2, 10, 14, 16, seed=26).to(dtype), rnd(2, 10, 14, 64, seed=27).to(dtype)]
+    y = K.upsample2x_concat(x0, skips, mode)
+    up = F.interpolate(nchw(x0.float()), scale_factor=2, mode="bilinear" if mode else "nearest",
+                       **({"align_corners": False} if mode else {}))
+    ref = torch.cat([nhwc(up)] + [s.float() for s in skips], dim=-1)
+    assert y.shape == ref.shape
+    assert (y.float() - ref).abs().max().item() < (1e-6 if dtype == torch.float32 else 2e-2)
+    y1 = K.upsample2x_concat(x0, [], mode)
+    assert (y1.float() - nhwc(up)).abs().max().item() < (1e-6 if dtype == torch.float32 else 2e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_mhca_gate(dtype):
+    att = rnd(2, 6, 6, 16, seed=28).to(dtype)
+    ori = rnd(2, 12, 12, 16, seed=29).to(dtype)
+    y = K.mhca_gate(ori, att)
+    g = F.interpolate(torch.sigmoid(nchw(att.float())), scale_factor=2, mode="bilinear", align_corners=False)
+    ref = ori.float() * nhwc(g)
+    assert (y.float() - ref).abs().max().item() < (1e-6 if dtype == torch.float32 else 2e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_head_conv(dtype):
+    x = rnd(2, 20, 24, 16, seed=30).to(dtype)
+    w = rnd(1, 16, 3, 3, seed=31, scale=0.1)
+    b = rnd(1, seed=32)
+    y = K.head_conv3x3(x, w.permute(0, 2, 3, 1).contiguous(), b)
+    ref = F.conv2d(nchw(x.float()), w, b, padding=1)
+    assert (y - ref).abs().max().item() < 1e-5
+
+
+# -------------------------------------------------------------------- attention
+def attention_ref(q, k, v, rel, sim_scale, out_scale, out_shift, dqk, dv):
+    """q,k [b,h,dqk,L]; v [b,h,dv,L] -- the einsums of axial_attention_v2.py:178-213 with the
+    BatchNorms already reduced to their eval-mode scale/shift."""
+    L = q.shape[-1]
+    idx = (torch.arange(L).view(L, 1) - torch.arange(L).view(1, L) + L - 1).to(q.device)
+    emb = rel[:, idx]  # [c, x, y]
+    rq, rk, rv = emb[:dqk], emb[dqk:2 * dqk], emb[2 * dqk:]
+    qr = torch.einsum("bhid,idj->bhdj", q, rq)
+    kr = torch.einsum("bhid,idj->bhdj", k, rk)
+    dots = torch.einsum("bhid,bhij->bhdj", q, k)
+    s = sim_scale.view(1, -1, 3, 1, 1)
+    sim = qr * s[:, :, 0] + kr * s[:, :, 1] + dots * s[:, :, 2]
+    attn = torch.softmax(sim, dim=-1)
+    out = torch.einsum("bhdj,bhij->bhid", attn, v)
+    kv = torch.einsum("bhdj,idj->bhid", attn, rv)
+    b, h = q.shape[:2]
+    CO = h * dv
+    kv = kv.reshape(b, CO, L) * out_scale[:CO].view(1, -1, 1) + out_shift[:CO].view(1, -1, 1)
+    out = out.reshape(b, CO, L) * out_scale[CO:].view(1, -1, 1) + out_shift[CO:].view(1, -1, 1)
+    return kv + out  # [b, h*dv, L]
+
+
+@pytest.mark.parametrize("axis", [0, 1])
+@pytest.mark.parametrize("cross", [False, True])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_axial_attention(axis, cross, dtype):
+    N, H, W, heads, dqk = 2, 16, 16, 4, 8
+    dv = 16
+    L = H if axis == 0 else W
+    G = 2 * dqk + (0 if cross else dv)
+    qk = rnd(N, H, W, heads * G, seed=40, scale=0.5).to(dtype)
+    vt = rnd(N, H, W, heads * dv, seed=41, scale=0.5).to(dtype) if cross else None
+    rel = rnd(2 * dqk + dv, 2 * L - 1, seed=42, scale=0.5)
+    sim_scale = rnd(heads, 3, seed=43, scale=0.3)
+    out_scale, out_shift = rnd(2, heads * dv, seed=44), rnd(2, heads * dv, seed=45)
+    y = K.axial_attention(qk, vt, axis, heads, dqk, dv, rel, sim_scale, out_scale, out_shift)
+
+    # sequences: axis 0 -> (n, w) along h ; axis 1 -> (n, h) along w
+    def seqs(t):  # [N,H,W,Cc] -> [b, Cc, L]
+        t = t.float()
+        return t.permute(0, 2, 3, 1).reshape(N * W, -1, H) if axis == 0 else t.permute(0, 1, 3, 2).reshape(N * H, -1, W)
+
+    qk_s = seqs(qk).reshape(-1, heads, G, L)
+    q, k = qk_s[:, :, :dqk], qk_s[:, :, dqk:2 * dqk]
+    v = seqs(vt).reshape(-1, heads, dv, L) if cross else qk_s[:, :, 2 * dqk:]
+    ref = attention_ref(q, k, v, rel, sim_scale, out_scale.reshape(-1), out_shift.reshape(-1), dqk, dv)
+    if axis == 0:
+        ref = ref.reshape(N, W, heads * dv, H).permute(0, 3, 1, 2)
+    else:
+        ref = ref.reshape(N, H, heads * dv, W).permute(0, 1, 3, 2)
+    tol = 2e-4 if dtype == torch.float32 else 5e-2
+    assert (y.float() - ref).abs().max().item() < tol
+
+
+# ----------------------------------------------------------- TTA / paste / tile
+@pytest.mark.parametrize("alias", ["d4_transform", "flip_transform", "hflip_transform"])
+def test_tta_merge_matches_ttach_semantics(alias):
+    from eyediseasesegmentation_b200 import ttach_compat as tta
+    tfm = getattr(tta.aliases, alias)()
+    B, S = 2, 96
+    V = len(tfm)
+    logits = rnd(V, B, 1, S, S, seed=50)
+    _, deaug = tta.view_maps(tfm, S, S)
+    prob = K.tta_merge(logits.view(V, B, S, S).contiguous(), deaug, True)
+    merger = tta.Merger("mean", V)
+    for v, t in enumerate(tfm):
+        merger.append(t.deaugment_mask(logits[v]))
+    ref = torch.sigmoid(merger.result)[:, 0]
+    assert (prob - ref).abs().max().item() < 2e-6
+    mean = K.tta_merge(logits.view(V, B, S, S).contiguous(), deaug, False)
+    assert torch.equal(mean, merger.result[:, 0])  # same fp32 summation order -> bit exact
+
+
+def test_resize_paste_x2_and_general():
+    src = torch.rand(64, 64, device=DEV)
+    dst = torch.zeros(200, 210, device=DEV)
+    K.resize_paste(src, dst, (0, 0, 64, 64), (10, 20), (128, 128))
+    ref = F.interpolate(src[None, None], scale_factor=2, mode="bilinear", align_corners=False)[0, 0]
+    assert (dst[10:138, 20:148] - ref).abs().max().item() < 1e-6
+    assert dst[:10].abs().max().item() == 0 and dst[138:].abs().max().item() == 0
+    # clipped paste + crop + non-integer scale
+    dst2 = torch.zeros(100, 100, device=DEV)
+    K.resize_paste(src, dst2, (4, 8, 40, 48), (50, 60), (90, 75))
+    ref2 = F.interpolate(src[None, None, 4:44, 8:56], size=(90, 75), mode="bilinear", align_corners=False)[0, 0]
+    assert (dst2[50:, 60:] - ref2[:50, :40]).abs().max().item() < 1e-5
+
+
+def test_preprocess_tile_matches_numpy_float64():
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, size=(300, 260, 3), dtype=np.uint8)
+    mean, std = [0.44976714, 0.2186806, 0.06459363], [0.33224553, 0.17116262, 0.086509705]
+    S, y0, x0 = 64, 100, 50
+    out = K.preprocess_tile(torch.from_numpy(img).to(DEV), y0, x0, S, mean, std).cpu().numpy()
+    win = img[y0:y0 + 2 * S, x0:x0 + 2 * S].astype(np.int32)
+    small = (win[0::2, 0::2] + win[0::2, 1::2] + win[1::2, 0::2] + win[1::2, 1::2] + 2) // 4
+    ref = ((small / 255.0 - np.array(mean)) / np.array(std)).astype(np.float32).transpose(2, 0, 1)
+    assert np.array_equal(out, ref)
+
+
+# ---------------------------------------------------------------------- scoring
+def _np_counts(prob, gt):
+    tp, pp = [], []
+    for t in np.array(_lib.PR_THRESHOLDS):
+        m = prob > t
+        tp.append(int((m & (gt > 0)).sum()))
+        pp.append(int(m.sum()))
+    return np.array(tp), np.array(pp)
+
+
+def _quantise(prob):
+    bits = prob.view(np.int32).astype(np.int64)
+    return np.clip((bits >> _lib.PR_KEY_SHIFT) - _lib.PR_KEY_BIAS, 0, _lib.PR_BINS - 1)
+
+
+@pytest.mark.parametrize("n_px", [4096 * 3, 10007, 1 << 20])
+def test_pr_hist_and_scan(n_px):
+    from sklearn.metrics import average_precision_score, roc_auc_score
+    rng = np.random.default_rng(n_px)
+    n_img = 3
+    logit = rng.normal(-3, 2.5, size=(n_img, n_px)).astype(np.float32)
+    prob = (1 / (1 + np.exp(-logit))).astype(np.float32)
+    gt = (rng.random((n_img, n_px)) < 1 / (1 + np.exp(-(logit + rng.normal(0, 1.5, logit.shape))))).astype(np.uint8)
+    # plant values exactly on and next to thresholds, zeros and ones
+    th32 = np.array(_lib.PR_THRESHOLDS, dtype=np.float32)
+    prob[0, :19] = th32
+    prob[0, 19:38] = np.nextafter(th32, np.float32(2))
+    prob[0, 38:57] = np.nextafter(th32, np.float32(-1))
+    prob[1, :100] = 0.0
+    prob[1, 100:200] = 1.0
+    gt[2] = 0  # image without positives
+    hist, strad = K.pr_hist(torch.from_numpy(prob).to(DEV), torch.from_numpy(gt).to(DEV))
+    ap, roc, counts, totals = [t.cpu().numpy() for t in K.pr_scan(hist, strad)]
+    hist = hist.cpu().numpy()
+    for i in range(n_img):
+        keys = _quantise(prob[i])
+        for cls in (0, 1):
+            ref = np.bincount(keys[(gt[i] > 0) == bool(cls)], minlength=_lib.PR_BINS)
+            assert np.array_equal(hist[i, cls], ref)
+        tp, pp = _np_counts(prob[i], gt[i])
+        assert np.array_equal(counts[i, :, 0], tp) and np.array_equal(counts[i, :, 1], pp)
+        assert totals[i, 0] == gt[i].sum() and totals[i, 1] == n_px - gt[i].sum()
+        if gt[i].sum() == 0:
+            assert np.isnan(ap[i])
+            continue
+        # exact on key-quantised scores, within the 1e-3 budget on raw fp32 scores
+        assert abs(ap[i] - average_precision_score(gt[i], keys)) < 1e-12
+        assert abs(roc[i] - roc_auc_score(gt[i], keys)) < 1e-12
+        assert abs(ap[i] - average_precision_score(gt[i], prob[i])) < 1e-3
+        assert abs(roc[i] - roc_auc_score(gt[i], prob[i])) < 1e-3
+
+
+def test_pr_hist_flat_regions_and_accumulate():
+    # large constant areas exercise the warp-aggregated path; two launches accumulate
+    n_px = 1 << 18
+    prob = np.full((1, n_px), 0.25, dtype=np.float32)
+    prob[0, 1000:2000] = 0.75
+    gt = np.zeros((1, n_px), dtype=np.uint8)
+    gt[0, 1500:2500] = 1
+    p, g = torch.from_numpy(prob).to(DEV), torch.from_numpy(gt).to(DEV)
+    hist, strad = K.pr_hist(p, g)
+    hist, strad = K.pr_hist(p, g, hist, strad)
+    _, _, counts, totals = [t.cpu().numpy() for t in K.pr_scan(hist, strad)]
+    tp, pp = _np_counts(prob[0], gt[0])
+    assert np.array_equal(counts[0, :, 0], 2 * tp) and np.array_equal(counts[0, :, 1], 2 * pp)
+    assert totals[0, 0] == 2000
