@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libeds_b200.so")
 
 EDS_BF16, EDS_F32 = 0, 1
-UP_NEAREST, UP_BILINEAR = 0, 1
+UP_NEAREST, UP_BILINEAR, UP_NONE = 0, 1, 2
 PR_KEY_SHIFT = 13
 PR_KEY_BIAS = (103 << 10) - 1
 PR_BINS = 24 * 1024 + 2
@@ -46,7 +46,7 @@ PROTOTYPES = {
     "eds_se_scale_add_relu": [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
     "eds_scse_apply": [_vp, _vp, _vp, _f, _i, _i, _i, _vp, _i, _vp],
     "eds_upsample2x_concat": [_vp, _i, _i, _i, _i, _i, C.POINTER(_vp), C.POINTER(_i), _i, _vp, _i, _vp],
-    "eds_axial_attention": [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+    "eds_axial_attention": [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp],
     "eds_mhca_gate": [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
     "eds_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
     "eds_cast_bf16_to_f32": [_vp, _vp, _i64, _vp],

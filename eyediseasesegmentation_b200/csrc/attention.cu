@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(kAttnThreads)
 axial_attention_kernel(const T* __restrict__ qk, int qk_cstride, const T* __restrict__ vsrc, int v_cstride, int H,
                        int W, int axis, int heads, int dqk, int dv, const float* __restrict__ rel,
                        const float* __restrict__ sim_scale, const float* __restrict__ out_scale,
-                       const float* __restrict__ out_shift, T* __restrict__ y) {
+                       const float* __restrict__ out_shift, int relu, T* __restrict__ y) {
     extern __shared__ float sm[];
     const int L = axis == 0 ? H : W;
     const int R = 2 * L - 1;
@@ -114,7 +114,7 @@ axial_attention_kernel(const T* __restrict__ qk, int qk_cstride, const T* __rest
         }
         const int ch = head * dv + i;
         const float r = (out_scale[ch] * kv + out_shift[ch]) + (out_scale[CO + ch] * out + out_shift[CO + ch]);
-        Elem<T>::st(y + (pix0 + (int64_t)d * pstride) * CO + ch, r);
+        Elem<T>::st(y + (pix0 + (int64_t)d * pstride) * CO + ch, relu ? fmaxf(r, 0.f) : r);
     }
 }
 
@@ -124,8 +124,8 @@ using namespace eds;
 
 extern "C" int eds_axial_attention(const void* qk, int qk_cstride, const void* v, int v_cstride, int N, int H, int W,
                                    int axis, int heads, int dqk, int dv, const float* rel, const float* sim_scale,
-                                   const float* out_scale, const float* out_shift, void* y, int dtype,
-                                   void* stream) {
+                                   const float* out_scale, const float* out_shift, int relu, void* y,
+                                   int dtype, void* stream) {
     EDS_REQUIRE(qk && rel && sim_scale && out_scale && out_shift && y, "axial_attention: null pointer");
     EDS_REQUIRE(axis == 0 || axis == 1, "axial_attention: axis=%d", axis);
     EDS_REQUIRE(N > 0 && H > 0 && W > 0 && heads > 0 && dqk > 0 && dv > 0, "axial_attention: bad shape");
@@ -145,7 +145,7 @@ extern "C" int eds_axial_attention(const void* qk, int qk_cstride, const void* v
         if (e == cudaSuccess)
             axial_attention_kernel<T><<<grid, kAttnThreads, smem, as_stream(stream)>>>(
                 (const T*)qk, qk_cstride, (const T*)v, v_cstride, H, W, axis, heads, dqk, dv, rel, sim_scale,
-                out_scale, out_shift, (T*)y);
+                out_scale, out_shift, relu, (T*)y);
     });
     if (e != cudaSuccess) {
         set_error("axial_attention: shared-memory opt-in failed: %s", cudaGetErrorString(e));

@@ -238,7 +238,8 @@ __device__ __forceinline__ void up2x_bilinear_vec(const T* __restrict__ x0, int 
 template <typename T>
 __global__ void upsample2x_concat_kernel(const T* __restrict__ x0, int N, int h, int w, int C0, int mode,
                                          ConcatSrc skips, int Ctot, T* __restrict__ y) {
-    const int H = 2 * h, W = 2 * w, Ct8 = Ctot / 8;
+    const int up = mode == EDS_UP_NONE ? 1 : 2;
+    const int H = up * h, W = up * w, Ct8 = Ctot / 8;
     const int64_t total = (int64_t)N * H * W * Ct8;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
@@ -250,7 +251,8 @@ __global__ void upsample2x_concat_kernel(const T* __restrict__ x0, int N, int h,
         float v[8];
         if (c < C0) {
             if (mode == EDS_UP_BILINEAR) up2x_bilinear_vec<T>(x0, n, h, w, C0, oy, ox, c, v);
-            else Vec8<T>::ld(x0 + (((int64_t)n * h + (oy >> 1)) * w + (ox >> 1)) * C0 + c, v);
+            else if (mode == EDS_UP_NEAREST) Vec8<T>::ld(x0 + (((int64_t)n * h + (oy >> 1)) * w + (ox >> 1)) * C0 + c, v);
+            else Vec8<T>::ld(x0 + (((int64_t)n * h + oy) * w + ox) * C0 + c, v);
         } else {
             c -= C0;
             int k = 0;
@@ -455,7 +457,8 @@ extern "C" int eds_upsample2x_concat(const void* x0, int N, int h, int w, int C0
     EDS_REQUIRE(x0 && y, "upsample2x_concat: null pointer");
     EDS_REQUIRE(n_skips >= 0 && n_skips <= 5, "upsample2x_concat: n_skips=%d not in 0..5", n_skips);
     EDS_REQUIRE(C0 % 8 == 0 && C0 > 0, "upsample2x_concat: C0=%d must be a multiple of 8", C0);
-    EDS_REQUIRE(mode == EDS_UP_NEAREST || mode == EDS_UP_BILINEAR, "upsample2x_concat: bad mode %d", mode);
+    EDS_REQUIRE(mode == EDS_UP_NEAREST || mode == EDS_UP_BILINEAR || mode == EDS_UP_NONE,
+                "upsample2x_concat: bad mode %d", mode);
     ConcatSrc src;
     src.n = n_skips;
     int Ctot = C0;
@@ -467,7 +470,8 @@ extern "C" int eds_upsample2x_concat(const void* x0, int N, int h, int w, int C0
             Ctot += src.ch[k];
         }
     }
-    const int64_t total = (int64_t)N * 2 * h * 2 * w * (Ctot / 8);
+    const int up = mode == EDS_UP_NONE ? 1 : 2;
+    const int64_t total = (int64_t)N * up * h * up * w * (Ctot / 8);
     EDS_DISPATCH_DTYPE(dtype, T, (upsample2x_concat_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
                                      (const T*)x0, N, h, w, C0, mode, src, Ctot, (T*)y)));
     return check_launch("upsample2x_concat_kernel");

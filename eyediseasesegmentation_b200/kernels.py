@@ -242,10 +242,11 @@ def upsample2x_concat(x0: torch.Tensor, skips: Sequence[torch.Tensor], mode: int
     _chk(x0, out, *skips)
     N, h, w, C0 = x0.shape
     ctot = C0 + sum(s.shape[3] for s in skips)
+    up = 1 if mode == _lib.UP_NONE else 2
     for s in skips:
-        assert s.shape[:3] == (N, 2 * h, 2 * w) and s.dtype == x0.dtype
+        assert s.shape[:3] == (N, up * h, up * w) and s.dtype == x0.dtype
     if out is None:
-        out = torch.empty((N, 2 * h, 2 * w, ctot), dtype=x0.dtype, device=x0.device)
+        out = torch.empty((N, up * h, up * w, ctot), dtype=x0.dtype, device=x0.device)
     n = len(skips)
     ptrs = (C.c_void_p * max(n, 1))(*[s.data_ptr() for s in skips])
     chans = (C.c_int * max(n, 1))(*[s.shape[3] for s in skips])
@@ -255,7 +256,7 @@ def upsample2x_concat(x0: torch.Tensor, skips: Sequence[torch.Tensor], mode: int
 
 def axial_attention(qk: torch.Tensor, v: Optional[torch.Tensor], axis: int, heads: int, dqk: int, dv: int,
                     rel: torch.Tensor, sim_scale: torch.Tensor, out_scale: torch.Tensor, out_shift: torch.Tensor,
-                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    relu: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _chk(qk, v, rel, sim_scale, out_scale, out_shift, out)
     N, H, W_, Cq = qk.shape
     L = H if axis == 0 else W_
@@ -266,7 +267,8 @@ def axial_attention(qk: torch.Tensor, v: Optional[torch.Tensor], axis: int, head
     if out is None:
         out = torch.empty((N, H, W_, heads * dv), dtype=qk.dtype, device=qk.device)
     check(_lib.lib().eds_axial_attention(_p(qk), Cq, _p(v), heads * dv, N, H, W_, axis, heads, dqk, dv, _p(rel),
-                                         _p(sim_scale), _p(out_scale), _p(out_shift), _p(out), _dt(qk), _stream()))
+                                         _p(sim_scale), _p(out_scale), _p(out_shift), int(relu), _p(out), _dt(qk),
+                                         _stream()))
     return out
 
 

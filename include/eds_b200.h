@@ -55,6 +55,7 @@ extern "C" {
 /* interpolation of the x2 decoder upsample */
 #define EDS_UP_NEAREST 0   /* deep_supunetplusplus.py:49, smp Unet decoder */
 #define EDS_UP_BILINEAR 1  /* unetplusplusstar.py:128 (align_corners=False) */
+#define EDS_UP_NONE 2      /* plain torch.cat: x0 already has the output resolution */
 
 EDS_API int eds_version(void);
 EDS_API const char* eds_last_error(void);
@@ -169,7 +170,9 @@ EDS_API int eds_scse_apply(const void* x, const float* cgate, const float* w_sse
                    int HW, int C, void* y, int dtype, void* stream);
 
 /* Decoder concat: y[N][2h][2w][C0 + sum Ci] = cat(up2x(x0), skip_1 .. skip_n) with
- * nearest or bilinear(align_corners=False) upsampling of x0 [N][h][w][C0].
+ * nearest or bilinear(align_corners=False) upsampling of x0 [N][h][w][C0]; with
+ * EDS_UP_NONE the output is [N][h][w][...] (torch.cat of same-size maps,
+ * unetplusplusstar.py:253-254).
  * skips_host / skip_channels_host: n_skips (<= 5) device pointers / channel counts. */
 EDS_API int eds_upsample2x_concat(const void* x0, int N, int h, int w, int C0, int mode,
                           const void* const* skips_host, const int* skip_channels_host,
@@ -182,11 +185,12 @@ EDS_API int eds_upsample2x_concat(const void* x0, int N, int h, int w, int C0, i
  * attends along H (one sequence per (n,w)), axis 1 along W.  L = length of that axis.
  * rel: [2*dqk+dv][2L-1] fp32 relative table; sim_scale: [heads][3] (qr, kr, dots BN
  * scales); out_scale/out_shift: [2][heads*dv] (kv part, out part) folded out_norm.
+ * relu: apply the block's trailing ReLU (axial_attention_v2.py:279) to the output.
  * y: [N][H][W][heads*dv]. */
 EDS_API int eds_axial_attention(const void* qk, int qk_cstride, const void* v, int v_cstride, int N, int H,
                         int W, int axis, int heads, int dqk, int dv, const float* rel,
                         const float* sim_scale, const float* out_scale, const float* out_shift,
-                        void* y, int dtype, void* stream);
+                        int relu, void* y, int dtype, void* stream);
 
 /* MHCA gate (unetplusplusstar.py:146-147): y = ori * up2x_bilinear(sigmoid(att)),
  * ori/y: [N][2h][2w][C], att: [N][h][w][C]. */

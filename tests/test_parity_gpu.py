@@ -1,0 +1,120 @@
+"""Network-level parity: the CUDA path (through the registry / model interface) against the
+oracle (oracle/nets.py, pinned to the reference in tests/test_oracle.py) on the same
+random-init weights and seeded inputs.
+
+Tolerances (BASELINE.json north_star): probability maps within 1e-4 max-abs in fp32 mode and
+2e-2 in bf16 mode.  Because random-init logits have a small spread, the bf16 runs are also
+held to a relative-L2 bound on the logits and on every encoder feature map, which is the
+check that actually catches structural mistakes.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from eyediseasesegmentation_b200 import archs, ttach_compat as tta  # noqa: E402
+from oracle import nets  # noqa: E402
+
+from helpers import randomize_bn, rel_l2, oracle_forward, star_cfg  # noqa: E402
+
+
+def setup_module(module):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _input(b, s, seed=7):
+    return torch.randn(b, 3, s, s, generator=torch.Generator().manual_seed(seed))
+
+
+CASES = [
+    ("unetplusplusstar", star_cfg(8), 256, 2),
+    ("unetplusplusstar", star_cfg(16), 512, 1),
+    ("unetplusplus_deepsup", dict(encoder_name="se_resnet50", encoder_weights=None, classes=1,
+                                  decoder_attention_type="scse", deep_supervision=True), 256, 2),
+    ("unetplusplus_deepsup", dict(encoder_name="resnet34", encoder_weights=None, classes=1), 256, 2),
+    ("Unet", dict(encoder_name="resnet34", encoder_weights=None, classes=1), 512, 1),  # BASELINE config 1
+]
+
+
+def _build(name, cfg, seed=1999):
+    torch.manual_seed(seed)
+    model = archs.Unet(**dict(cfg)) if name == "Unet" else archs.get_model(name, dict(cfg), training=False)
+    randomize_bn(model, seed + 1)
+    return model.eval()
+
+
+@pytest.mark.parametrize("name,cfg,size,batch", CASES)
+def test_fp32_mode_matches_oracle(name, cfg, size, batch):
+    model = _build(name, cfg)
+    x = _input(batch, size)
+    ref, ref_feats = oracle_forward(name, cfg, model.state_dict(), x, features=True)
+    model = model.to("cuda")
+    model.precision = "fp32"
+    eng = model.engine()
+    eng.keep_features = True
+    out = model(x.cuda()).cpu()
+    assert out.shape == ref.shape
+    for i in range(1, 6):
+        f = eng.features[f"f{i}"].float().permute(0, 3, 1, 2).cpu()
+        assert rel_l2(f, ref_feats[i]) < 1e-4, f"encoder feature f{i}"
+    assert rel_l2(out, ref) < 1e-4
+    assert (torch.sigmoid(out) - torch.sigmoid(ref)).abs().max().item() < 1e-4  # north_star fp32 tolerance
+
+
+@pytest.mark.parametrize("name,cfg,size,batch", CASES)
+def test_bf16_mode_matches_oracle(name, cfg, size, batch):
+    model = _build(name, cfg)
+    x = _input(batch, size)
+    ref, ref_feats = oracle_forward(name, cfg, model.state_dict(), x, features=True)
+    model = model.to("cuda")
+    model.precision = "bf16"
+    eng = model.engine()
+    eng.keep_features = True
+    out = model(x.cuda()).cpu()
+    for i in range(1, 6):
+        f = eng.features[f"f{i}"].float().permute(0, 3, 1, 2).cpu()
+        assert rel_l2(f, ref_feats[i]) < 3e-2, f"encoder feature f{i}: {rel_l2(f, ref_feats[i])}"
+    assert rel_l2(out - out.mean(), ref - ref.mean()) < 8e-2, rel_l2(out - out.mean(), ref - ref.mean())
+    assert (torch.sigmoid(out) - torch.sigmoid(ref)).abs().max().item() < 2e-2  # north_star bf16 tolerance
+
+
+@pytest.mark.parametrize("alias,kind", [("d4_transform", "d4"), ("flip_transform", "flip")])
+def test_fused_tta_matches_ttach_semantics(alias, kind):
+    name, cfg = "unetplusplusstar", star_cfg(8)
+    model = _build(name, cfg)
+    x = _input(2, 256, seed=11)
+    sd = model.state_dict()
+    ref = nets.tta_mean_logits(lambda t: nets.forward(name, sd, t, cfg), x, kind)
+    model = model.to("cuda")
+    model.precision = "fp32"
+    wrapped = tta.SegmentationTTAWrapper(model, getattr(tta.aliases, alias)(), merge_mode="mean")
+    out = wrapped(x.cuda()).cpu()
+    assert out.shape == ref.shape
+    assert (torch.sigmoid(out) - torch.sigmoid(ref)).abs().max().item() < 1e-4
+    # the unfused route (one forward per materialised view) must agree with the fused one
+    plain = tta.Merger("mean", 8 if kind == "d4" else 4)
+    for t in getattr(tta.aliases, alias)():
+        plain.append(t.deaugment_mask(model(t.augment_image(x.cuda()).contiguous())))
+    assert (plain.result.cpu() - out).abs().max().item() < 1e-4
+    model.precision = "bf16"
+    out16 = wrapped(x.cuda()).cpu()
+    assert (torch.sigmoid(out16) - torch.sigmoid(ref)).abs().max().item() < 2e-2
+
+
+def test_reference_checkpoint_roundtrip(tmp_path):
+    """tta.py:86-87: torch.load(...)['model_state_dict'] -> load_state_dict -> identical outputs."""
+    name, cfg = "unetplusplus_deepsup", dict(encoder_name="resnet34", encoder_weights=None, classes=1)
+    a = _build(name, cfg, seed=3).to("cuda")
+    torch.save({"model_state_dict": a.state_dict()}, tmp_path / "best.pth")
+    b = _build(name, cfg, seed=4).to("cuda")
+    x = _input(1, 256).cuda()
+    assert not torch.equal(a(x), b(x))
+    b.load_state_dict(torch.load(tmp_path / "best.pth")["model_state_dict"])
+    assert torch.equal(a(x), b(x))
+
+
+def test_no_cpu_fallback():
+    model = _build("Unet", dict(encoder_name="resnet34", encoder_weights=None, classes=1))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model(_input(1, 64))
