@@ -1,0 +1,190 @@
+"""Shared core of the inference drivers (``tta.py`` / ``tta_vessel.py`` mirrors).
+
+One pass per image does everything the reference's three generator passes redo
+(src/main/tta.py:218,221,225): forward of all TTA views, merge, sigmoid, paste, and -- while
+the probability map is still in HBM -- the PR/ROC histogram.  The yielded arrays carry their
+scores (:class:`aucpr.ScoredArray`), so ``get_auc`` / ``plot_*`` / the mask writer reuse them.
+
+Multi-GPU: with ``torch.distributed`` initialised (torchrun, one process per
+GPU) the image list is sharded ``images[rank::world_size]``; no activation crosses ranks.
+The only exchange is the all-reduce of the pooled integer counts / AP sums in ``aucpr``.
+"""
+from __future__ import annotations
+
+import logging
+import os
+import re
+from pathlib import Path
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import archs, kernels as K, ttach_compat as tta
+from .aucpr import ScoredArray, score_device
+from .util import lesion_dict, make_grid
+
+logging.basicConfig(level=logging.INFO)
+
+
+class _Smp:
+    """Stand-in for the ``segmentation_models_pytorch`` namespace probed by
+    ``hasattr(smp, config['model_name'])`` (tta.py:62,155)."""
+    Unet = staticmethod(archs.Unet)
+
+
+smp = _Smp()
+
+
+def get_model(params, model_name):
+    """tta.py:40-46."""
+    params["encoder_weights"] = None
+    return getattr(smp, model_name)(**params)
+
+
+def str_2_bool(value: str):
+    if value.lower() in ["1", "true"]:
+        return True
+    elif value.lower() in ["0", "false"]:
+        return False
+    else:
+        raise ValueError("Invalid value, should be one of these 1, true, 0, false")
+
+
+def device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("the B200 inference drivers need a CUDA device; there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def build_model(config, logdir, args):
+    """Model dispatch + checkpoint load of tta.py:61-72,86-88 / 155-171."""
+    if hasattr(smp, config["model_name"]):
+        model = get_model(config["model_params"], config["model_name"])
+    elif config["model_name"] == "TransUnet":
+        raise NotImplementedError("TransUnet is outside the B200 hot path")
+    else:
+        model = archs.get_model(model_name=config["model_name"], params=config["model_params"], training=False)
+    ckpt = torch.load(f"{logdir}/checkpoints/{'best' if str_2_bool(args['best']) else 'last'}.pth",
+                      map_location="cpu")
+    model.load_state_dict(ckpt["model_state_dict"])
+    model = model.to(device())
+    model.eval()
+    return model
+
+
+def tta_transforms(args):
+    """tta.py:92-99: ``getattr(tta.aliases, args['tta'] + '_transform')``."""
+    factory = getattr(tta.aliases, args["tta"] + "_transform")
+    return factory(scales=[1, 2, 4]) if args["tta"] == "multiscale" else factory()
+
+
+def shard(items: Sequence, what: str = "images") -> List:
+    """This rank's slice of the work list (round-robin by index)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return list(items)[dist.get_rank()::dist.get_world_size()]
+    return list(items)
+
+
+def predict_probs(model, transforms, x: torch.Tensor) -> torch.Tensor:
+    """x [B,3,S,S] on the device -> probabilities [B,S,S] (sigmoid of the TTA-mean logits)."""
+    fused = getattr(model, "forward_tta", None)
+    if fused is not None and tta.is_fusable(transforms) and x.shape[2] == x.shape[3]:
+        return fused(x, transforms, apply_sigmoid=True)[:, 0]
+    wrapped = tta.SegmentationTTAWrapper(model, transforms, merge_mode="mean")
+    return torch.sigmoid(wrapped(x))[:, 0].contiguous()
+
+
+class CachedPredictions:
+    """Re-iterable ``(pred, gt, name)`` source: the first iteration runs ``produce`` (inference
+    + scoring) and keeps the results on the host; later iterations replay them.  This is what
+    makes the reference's ``@multigen`` pattern cost one pass instead of three."""
+
+    def __init__(self, produce: Callable):
+        self._produce = produce
+        self._items: Optional[list] = None
+
+    def __iter__(self):
+        if self._items is not None:
+            return iter(self._items)
+        return self._first_pass()
+
+    def _first_pass(self):
+        items = []
+        for item in self._produce():
+            items.append(item)
+            yield item
+        self._items = items
+
+    def __call__(self):   # ``predict_generator()`` call sites keep working
+        return self
+
+
+def read_rgb(path) -> np.ndarray:
+    from PIL import Image
+    return np.asarray(Image.open(path).convert("RGB")).astype("uint8")
+
+
+def read_mask(path, threshold: int) -> np.ndarray:
+    """PIL 'L' -> (x > threshold) -> {0,1} uint8 (tta.py:192-194 uses 0, the datasets use 50)."""
+    from PIL import Image
+    m = np.asarray(Image.open(path).convert("L"))
+    return (m > threshold).astype(np.uint8)
+
+
+def longest_max_size(img: np.ndarray, max_size: int, interpolation) -> np.ndarray:
+    """albumentations 1.0 ``F.longest_max_size`` (3P): scale so the longest side == max_size."""
+    import cv2
+    h, w = img.shape[:2]
+    scale = max_size / float(max(h, w))
+    if scale == 1.0:
+        return img
+    new_h, new_w = int(round(h * scale)), int(round(w * scale))
+    return cv2.resize(img, (new_w, new_h), interpolation=interpolation)
+
+
+def pad_to_square(img: np.ndarray, size: int) -> np.ndarray:
+    """albumentations ``PadIfNeeded(size, size, BORDER_CONSTANT, 0)`` (3P): centred zero pad."""
+    h, w = img.shape[:2]
+    top = int((size - h) / 2.0) if h < size else 0
+    left = int((size - w) / 2.0) if w < size else 0
+    out = np.zeros((max(size, h), max(size, w)) + img.shape[2:], dtype=img.dtype)
+    out[top:top + h, left:left + w] = img
+    return out
+
+
+def tiled_probability_map(model, transforms, image_dev: torch.Tensor, S: int, mean, std,
+                          tiles_per_batch: int = 6) -> torch.Tensor:
+    """Sliding-window inference of tta.py:196-213 on one decoded image (``[H,W,3]`` u8 on the
+    device): window 2S, min_overlap 32, each window box-averaged to SxS, all TTA views, sigmoid,
+    bilinear x2, overwrite-paste in ``make_grid`` order (last writer wins)."""
+    H, W = int(image_dev.shape[0]), int(image_dev.shape[1])
+    slices = make_grid((H, W), window=2 * S, min_overlap=32)
+    preds = torch.zeros((H, W), dtype=torch.float32, device=image_dev.device)
+    for (x1, x2, y1, y2) in slices:
+        if x1 < 0 or y1 < 0 or x2 - x1 != 2 * S or y2 - y1 != 2 * S:
+            raise ValueError(f"could not broadcast input array from shape ({2 * S},{2 * S}) into shape "
+                             f"({max(x2 - max(x1, 0), 0)},{max(y2 - max(y1, 0), 0)}): window larger than the image")
+    for i in range(0, len(slices), tiles_per_batch):
+        group = slices[i:i + tiles_per_batch]
+        x = torch.empty((len(group), 3, S, S), dtype=torch.float32, device=image_dev.device)
+        for j, (x1, _, y1, _) in enumerate(group):
+            K.preprocess_tile(image_dev, int(x1), int(y1), S, mean, std, out=x[j])
+        prob = predict_probs(model, transforms, x)
+        for j, (x1, _, y1, _) in enumerate(group):
+            K.resize_paste(prob[j], preds, (0, 0, S, S), (int(x1), int(y1)), (2 * S, 2 * S))
+    return preds
+
+
+def scored(preds_dev: torch.Tensor, gt: np.ndarray) -> ScoredArray:
+    gt_dev = torch.from_numpy(np.ascontiguousarray(gt)).to(preds_dev.device)
+    scores = score_device(preds_dev, gt_dev)
+    return ScoredArray(preds_dev.cpu().numpy(), scores)
+
+
+def output_dir(config, logdir) -> Path:
+    out_path = Path(config["out_dir"]) / config["dataset_name"] / "tta" / config["lesion_type"] / Path(logdir).name
+    if not os.path.isdir(out_path):
+        os.makedirs(out_path, exist_ok=True)
+    return out_path

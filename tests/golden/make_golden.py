@@ -1,0 +1,91 @@
+"""Generates the committed fixtures of tests/golden/ by running the REFERENCE'S OWN code
+(loaded by oracle/ref_loader.py) in the build container, where /root/reference exists:
+
+    python tests/golden/make_golden.py
+
+The fixtures travel to the GPU box (which has no /root/reference) and pin both the oracle
+(tests/test_oracle.py, CPU) and the CUDA path (tests/test_golden_gpu.py).  Inputs are
+re-created from seeds on both sides: the weights come from the product's deterministic
+initialiser and are loaded into the reference modules with load_state_dict(strict=True), which
+also pins the state_dict key layout.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle import ref_loader  # noqa: E402
+import helpers  # noqa: E402
+
+
+def reference_module(ref, name, cfg):
+    cfg = dict(cfg)
+    if name == "unetplusplusstar":
+        return ref.unetplusplusstar.UnetPlusPlusStar(**cfg)
+    if name == "unetplusplus_deepsup":
+        cfg["deep_supervision"] = False          # archs/__init__.py:118-119 (training=False)
+        return ref.deep_supunetplusplus.UnetPlusPlus(**cfg)
+    if name == "Unet":
+        return ref.smp.Unet(**cfg)
+    raise KeyError(name)
+
+
+def main():
+    ref = ref_loader.load()
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+
+    # 1. network outputs of the reference modules on product-initialised weights
+    nets_out, layout = {}, {}
+    for key, name, cfg, size, batch in helpers.NET_GOLDEN_CASES:
+        product = helpers.build_product_model(name, cfg)
+        module = reference_module(ref, name, cfg).eval()
+        module.load_state_dict(product.state_dict(), strict=True)
+        x = helpers.golden_input(batch, size)
+        with torch.no_grad():
+            y = module(x)
+        nets_out[key] = y.numpy().astype(np.float32)
+        layout[key] = {k: list(v.shape) for k, v in module.state_dict().items()}
+        print(key, tuple(y.shape), float(y.mean()), float(y.std()))
+    np.savez_compressed(os.path.join(HERE, "net_logits.npz"), **nets_out)
+    json.dump(layout, open(os.path.join(HERE, "state_dict_layout.json"), "w"))
+
+    # 2. scoring: the reference's aucpr.py on seeded synthetic probability maps
+    scoring = {}
+    cfg = {"out_dir": "/tmp/eds_golden_out", "dataset_name": "IDRiD", "lesion_type": "EX"}
+    for seed in (0, 1, 2):
+        items = helpers.synth_scoring_case(seed)
+        scoring[str(seed)] = {
+            "get_auc": float(ref.aucpr.get_auc(items, cfg)),
+            "get_aucroc": float(ref.aucpr.get_aucroc(items, cfg)),
+            "plot_aucpr_curve": [float(t) for t in ref.aucpr.plot_aucpr_curve(items, "golden", cfg)],
+            "plot_aucroc_curve": float(ref.aucpr.plot_aucroc_curve(items, "golden", cfg)),
+        }
+    json.dump(scoring, open(os.path.join(HERE, "scoring.json"), "w"), indent=1)
+
+    # 3. tiling
+    shapes = [((2848, 4288), 2048, 32), ((2848, 4288), 1024, 32), ((608, 608), 512, 32), ((1024, 1024), 1024, 32),
+              ((584, 565), 1024, 32), ((960, 999), 512, 32), ((2000, 3000), 256, 32), ((512, 512), 256, 0)]
+    grids = [{"shape": list(s), "window": w, "min_overlap": o,
+              "grid": ref.base_utils.make_grid(s, window=w, min_overlap=o).tolist()} for s, w, o in shapes]
+    json.dump(grids, open(os.path.join(HERE, "make_grid.json"), "w"))
+
+    # 4. preprocessing + registry names
+    pre = {}
+    sample = np.arange(0, 256, 5, dtype=np.uint8).reshape(-1, 1, 1).repeat(3, axis=2)
+    for ds in ("IDRiD", "FGADR", "DDR", "DRIVE", "HRF", "CHASEDB1", None):
+        fn, mean, std = ref_loader.get_preprocessing_fn(ds, False)
+        pre[str(ds)] = {"mean": mean, "std": std, "out": fn(sample).astype(np.float32).reshape(-1).tolist()}
+    json.dump({"preprocessing": pre, "registry": ref_loader.registry_names()},
+              open(os.path.join(HERE, "registry_preprocessing.json"), "w"))
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()

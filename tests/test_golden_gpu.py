@@ -1,0 +1,135 @@
+"""GPU parity against the committed outputs of the reference itself (tests/golden/) and
+pipeline-level parity against the oracle's restatement of the reference loops.  Nothing here
+reads /root/reference."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from eyediseasesegmentation_b200 import _driver as drv, aucpr, kernels as K, ttach_compat as tta  # noqa: E402
+from oracle import nets, pipeline, scoring  # noqa: E402
+import helpers  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("case", helpers.NET_GOLDEN_CASES, ids=[c[0] for c in helpers.NET_GOLDEN_CASES])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_cuda_path_reproduces_reference_logits(case, precision, tol):
+    key, name, cfg, size, batch = case
+    ref = torch.from_numpy(np.load(os.path.join(GOLDEN, "net_logits.npz"))[key])
+    model = helpers.build_product_model(name, cfg).to("cuda")
+    model.precision = precision
+    out = model(helpers.golden_input(batch, size).cuda()).cpu()
+    assert out.shape == ref.shape
+    assert (torch.sigmoid(out) - torch.sigmoid(ref)).abs().max().item() < tol
+    bound = 1e-4 if precision == "fp32" else 8e-2
+    assert helpers.rel_l2(out - out.mean(), ref - ref.mean()) < bound
+
+
+def test_scoring_interface_reproduces_reference_outputs(tmp_path):
+    golden = json.load(open(os.path.join(GOLDEN, "scoring.json")))
+    cfg = {"out_dir": str(tmp_path), "dataset_name": "IDRiD", "lesion_type": "EX"}
+    for seed, ref in golden.items():
+        items = helpers.synth_scoring_case(int(seed))
+        gen = helpers_multigen(items)
+        assert aucpr.get_auc(gen, cfg) == pytest.approx(ref["get_auc"], abs=1e-3)         # north_star: AUC-PR within 1e-3
+        assert aucpr.get_aucroc(gen, cfg) == pytest.approx(ref["get_aucroc"], abs=1e-3)
+        assert list(aucpr.plot_aucpr_curve(gen, "exp", cfg)) == ref["plot_aucpr_curve"]  # integer counts -> same picks
+        assert aucpr.plot_aucroc_curve(gen, "exp", cfg) == ref["plot_aucroc_curve"]
+        tp, pp, ap, an = aucpr._pooled_counts(gen)
+        o = scoring.pr_curve(items)
+        assert np.array_equal(tp, o["tp"]) and np.array_equal(pp, o["pp"]) and ap == o["ap"]   # bit-exact counts
+
+
+def helpers_multigen(items):
+    class Re:
+        def __iter__(self):
+            return iter(items)
+    return Re()
+
+
+def _fundus(h, w, seed):
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+    yy, xx = np.mgrid[:h, :w]
+    img[(yy - h / 2) ** 2 + (xx - w / 2) ** 2 > (0.48 * min(h, w)) ** 2] = 0      # black outside the disc
+    return img
+
+
+@pytest.mark.parametrize("alias,kind", [("flip_transform", "flip"), ("d4_transform", "d4")])
+def test_sliding_window_pipeline_matches_oracle(alias, kind):
+    """tta.py:196-213 end to end: tile fetch, TTA net, sigmoid, x2 paste, overwrite order."""
+    name, cfg = "unetplusplus_deepsup", dict(encoder_name="resnet34", encoder_weights=None, classes=1)
+    S = 128
+    model = helpers.build_product_model(name, cfg)
+    sd = model.state_dict()
+    image = _fundus(300, 420, 5)
+    mean, std = pipeline.DATASET_STATS["IDRiD"]
+    want = pipeline.tiled_probability_map(image, lambda t: nets.unetplusplus_forward(sd, t), S, mean, std, kind)
+    model = model.to("cuda")
+    model.precision = "fp32"
+    tfm = getattr(tta.aliases, alias)()
+    got = drv.tiled_probability_map(model, tfm, torch.from_numpy(image).cuda(), S, mean, std, tiles_per_batch=3)
+    assert got.shape == want.shape
+    assert np.abs(got.cpu().numpy() - want).max() < 1e-4
+    model.precision = "bf16"
+    got16 = drv.tiled_probability_map(model, tfm, torch.from_numpy(image).cuda(), S, mean, std)
+    assert np.abs(got16.cpu().numpy() - want).max() < 2e-2
+
+
+def test_window_larger_than_image_is_rejected():
+    model = helpers.build_product_model("Unet", dict(encoder_name="resnet34", encoder_weights=None, classes=1)).to("cuda")
+    img = torch.zeros((200, 200, 3), dtype=torch.uint8, device="cuda")
+    with pytest.raises(ValueError, match="window larger"):
+        drv.tiled_probability_map(model, tta.aliases.hflip_transform(), img, 128, [0, 0, 0], [1, 1, 1])
+
+
+def test_whole_image_resize_matches_cv2():
+    prob = torch.rand(1024, 1024, device="cuda")
+    full = torch.empty((2848, 4288), dtype=torch.float32, device="cuda")
+    K.resize_paste(prob, full, (172, 0, 680, 1024), (0, 0), (2848, 4288))
+    want = pipeline.whole_image_probability(prob.cpu().numpy(), (680, 1024), (2848, 4288))
+    assert np.abs(full.cpu().numpy() - want).max() < 2e-6
+
+
+# ---------------------------------------------------------------- full-size properties
+def test_full_size_scoring_properties():
+    """BASELINE size (2848 x 4288): size-independent properties instead of a CPU re-computation."""
+    H, W = 2848, 4288
+    g = torch.Generator(device="cuda").manual_seed(0)
+    logit = torch.randn(H * W, generator=g, device="cuda") * 3 - 4
+    prob = torch.sigmoid(logit)
+    gt = (torch.rand(H * W, generator=g, device="cuda") < torch.sigmoid(logit - 1)).to(torch.uint8)
+    s = aucpr.score_device(prob.view(H, W), gt.view(H, W))
+    assert s.n_pos + s.n_neg == H * W and s.n_pos == int(gt.sum())
+    assert np.all(np.diff(s.pp) <= 0) and np.all(np.diff(s.tp) <= 0) and np.all(s.tp <= s.pp)
+    assert s.pp[0] == int((prob > 0).sum()) and s.pp[-1] == 0
+    for k, t in enumerate(aucpr.thresh_list):                       # exact counts at every threshold
+        m = prob.double() > t
+        assert s.pp[k] == int(m.sum()) and s.tp[k] == int((m & (gt > 0)).sum())
+    perm = torch.randperm(H * W, device="cuda", generator=g)         # order of pixels is irrelevant
+    s2 = aucpr.score_device(prob[perm].view(H, W), gt[perm].view(H, W))
+    assert s2.ap == pytest.approx(s.ap, abs=1e-12) and np.array_equal(s2.tp, s.tp)
+    inv = aucpr.score_device(prob.view(H, W), (1 - gt).view(H, W))   # ROC symmetry under label flip
+    assert inv.roc == pytest.approx(1 - s.roc, abs=1e-9)
+    sub = slice(0, 1 << 20)                                          # vs sklearn on a 1 Mpx slice
+    from sklearn.metrics import average_precision_score
+    s3 = aucpr.score_device(prob[sub].view(1024, 1024), gt[sub].view(1024, 1024))
+    assert s3.ap == pytest.approx(average_precision_score(gt[sub].cpu().numpy(), prob[sub].cpu().numpy()), abs=1e-3)
+
+
+def test_tta_merge_linearity_full_tile():
+    S, V = 1024, 8
+    _, deaug = tta.view_maps(tta.aliases.d4_transform(), S, S)
+    a = torch.randn(V, 1, S, S, device="cuda")
+    b = torch.randn(V, 1, S, S, device="cuda")
+    ma, mb = K.tta_merge(a, deaug, False), K.tta_merge(b, deaug, False)
+    mab = K.tta_merge(a + b, deaug, False)
+    assert (mab - (ma + mb)).abs().max().item() < 1e-5
+    const = K.tta_merge(torch.full((V, 1, S, S), 0.25, device="cuda"), deaug, False)
+    assert torch.all(const == 0.25)

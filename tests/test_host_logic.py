@@ -1,0 +1,197 @@
+"""CPU tests of the host side: C-ABI surface, TTA view algebra, scoring curves from counts,
+prediction caching, and the world_size-2 reduction (gloo) that stands in for the NCCL
+all-reduce of the GPU box."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from eyediseasesegmentation_b200 import _lib, aucpr, ttach_compat as tta
+from eyediseasesegmentation_b200._driver import CachedPredictions, longest_max_size, pad_to_square
+from eyediseasesegmentation_b200.util import multigen
+from oracle import nets, scoring
+import helpers
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------ C ABI
+def test_library_loads_and_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "eds_b200.h")).read()
+    declared = sorted(set(re.findall(r"EDS_API\s+[\w\s\*]+?\b(eds_\w+)\s*\(", header)))
+    assert declared, "no declarations parsed"
+    lib = _lib.load()                      # dlopen only; no CUDA call
+    missing = [n for n in declared if not hasattr(lib, n)]
+    assert not missing, missing
+    assert declared == _lib.EXPORTS        # the ctypes table covers exactly the header
+    assert lib.eds_version() >= 100
+
+
+def test_compute_entries_fail_loudly_without_a_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _lib.load()
+    assert lib.eds_device_ok() == 0
+    assert lib.eds_init() != 0 and b"no CPU fallback" in lib.eds_last_error()
+    with pytest.raises(_lib.EdsError):
+        _lib.lib()
+    model = helpers.build_product_model("Unet", dict(encoder_name="resnet34", encoder_weights=None, classes=1))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model(torch.zeros(1, 3, 64, 64))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "eyediseasesegmentation_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "/root/reference" not in src, f
+
+
+# ------------------------------------------------------------------ TTA algebra
+@pytest.mark.parametrize("alias,kind,n", [("d4_transform", "d4", 8), ("flip_transform", "flip", 4),
+                                          ("hflip_transform", "hflip", 2)])
+def test_view_maps_agree_with_transform_chains(alias, kind, n):
+    tfm = getattr(tta.aliases, alias)()
+    assert len(tfm) == n
+    S = 12
+    x = torch.randn(2, 3, S, S)
+    aug, deaug = tta.view_maps(tfm, S, S)
+    ii, jj = torch.meshgrid(torch.arange(S), torch.arange(S), indexing="ij")
+    oracle_views = nets.tta_views(kind)
+    for v, t in enumerate(tfm):
+        a, b, c, d, e, f = aug[v]
+        assert torch.equal(t.augment_image(x), x[:, :, a * ii + b * jj + c, d * ii + e * jj + f])
+        assert torch.equal(t.augment_image(x), oracle_views[v][0](x))       # independent restatement
+        a, b, c, d, e, f = deaug[v]
+        y = torch.randn(2, 1, S, S)
+        assert torch.equal(t.deaugment_mask(y), y[:, :, a * ii + b * jj + c, d * ii + e * jj + f])
+        assert torch.equal(t.deaugment_mask(y), oracle_views[v][1](y))
+        assert torch.equal(t.deaugment_mask(t.augment_image(x)), x)
+
+
+def test_generic_wrapper_equals_oracle_tta_mean():
+    net = torch.nn.Conv2d(3, 1, 3, padding=1).eval()
+    x = torch.randn(2, 3, 16, 16)
+    with torch.no_grad():
+        for alias, kind in (("d4_transform", "d4"), ("flip_transform", "flip")):
+            w = tta.SegmentationTTAWrapper(net, getattr(tta.aliases, alias)(), merge_mode="mean")
+            assert torch.equal(w(x), nets.tta_mean_logits(net, x, kind))
+
+
+def test_multiscale_alias_is_not_fused():
+    t = tta.aliases.multiscale_transform(scales=[1, 2, 4])
+    assert len(t) == 3 and not tta.is_fusable(t)
+
+
+# ------------------------------------------------------------------ scoring host logic
+def _as_scored(items):
+    """Attach oracle-computed ImageScores so the aucpr entry points run without a GPU."""
+    out = []
+    for pred, gt, name in items:
+        tp, ap, pp = scoring.threshold_counts(pred, gt)
+        from sklearn.metrics import average_precision_score, roc_auc_score
+        pos = int(gt.sum())
+        s = aucpr.ImageScores(average_precision_score(gt.ravel(), pred.ravel()) if pos else float("nan"),
+                              roc_auc_score(gt.ravel(), pred.ravel()) if pos else float("nan"), tp, pp, pos,
+                              int(gt.size - pos))
+        out.append((aucpr.ScoredArray(pred, s), gt, name))
+    return out
+
+
+def test_aucpr_entry_points_from_counts_match_oracle(tmp_path):
+    cfg = {"out_dir": str(tmp_path), "dataset_name": "IDRiD", "lesion_type": "EX"}
+    for seed in (0, 1):
+        items = helpers.synth_scoring_case(seed)
+        scored = _as_scored(items)
+        assert aucpr.get_auc(scored, cfg) == pytest.approx(scoring.get_auc(items), abs=1e-15)
+        assert aucpr.get_aucroc(scored, cfg) == pytest.approx(scoring.get_aucroc(items), abs=1e-15)
+        assert aucpr.plot_aucpr_curve(scored, "exp", cfg) == scoring.pr_curve(items)["thresholds"]
+        assert aucpr.plot_aucroc_curve(scored, "exp", cfg) == scoring.roc_curve(items)["threshold"]
+        tp, pp, ap, an = aucpr._pooled_counts(scored)
+        o = scoring.pr_curve(items)
+        assert np.array_equal(tp, o["tp"]) and np.array_equal(pp, o["pp"]) and ap == o["ap"]
+        assert aucpr.pr_curve_from_counts(tp, pp, ap)[3] == pytest.approx(o["aucpr"], abs=1e-15)
+    assert os.path.isdir(os.path.join(str(tmp_path), "IDRiD", "figures", "EX"))
+    with pytest.raises(ZeroDivisionError):
+        aucpr.get_auc(_as_scored([helpers.synth_scoring_case(0)[-1]]), cfg)      # no image has positives
+
+
+def test_scored_array_does_not_leak_scores_to_derived_arrays():
+    a = aucpr.ScoredArray(np.zeros((4, 4), np.float32), aucpr.ImageScores(1.0, 1.0, None, None, 1, 15))
+    assert a._eds_scores is not None
+    assert getattr(a > 0.5, "_eds_scores", None) is None and getattr(a[1:], "_eds_scores", None) is None
+
+
+def test_cached_predictions_run_inference_once():
+    calls = []
+
+    def produce():
+        calls.append(1)
+        for i in range(3):
+            yield i, i, str(i)
+
+    gen = CachedPredictions(produce)
+    assert list(gen()) == list(gen()) == list(gen) == [(i, i, str(i)) for i in range(3)]
+    assert len(calls) == 1
+
+    @multigen
+    def g(n):
+        for i in range(n):
+            yield i
+    r = g(3)
+    assert list(r) == list(r) == [0, 1, 2]
+
+
+def test_whole_image_geometry_idrid():
+    img = np.zeros((2848, 4288, 3), np.uint8)
+    import cv2
+    small = longest_max_size(img, 1024, cv2.INTER_LINEAR)
+    assert small.shape[:2] == (680, 1024)
+    padded = pad_to_square(small, 1024)
+    assert padded.shape[:2] == (1024, 1024)
+    marker = pad_to_square(np.ones((680, 1024), np.uint8), 1024)
+    assert marker[:172].sum() == 0 and marker[172:852].all() and marker[852:].sum() == 0
+
+
+# ------------------------------------------------------------------ world_size 2 (gloo)
+_WORKER = r"""
+import os, sys, json
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, 'tests'))
+import torch.distributed as dist
+import helpers, test_host_logic as T
+from eyediseasesegmentation_b200 import aucpr, _driver
+dist.init_process_group('gloo', init_method='tcp://127.0.0.1:{port}', rank=int(sys.argv[1]), world_size=2)
+items = T._as_scored(helpers.synth_scoring_case(3, n_images=5))
+mine = _driver.shard(items)
+cfg = dict(out_dir={out!r}, dataset_name='IDRiD', lesion_type='EX')
+res = dict(n=len(mine), auc=aucpr.get_auc(mine, cfg), roc=aucpr.get_aucroc(mine, cfg),
+           pr=list(aucpr.plot_aucpr_curve(mine, 'e', cfg)), rocthr=aucpr.plot_aucroc_curve(mine, 'e', cfg))
+print('RESULT' + json.dumps(res)); dist.destroy_process_group()
+"""
+
+
+def test_two_rank_sharding_reduces_to_single_process_answer(tmp_path):
+    import json
+    port = 29600 + os.getpid() % 300
+    code = _WORKER.format(root=ROOT, port=port, out=str(tmp_path))
+    procs = [subprocess.Popen([sys.executable, "-c", code, str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                              text=True) for r in range(2)]
+    outs = []
+    for p in procs:
+        o, e = p.communicate(timeout=240)
+        assert p.returncode == 0, e[-2000:]
+        outs.append(json.loads([l for l in o.splitlines() if l.startswith("RESULT")][0][6:]))
+    items = helpers.synth_scoring_case(3, n_images=5)
+    assert sorted(r["n"] for r in outs) == [2, 3]
+    for r in outs:                                   # every rank holds the global answer
+        assert r["auc"] == pytest.approx(scoring.get_auc(items), abs=1e-12)
+        assert r["roc"] == pytest.approx(scoring.get_aucroc(items), abs=1e-12)
+        assert tuple(r["pr"]) == scoring.pr_curve(items)["thresholds"]
+        assert r["rocthr"] == scoring.roc_curve(items)["threshold"]

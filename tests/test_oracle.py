@@ -1,0 +1,151 @@
+"""CPU tests (no GPU): the oracle against the reference's own outputs.
+
+  - committed golden fixtures (tests/golden/, produced by the reference code itself via
+    tests/golden/make_golden.py) pin oracle/nets.py, oracle/scoring.py and oracle/pipeline.py
+    everywhere, including the GPU box where /root/reference does not exist;
+  - when /root/reference is present (build container) the oracle is additionally compared
+    with the reference modules directly, bit for bit.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nets, pipeline, ref_loader, scoring
+import helpers
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+HAS_REF = ref_loader.available()
+
+
+def _golden_logits():
+    return np.load(os.path.join(GOLDEN, "net_logits.npz"))
+
+
+@pytest.mark.parametrize("case", helpers.NET_GOLDEN_CASES, ids=[c[0] for c in helpers.NET_GOLDEN_CASES])
+def test_oracle_nets_reproduce_reference_logits(case):
+    key, name, cfg, size, batch = case
+    model = helpers.build_product_model(name, cfg)
+    out = helpers.oracle_forward(name, cfg, model.state_dict(), helpers.golden_input(batch, size))
+    ref = torch.from_numpy(_golden_logits()[key])
+    assert out.shape == ref.shape
+    # same ops in the same order on the same CPU build: exact in the build container; allow a few
+    # ulp for a different host CPU's conv algorithm choice
+    assert (out - ref).abs().max().item() < 2e-5
+
+
+def test_state_dict_layout_matches_reference():
+    layout = json.load(open(os.path.join(GOLDEN, "state_dict_layout.json")))
+    for key, name, cfg, _, _ in helpers.NET_GOLDEN_CASES:
+        mine = {k: list(v.shape) for k, v in helpers.build_product_model(name, cfg).state_dict().items()}
+        assert mine == layout[key], key
+
+
+def test_shared_axial_block_aliases_storage():
+    sd = helpers.build_product_model("unetplusplusstar", helpers.star_cfg(8)).state_dict()
+    assert len(sd) == 869 and len({v.data_ptr() for v in sd.values()}) == 821
+    a, b = sd["encoder.layer4.1.in_conv1x1.0.weight"], sd["encoder.layer4.2.in_conv1x1.0.weight"]
+    assert a.data_ptr() == b.data_ptr()
+
+
+@pytest.mark.parametrize("bd,count", [(8, 60167435), (16, 60179723), (19, 60184331), (32, 60204299)])
+def test_parameter_counts(bd, count):
+    m = helpers.build_product_model("unetplusplusstar", helpers.star_cfg(bd))
+    assert sum(p.numel() for p in m.parameters()) == count          # SURVEY.md 8c known answers
+
+
+def test_parameter_counts_baselines():
+    counts = {"upp_se50_scse": 53658171, "upp_r34": 26080340, "unet_r34": 24436369}
+    for key, name, cfg, _, _ in helpers.NET_GOLDEN_CASES[1:]:
+        m = helpers.build_product_model(name, cfg)
+        assert sum(p.numel() for p in m.parameters()) == counts[key]
+
+
+def test_oracle_scoring_matches_reference_golden():
+    golden = json.load(open(os.path.join(GOLDEN, "scoring.json")))
+    for seed, ref in golden.items():
+        items = helpers.synth_scoring_case(int(seed))
+        assert scoring.get_auc(items) == pytest.approx(ref["get_auc"], abs=1e-12)
+        assert scoring.get_aucroc(items) == pytest.approx(ref["get_aucroc"], abs=1e-12)
+        assert list(scoring.pr_curve(items)["thresholds"]) == ref["plot_aucpr_curve"]
+        assert scoring.roc_curve(items)["threshold"] == ref["plot_aucroc_curve"]
+
+
+def test_make_grid_matches_reference_golden():
+    from eyediseasesegmentation_b200.util import make_grid
+    for case in json.load(open(os.path.join(GOLDEN, "make_grid.json"))):
+        want = np.array(case["grid"], dtype=np.int64)
+        for fn in (pipeline.make_grid, make_grid):
+            got = fn(tuple(case["shape"]), window=case["window"], min_overlap=case["min_overlap"])
+            assert got.dtype == np.int64 and np.array_equal(got, want), (fn.__module__, case["shape"])
+
+
+def test_registry_and_preprocessing_match_reference_golden():
+    from eyediseasesegmentation_b200 import archs
+    g = json.load(open(os.path.join(GOLDEN, "registry_preprocessing.json")))
+    assert archs.list_models() == list(dict.fromkeys(g["registry"]))
+    sample = np.arange(0, 256, 5, dtype=np.uint8).reshape(-1, 1, 1).repeat(3, axis=2)
+    for ds, ref in g["preprocessing"].items():
+        fn, mean, std = archs.get_preprocessing_fn(None if ds == "None" else ds, False)
+        assert mean == ref["mean"] and std == ref["std"]
+        assert np.array_equal(fn(sample).astype(np.float32).reshape(-1), np.array(ref["out"], dtype=np.float32))
+    with pytest.raises(KeyError):
+        archs.get_model("no_such_model", {}, training=False)
+    with pytest.raises(NotImplementedError):
+        archs.get_model("hrnet18", {}, training=False)
+
+
+def test_get_model_applies_inference_overrides():
+    from eyediseasesegmentation_b200 import archs
+    params = dict(encoder_name="resnet34", encoder_weights="imagenet", classes=1, deep_supervision=True)
+    archs.get_model("unetplusplus_deepsup", params, training=False)
+    assert params["encoder_weights"] is None and params["deep_supervision"] is False   # archs/__init__.py:111-119
+
+
+# ------------------------------------------------------------ direct, when the reference is here
+@pytest.mark.skipif(not HAS_REF, reason="/root/reference is only present in the build container")
+def test_oracle_nets_bit_exact_against_reference_modules():
+    ref = ref_loader.load()
+    x = helpers.golden_input(1, 256)
+    torch.manual_seed(3)
+    m = ref.unetplusplusstar.UnetPlusPlusStar(**helpers.star_cfg(8)).eval()
+    helpers.randomize_bn(m, 5)
+    with torch.no_grad():
+        assert torch.equal(m(x), nets.unetplusplusstar_forward(m.state_dict(), x, 8))
+        m2 = ref.deep_supunetplusplus.UnetPlusPlus(encoder_name="se_resnet50", encoder_weights=None, classes=1,
+                                                   decoder_attention_type="scse").eval()
+        helpers.randomize_bn(m2, 6)
+        assert torch.equal(m2(x), nets.unetplusplus_forward(m2.state_dict(), x))
+        m3 = ref.smp.Unet(encoder_name="resnet34", encoder_weights=None, classes=1).eval()
+        helpers.randomize_bn(m3, 7)
+        assert torch.equal(m3(x), nets.unet_forward(m3.state_dict(), x))
+
+
+@pytest.mark.skipif(not HAS_REF, reason="/root/reference is only present in the build container")
+def test_oracle_scoring_against_reference_aucpr(tmp_path):
+    ref = ref_loader.load()
+    cfg = {"out_dir": str(tmp_path), "dataset_name": "IDRiD", "lesion_type": "EX"}
+    items = helpers.synth_scoring_case(11, shape=(64, 80), n_images=4)
+    assert scoring.get_auc(items) == ref.aucpr.get_auc(items, cfg)
+    assert scoring.get_aucroc(items) == ref.aucpr.get_aucroc(items, cfg)
+    assert scoring.pr_curve(items)["thresholds"] == tuple(ref.aucpr.plot_aucpr_curve(items, "t", cfg))
+    assert scoring.roc_curve(items)["threshold"] == ref.aucpr.plot_aucroc_curve(items, "t", cfg)
+    with pytest.raises(ZeroDivisionError):
+        ref.aucpr.get_auc([(items[0][0], np.zeros_like(items[0][1]), "empty")], cfg)
+    with pytest.raises(ZeroDivisionError):
+        scoring.get_auc([(items[0][0], np.zeros_like(items[0][1]), "empty")])
+
+
+def test_histogram_key_keeps_ap_within_budget():
+    """DESIGN.md 'score key': AP on key-quantised scores vs AP on raw fp32 scores."""
+    from sklearn.metrics import average_precision_score
+    worst = 0.0
+    for seed in range(4):
+        for pred, gt, _ in helpers.synth_scoring_case(seed, shape=(128, 160), n_images=3)[:2]:
+            a = average_precision_score(gt.reshape(-1), pred.reshape(-1))
+            b = average_precision_score(gt.reshape(-1), scoring.score_key(pred).reshape(-1))
+            worst = max(worst, abs(a - b))
+    # 20 K-pixel images are the hard case (one tie is worth 1/n_pos); the budget is 1e-3
+    assert worst < 5e-4, worst
