@@ -46,6 +46,8 @@ PROTOTYPES = {
     "eds_se_scale_add_relu": [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
     "eds_scse_apply": [_vp, _vp, _vp, _f, _i, _i, _i, _vp, _i, _vp],
     "eds_upsample2x_concat": [_vp, _i, _i, _i, _i, _i, C.POINTER(_vp), C.POINTER(_i), _i, _vp, _i, _vp],
+    "eds_concat_stats": [_vp, _i, _i, _i, _i, _i, C.POINTER(_vp), C.POINTER(_i), _i, _vp, _f, _vp, _vp, _vp, _i, _vp],
+    "eds_scse_scale": [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
     "eds_axial_attention": [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp],
     "eds_mhca_gate": [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
     "eds_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],

@@ -179,11 +179,21 @@ class Engine:
             self.features[name] = t
 
     def _apply_scse(self, name, x):
+        """SCSE on an existing map (attention2): statistics pass + MLP + in-place scale."""
         if (name + ".sse") not in self.w:
             return x
-        gate = K.se_gate(K.channel_mean(x), *self.w[name + ".cse"])
         w_sse, b_sse = self.w[name + ".sse"]
-        return K.scse_apply(x, gate, w_sse, b_sse, out=x)
+        _, mean, logit = K.concat_stats(x, [], _lib.UP_NONE, w_sse, b_sse, write=False)
+        gate = K.se_gate(mean, *self.w[name + ".cse"])
+        return K.scse_scale(x, gate, logit, out=x)
+
+    def _concat_scse(self, name, x, skips):
+        """cat([up2x(x), *skips]) followed by SCSE (attention1): one pass builds the concat and its
+        statistics, the second scales it in place."""
+        w_sse, b_sse = self.w[name + ".sse"]
+        cat, mean, logit = K.concat_stats(x, list(skips), self.up_mode, w_sse, b_sse, write=True)
+        gate = K.se_gate(mean, *self.w[name + ".cse"])
+        return K.scse_scale(cat, gate, logit, out=cat)
 
     # ---------------------------------------------------------------- encoders
     def _se_bottleneck(self, p, x, stride):
@@ -266,9 +276,13 @@ class Engine:
         if (p + ".down_sample") in self.w:
             cat = K.upsample2x_concat(x, [self._mhca_skip(p, x, skips)], self.up_mode)
         else:
-            cat = K.upsample2x_concat(x, list(skips), self.up_mode)
-            if skips:
-                cat = self._apply_scse(p + ".attention1", cat)
+            if skips and (p + ".attention1.sse") in self.w and sum(t.shape[3] for t in skips) + x.shape[3] <= 1024:
+                cat = self._concat_scse(p + ".attention1", x, skips)
+            else:
+                cat = K.upsample2x_concat(x, list(skips), self.up_mode)
+                if skips and (p + ".attention1.sse") in self.w:   # > 1024 channels: one-pass form
+                    gate = K.se_gate(K.channel_mean(cat), *self.w[p + ".attention1.cse"])
+                    cat = K.scse_apply(cat, gate, *self.w[p + ".attention1.sse"], out=cat)
         y = self._cv(cat, p + ".conv1", pad=1, relu=True)
         y = self._cv(y, p + ".conv2", pad=1, relu=True)
         if (p + ".down_sample") not in self.w:

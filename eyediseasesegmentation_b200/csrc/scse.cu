@@ -1,0 +1,225 @@
+// Decoder concat + SCSE in two streaming passes.
+//
+// Reference: DecoderBlock.forward (src/main/archs/unetplusplusstar.py:127-161):
+//     x_up = interpolate(x, 2, bilinear); x = cat([x_up, skip]); x = attention1(x)   # smp SCSEModule
+// and attention2 on the block output.  SCSE needs two global quantities of its input before
+// it can scale a single element: the channel means (cSE) and, per pixel, w_sse . x (sSE).
+//
+//   pass 1  eds_concat_stats : reads the sources ONCE, writes the concatenated map (optional),
+//                              accumulates channel means and writes the per-pixel sSE logit;
+//   (tiny)  eds_se_gate      : cSE MLP on the means;
+//   pass 2  eds_scse_scale   : y = x * (cgate[n][c] + sigmoid(logit[n][p])) in place.
+//
+// One warp walks pixels; lane L owns channel vectors L, L+32, ... of every pixel it visits, so
+// its channel sums and sSE weights stay in registers and every global access is a contiguous
+// 512 B per warp instruction.
+#include "common.cuh"
+
+namespace eds {
+
+constexpr int kMaxVecPerLane = 4;   // up to 4 * 32 * 8 = 1024 channels
+constexpr int kStatsThreads = 256;
+
+struct StatSrc {
+    const void* ptr[6];   // [0] may be upsampled; the rest are same-resolution maps
+    int ch[6];
+    int n;
+};
+
+template <typename T>
+__device__ __forceinline__ void load_up2x(const T* __restrict__ base, int h, int w, int C0, int oy, int ox, int mode,
+                                          float (&v)[8]) {
+    if (mode == EDS_UP_NONE) {
+        Vec8<T>::ld(base + ((int64_t)oy * w + ox) * C0, v);
+        return;
+    }
+    const int iy = oy >> 1, ix = ox >> 1;
+    if (mode == EDS_UP_NEAREST) {
+        Vec8<T>::ld(base + ((int64_t)iy * w + ix) * C0, v);
+        return;
+    }
+    int y0, y1, x0, x1;
+    float ly, lx;
+    if (oy & 1) { y0 = iy; y1 = min(iy + 1, h - 1); ly = 0.25f; }
+    else if (iy == 0) { y0 = 0; y1 = min(1, h - 1); ly = 0.f; }
+    else { y0 = iy - 1; y1 = iy; ly = 0.75f; }
+    if (ox & 1) { x0 = ix; x1 = min(ix + 1, w - 1); lx = 0.25f; }
+    else if (ix == 0) { x0 = 0; x1 = min(1, w - 1); lx = 0.f; }
+    else { x0 = ix - 1; x1 = ix; lx = 0.75f; }
+    float a[8], b[8], c[8], d[8];
+    Vec8<T>::ld(base + ((int64_t)y0 * w + x0) * C0, a);
+    Vec8<T>::ld(base + ((int64_t)y0 * w + x1) * C0, b);
+    Vec8<T>::ld(base + ((int64_t)y1 * w + x0) * C0, c);
+    Vec8<T>::ld(base + ((int64_t)y1 * w + x1) * C0, d);
+    const float hy = 1.f - ly, hx = 1.f - lx;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = hy * (hx * a[i] + lx * b[i]) + ly * (hx * c[i] + lx * d[i]);
+}
+
+// grid = (chunks, N).  h, w: resolution of source 0; output resolution H x W = up*h x up*w.
+// `lpp` lanes (a power of two) cooperate on one pixel, so a warp covers 32/lpp pixels per step
+// (narrow maps: 16 channels -> 2 lanes per pixel, 16 pixels per warp step).
+template <typename T>
+__global__ void __launch_bounds__(kStatsThreads, 2)
+concat_stats_kernel(StatSrc src, int h, int w, int mode, int Ctot, int lpp, const float* __restrict__ w_sse,
+                    float b_sse, float inv_hw, T* __restrict__ y, float* __restrict__ chan_mean,
+                    float* __restrict__ sse_logit) {
+    extern __shared__ float s_sum[];   // [8 warps * 32/lpp pixel slots][Ctot]
+    const int up = mode == EDS_UP_NONE ? 1 : 2;
+    const int H = up * h, W = up * w;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int l = lane % lpp, sub = lane / lpp, ppw = 32 / lpp;
+    const int n = blockIdx.y;
+    const int C8 = Ctot / 8;
+
+    // per-lane channel ownership: vector r covers channels [(l + lpp r) * 8, +8)
+    const T* sp[kMaxVecPerLane];
+    int sc[kMaxVecPerLane];          // channel count of the owning source (pixel stride)
+    bool is_up[kMaxVecPerLane], live[kMaxVecPerLane];
+    float wv[kMaxVecPerLane][8], acc[kMaxVecPerLane][8];
+#pragma unroll
+    for (int r = 0; r < kMaxVecPerLane; ++r) {
+        const int v8 = l + lpp * r;
+        live[r] = v8 < C8 && (r == 0 || lpp == 32);
+        int c = v8 * 8, k = 0;
+        if (live[r]) {
+            while (k < src.n - 1 && c >= src.ch[k]) { c -= src.ch[k]; ++k; }
+        }
+        sc[r] = live[r] ? src.ch[k] : 0;
+        is_up[r] = live[r] && k == 0;
+        const int64_t img = is_up[r] ? (int64_t)h * w : (int64_t)H * W;
+        sp[r] = live[r] ? reinterpret_cast<const T*>(src.ptr[k]) + (int64_t)n * img * sc[r] + c : nullptr;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            wv[r][i] = (live[r] && w_sse) ? w_sse[v8 * 8 + i] : 0.f;
+            acc[r][i] = 0.f;
+        }
+    }
+
+    const int n_pix = H * W;
+    const int per = (n_pix + gridDim.x - 1) / gridDim.x;
+    const int p_begin = blockIdx.x * per;
+    const int p_end = min(n_pix, p_begin + per);
+    // the loop bound is warp-uniform (shuffles below); lanes past the end are masked by `ok`
+    for (int pb = p_begin + warp * ppw; pb < p_end; pb += (kStatsThreads / 32) * ppw) {
+        const int p = pb + sub;
+        const bool ok = p < p_end;
+        const int oy = p / W, ox = p - oy * W;
+        float dot = 0.f;
+#pragma unroll
+        for (int r = 0; r < kMaxVecPerLane; ++r) {
+            if (!live[r] || !ok) continue;
+            float v[8];
+            if (is_up[r]) load_up2x<T>(sp[r], h, w, sc[r], oy, ox, mode, v);
+            else Vec8<T>::ld(sp[r] + (int64_t)p * sc[r], v);
+            if (y) Vec8<T>::st(y + ((int64_t)n * n_pix + p) * Ctot + (l + lpp * r) * 8, v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                dot = fmaf(v[i], wv[r][i], dot);
+                acc[r][i] += v[i];
+            }
+        }
+        if (sse_logit) {
+            for (int o = lpp >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            if (l == 0 && ok) sse_logit[(int64_t)n * n_pix + p] = dot + b_sse;
+        }
+    }
+
+    // channel sums: (8 warps x ppw pixel slots) -> smem -> one atomicAdd per channel per CTA
+    const int rows = (kStatsThreads / 32) * ppw;
+#pragma unroll
+    for (int r = 0; r < kMaxVecPerLane; ++r)
+        if (live[r]) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s_sum[(warp * ppw + sub) * Ctot + (l + lpp * r) * 8 + i] = acc[r][i];
+        }
+    __syncthreads();
+    for (int c = threadIdx.x; c < Ctot; c += kStatsThreads) {
+        float t = 0.f;
+        for (int wi = 0; wi < rows; ++wi) t += s_sum[wi * Ctot + c];
+        atomicAdd(chan_mean + (int64_t)n * Ctot + c, t * inv_hw);
+    }
+}
+
+// y = x * (cgate[n][c] + sigmoid(logit[n][p])), in place allowed.  grid-stride over (pixel, vec8).
+template <typename T>
+__global__ void __launch_bounds__(256)
+scse_scale_kernel(const T* __restrict__ x, const float* __restrict__ cgate, const float* __restrict__ logit, int HW,
+                  int C8, int64_t total, T* __restrict__ y) {
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pix = idx / C8;               // n * HW + p
+        const int c8 = (int)(idx - pix * C8);
+        const int n = (int)(pix / HW);
+        const float s = sigmoidf_acc(__ldg(logit + pix));
+        const float4* g4 = reinterpret_cast<const float4*>(cgate + (int64_t)n * C8 * 8 + c8 * 8);
+        const float4 g0 = __ldg(g4), g1 = __ldg(g4 + 1);
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        float v[8];
+        Vec8<T>::ld(x + idx * 8, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = v[i] * g[i] + v[i] * s;
+        Vec8<T>::st(y + idx * 8, v);
+    }
+}
+
+}  // namespace eds
+
+using namespace eds;
+
+extern "C" int eds_concat_stats(const void* x0, int N, int h, int w, int C0, int mode,
+                                const void* const* skips_host, const int* skip_channels_host, int n_skips,
+                                const float* w_sse, float b_sse, void* y, float* chan_mean, float* sse_logit,
+                                int dtype, void* stream) {
+    EDS_REQUIRE(x0 && chan_mean, "concat_stats: null pointer");
+    EDS_REQUIRE(n_skips >= 0 && n_skips <= 5, "concat_stats: n_skips=%d not in 0..5", n_skips);
+    EDS_REQUIRE(mode == EDS_UP_NEAREST || mode == EDS_UP_BILINEAR || mode == EDS_UP_NONE, "concat_stats: bad mode %d",
+                mode);
+    EDS_REQUIRE(N > 0 && N <= 65535 && h > 0 && w > 0 && C0 > 0 && C0 % 8 == 0, "concat_stats: bad shape");
+    EDS_REQUIRE(!sse_logit || w_sse, "concat_stats: sse_logit requested without w_sse");
+    StatSrc src;
+    src.n = n_skips + 1;
+    src.ptr[0] = x0;
+    src.ch[0] = C0;
+    int Ctot = C0;
+    for (int k = 0; k < 5; ++k) {
+        src.ptr[k + 1] = k < n_skips ? skips_host[k] : nullptr;
+        src.ch[k + 1] = k < n_skips ? skip_channels_host[k] : 0;
+        if (k < n_skips) {
+            EDS_REQUIRE(src.ptr[k + 1] && src.ch[k + 1] > 0 && src.ch[k + 1] % 8 == 0, "concat_stats: bad skip %d", k);
+            Ctot += src.ch[k + 1];
+        }
+    }
+    EDS_REQUIRE(Ctot <= kMaxVecPerLane * 32 * 8, "concat_stats: %d channels > %d", Ctot, kMaxVecPerLane * 32 * 8);
+    const int up = mode == EDS_UP_NONE ? 1 : 2;
+    const int n_pix = up * h * up * w;
+    cudaError_t e = cudaMemsetAsync(chan_mean, 0, sizeof(float) * (size_t)N * Ctot, as_stream(stream));
+    if (e != cudaSuccess) {
+        set_error("concat_stats: memset failed: %s", cudaGetErrorString(e));
+        return EDS_ERR_CUDA;
+    }
+    int chunks = ceil_div(148 * 8, N);
+    const int max_chunks = ceil_div(n_pix, 256);  // at least 32 pixels per warp
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    int lpp = 32;                                  // lanes per pixel: pow2 >= Ctot/8, capped at a warp
+    while (lpp > 1 && lpp / 2 >= Ctot / 8) lpp /= 2;
+    const size_t smem = sizeof(float) * (kStatsThreads / 32) * (32 / lpp) * Ctot;
+    dim3 grid(chunks, N);
+    EDS_DISPATCH_DTYPE(dtype, T, (concat_stats_kernel<T><<<grid, kStatsThreads, smem, as_stream(stream)>>>(
+                                     src, h, w, mode, Ctot, lpp, w_sse, b_sse, 1.0f / (float)n_pix, (T*)y, chan_mean,
+                                     sse_logit)));
+    return check_launch("concat_stats_kernel");
+}
+
+extern "C" int eds_scse_scale(const void* x, const float* cgate, const float* sse_logit, int N, int HW, int C,
+                              void* y, int dtype, void* stream) {
+    EDS_REQUIRE(x && cgate && sse_logit && y, "scse_scale: null pointer");
+    EDS_REQUIRE(C % 8 == 0 && C > 0 && N > 0 && HW > 0, "scse_scale: bad shape");
+    const int64_t total = (int64_t)N * HW * (C / 8);
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    EDS_DISPATCH_DTYPE(dtype, T, (scse_scale_kernel<T><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+                                     (const T*)x, cgate, sse_logit, HW, C / 8, total, (T*)y)));
+    return check_launch("scse_scale_kernel");
+}

@@ -54,7 +54,7 @@ tta_merge_kernel(const float* __restrict__ logits, int V, int B, int S, ViewMaps
 }
 
 // One thread per output pixel; coordinate arithmetic follows cv2's resizeLinear for
-// CV_32F (double scale, float weights, horizontal pass then vertical pass).
+// CV_32F (double coordinates, float weights, horizontal pass then vertical pass).
 __global__ void resize_paste_kernel(const float* __restrict__ src, int src_w, int crop_y, int crop_x, int crop_h,
                                     int crop_w, float* __restrict__ dst, int dst_h, int dst_w, int dst_y,
                                     int dst_x, int out_h, int out_w, double scale_y, double scale_x) {
@@ -63,14 +63,16 @@ __global__ void resize_paste_kernel(const float* __restrict__ src, int src_w, in
     if (ox >= out_w || oy >= out_h) return;
     const int gy = dst_y + oy, gx = dst_x + ox;
     if (gy < 0 || gy >= dst_h || gx < 0 || gx >= dst_w) return;
-    float fy = (float)((oy + 0.5) * scale_y - 0.5);
-    int sy = (int)floorf(fy);
-    fy -= (float)sy;
+    // source coordinate in double, fraction rounded to float once (matches cv2 4.x to 2e-7;
+    // rounding the coordinate itself to float would cost 5e-5 at x ~ 1000)
+    const double dy = (oy + 0.5) * scale_y - 0.5;
+    int sy = (int)floor(dy);
+    float fy = (float)(dy - (double)sy);
     if (sy < 0) { sy = 0; fy = 0.f; }
     if (sy >= crop_h - 1) { sy = crop_h - 1; fy = 0.f; }
-    float fx = (float)((ox + 0.5) * scale_x - 0.5);
-    int sx = (int)floorf(fx);
-    fx -= (float)sx;
+    const double dx = (ox + 0.5) * scale_x - 0.5;
+    int sx = (int)floor(dx);
+    float fx = (float)(dx - (double)sx);
     if (sx < 0) { sx = 0; fx = 0.f; }
     if (sx >= crop_w - 1) { sx = crop_w - 1; fx = 0.f; }
     const int sy1 = sy + 1 < crop_h ? sy + 1 : crop_h - 1;

@@ -11,7 +11,18 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import EDS_BF16, EDS_F32, check
+from ._lib import EDS_BF16, EDS_F32
+from ._lib import check as _check
+
+#: number of kernel launches issued through this module (every wrapper below is one launch)
+LAUNCHES = [0]
+#: when set to a list, conv2d(impl="tc") appends (algorithmic_flops, start_event, end_event)
+CONV_TRACE = None
+
+
+def check(rc: int) -> None:
+    LAUNCHES[0] += 1
+    _check(rc)
 
 
 def _stream() -> int:
@@ -143,8 +154,15 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], strid
     if impl == "tc":
         if x.dtype != torch.bfloat16:
             raise TypeError("the tcgen05 kernel takes bf16 activations")
+        trace = CONV_TRACE
+        if trace is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         check(_lib.lib().eds_conv2d_igemm_bf16(_p(x), N, H, W_, Cin, _p(w), _p(bias), Cout, R, S, stride, pad,
                                                int(relu), _p(residual), _p(out), _stream()))
+        if trace is not None:
+            ev1.record()
+            trace.append((2.0 * N * Ho * Wo * Cout * R * S * Cin, ev0, ev1))
     elif impl == "simt":
         check(_lib.lib().eds_conv2d_simt(_p(x), N, H, W_, Cin, _p(w), _p(bias), Cout, R, S, stride, pad, int(relu),
                                          _p(residual), _p(out), _dt(x), _stream()))
@@ -251,6 +269,36 @@ def upsample2x_concat(x0: torch.Tensor, skips: Sequence[torch.Tensor], mode: int
     ptrs = (C.c_void_p * max(n, 1))(*[s.data_ptr() for s in skips])
     chans = (C.c_int * max(n, 1))(*[s.shape[3] for s in skips])
     check(_lib.lib().eds_upsample2x_concat(_p(x0), N, h, w, C0, mode, ptrs, chans, n, _p(out), _dt(x0), _stream()))
+    return out
+
+
+def concat_stats(x0: torch.Tensor, skips: Sequence[torch.Tensor], mode: int, w_sse: Optional[torch.Tensor],
+                 b_sse: float = 0.0, write: bool = True):
+    """Pass 1 of the two-pass SCSE: -> (concat or None, chan_mean [N,Ctot] f32, sse_logit [N,H,W] f32 or None)."""
+    _chk(x0, w_sse, *skips)
+    N, h, w, C0 = x0.shape
+    ctot = C0 + sum(s.shape[3] for s in skips)
+    up = 1 if mode == _lib.UP_NONE else 2
+    for s in skips:
+        assert s.shape[:3] == (N, up * h, up * w) and s.dtype == x0.dtype
+    dev = x0.device
+    y = torch.empty((N, up * h, up * w, ctot), dtype=x0.dtype, device=dev) if write else None
+    mean = torch.empty((N, ctot), dtype=torch.float32, device=dev)
+    logit = torch.empty((N, up * h, up * w), dtype=torch.float32, device=dev) if w_sse is not None else None
+    n = len(skips)
+    ptrs = (C.c_void_p * max(n, 1))(*[s.data_ptr() for s in skips])
+    chans = (C.c_int * max(n, 1))(*[s.shape[3] for s in skips])
+    check(_lib.lib().eds_concat_stats(_p(x0), N, h, w, C0, mode, ptrs, chans, n, _p(w_sse), float(b_sse), _p(y),
+                                      _p(mean), _p(logit), _dt(x0), _stream()))
+    return y, mean, logit
+
+
+def scse_scale(x: torch.Tensor, cgate: torch.Tensor, logit: torch.Tensor, out: Optional[torch.Tensor] = None):
+    _chk(x, cgate, logit, out)
+    N, H, W_, Cc = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.lib().eds_scse_scale(_p(x), _p(cgate), _p(logit), N, H * W_, Cc, _p(out), _dt(x), _stream()))
     return out
 
 

@@ -178,6 +178,20 @@ EDS_API int eds_upsample2x_concat(const void* x0, int N, int h, int w, int C0, i
                           const void* const* skips_host, const int* skip_channels_host,
                           int n_skips, void* y, int dtype, void* stream);
 
+/* SCSE in two streaming passes (the product path; eds_scse_apply is the one-pass form for an
+ * already materialised tensor).  Pass 1: concatenate like eds_upsample2x_concat (y may be NULL
+ * = statistics only) and, from the same read, produce chan_mean [N][Ctot] fp32 (global average
+ * pool for cSE; zeroed inside) and sse_logit [N][H][W] fp32 = w_sse . x + b_sse (may be NULL).
+ * Ctot <= 1024. */
+EDS_API int eds_concat_stats(const void* x0, int N, int h, int w, int C0, int mode,
+                             const void* const* skips_host, const int* skip_channels_host, int n_skips,
+                             const float* w_sse, float b_sse, void* y, float* chan_mean, float* sse_logit,
+                             int dtype, void* stream);
+
+/* Pass 2: y = x * (cgate[n][c] + sigmoid(sse_logit[n][p])); y may alias x. */
+EDS_API int eds_scse_scale(const void* x, const float* cgate, const float* sse_logit, int N, int HW, int C,
+                           void* y, int dtype, void* stream);
+
 /* Axial attention core (axial_attention_v2.py:100-135,178-213) for one axis.
  * qk: per pixel `heads` groups of [q(dqk) | k(dqk) | (v(dv) if v == NULL)] channels,
  * pixel stride qk_cstride elements; v: optional separate tensor with `heads` groups

@@ -403,3 +403,38 @@ def test_pr_hist_flat_regions_and_accumulate():
     tp, pp = _np_counts(prob[0], gt[0])
     assert np.array_equal(counts[0, :, 0], 2 * tp) and np.array_equal(counts[0, :, 1], 2 * pp)
     assert totals[0, 0] == 2000
+
+
+@pytest.mark.parametrize("C0,skip_ch,mode", [(32, [16, 64], 1), (128, [256, 512], 1), (64, [64], 0), (16, [], 2),
+                                             (32, [], 2), (320, [], 2), (256, [256, 256, 256], 1)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_concat_stats_and_scse_scale(C0, skip_ch, mode, dtype):
+    """Two-pass SCSE == smp SCSEModule on the concatenated map."""
+    N, h, w = 2, 6, 5
+    up = 1 if mode == 2 else 2
+    x0 = rnd(N, h, w, C0, seed=60).to(dtype)
+    skips = [rnd(N, up * h, up * w, c, seed=61 + i).to(dtype) for i, c in enumerate(skip_ch)]
+    Ct = C0 + sum(skip_ch)
+    w_sse, b_sse = rnd(Ct, seed=70, scale=0.1), -0.2
+    cat, mean, logit = K.concat_stats(x0, skips, mode, w_sse, b_sse, write=True)
+    x0f = nchw(x0.float())
+    if mode == 1:
+        x0f = F.interpolate(x0f, scale_factor=2, mode="bilinear", align_corners=False)
+    elif mode == 0:
+        x0f = F.interpolate(x0f, scale_factor=2, mode="nearest")
+    ref_cat = torch.cat([nhwc(x0f)] + [s.float() for s in skips], dim=-1)
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    assert cat.shape == ref_cat.shape and (cat.float() - ref_cat).abs().max().item() < tol
+    assert (mean - ref_cat.mean(dim=(1, 2))).abs().max().item() < 1e-4
+    assert (logit - ((ref_cat * w_sse).sum(-1) + b_sse)).abs().max().item() < 1e-3
+    # statistics-only mode on the materialised map gives the same numbers
+    _, mean2, logit2 = K.concat_stats(cat, [], 2, w_sse, b_sse, write=False)
+    assert (mean2 - cat.float().mean(dim=(1, 2))).abs().max().item() < 1e-4
+    assert (logit2 - ((cat.float() * w_sse).sum(-1) + b_sse)).abs().max().item() < 1e-3
+    cg = torch.rand(N, Ct, device=DEV)
+    y = K.scse_scale(cat, cg, logit2)
+    cf = cat.float()
+    ref = cf * cg.view(N, 1, 1, Ct) + cf * torch.sigmoid(logit2).unsqueeze(-1)
+    assert (y.float() - ref).abs().max().item() < (2e-5 if dtype == torch.float32 else 4e-2)
+    y2 = K.scse_scale(cat, cg, logit2, out=cat)   # in place
+    assert torch.equal(y2, y)
