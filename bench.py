@@ -245,8 +245,8 @@ def conv_roofline(model, tfm, image, mean, std, tiles, peak, peak_src):
     drv.tiled_probability_map(model, tfm, image, S, mean, std, tiles_per_batch=tiles)
     torch.cuda.synchronize()
     trace, K.CONV_TRACE = K.CONV_TRACE, None
-    flops = sum(f for f, _, _ in trace)
-    ms = sum(a.elapsed_time(b) for _, a, b in trace)
+    flops = sum(t[0] for t in trace)
+    ms = sum(t[1].elapsed_time(t[2]) for t in trace)
     achieved = flops / (ms / 1e3) / 1e12
     return {"kernel": "conv_igemm_kernel (tcgen05 implicit GEMM)", "bound": "tensor", "achieved": achieved,
             "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,

@@ -276,13 +276,10 @@ class Engine:
         if (p + ".down_sample") in self.w:
             cat = K.upsample2x_concat(x, [self._mhca_skip(p, x, skips)], self.up_mode)
         else:
-            if skips and (p + ".attention1.sse") in self.w and sum(t.shape[3] for t in skips) + x.shape[3] <= 1024:
+            if skips and (p + ".attention1.sse") in self.w:
                 cat = self._concat_scse(p + ".attention1", x, skips)
             else:
                 cat = K.upsample2x_concat(x, list(skips), self.up_mode)
-                if skips and (p + ".attention1.sse") in self.w:   # > 1024 channels: one-pass form
-                    gate = K.se_gate(K.channel_mean(cat), *self.w[p + ".attention1.cse"])
-                    cat = K.scse_apply(cat, gate, *self.w[p + ".attention1.sse"], out=cat)
         y = self._cv(cat, p + ".conv1", pad=1, relu=True)
         y = self._cv(y, p + ".conv2", pad=1, relu=True)
         if (p + ".down_sample") not in self.w:

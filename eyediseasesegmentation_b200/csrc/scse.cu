@@ -6,19 +6,21 @@
 // it can scale a single element: the channel means (cSE) and, per pixel, w_sse . x (sSE).
 //
 //   pass 1  eds_concat_stats : reads the sources ONCE, writes the concatenated map (optional),
-//                              accumulates channel means and writes the per-pixel sSE logit;
+//                              accumulates channel means and the per-pixel sSE logit;
 //   (tiny)  eds_se_gate      : cSE MLP on the means;
 //   pass 2  eds_scse_scale   : y = x * (cgate[n][c] + sigmoid(logit[n][p])) in place.
 //
-// One warp walks pixels; lane L owns channel vectors L, L+32, ... of every pixel it visits, so
-// its channel sums and sSE weights stay in registers and every global access is a contiguous
-// 512 B per warp instruction.
+// Pass 1 layout: grid = (pixel chunks, N, 256-channel chunks).  A warp walks pixels; lane L owns
+// ONE 8-channel vector (chunk*32 + L) of every pixel it visits, so its channel sums and sSE
+// weights live in 16 registers, every global access is a contiguous 512 B per warp instruction,
+// and the low register count keeps ~40 warps per SM in flight (the first version held 4
+// vectors per lane, ran 16 warps/SM and reached 31 % of HBM: profiles/r01_ncu_summary.md).
 #include "common.cuh"
 
 namespace eds {
 
-constexpr int kMaxVecPerLane = 4;   // up to 4 * 32 * 8 = 1024 channels
 constexpr int kStatsThreads = 256;
+constexpr int kStatsUnroll = 2;     // pixels in flight per lane group
 
 struct StatSrc {
     const void* ptr[6];   // [0] may be upsampled; the rest are same-resolution maps
@@ -56,88 +58,100 @@ __device__ __forceinline__ void load_up2x(const T* __restrict__ base, int h, int
     for (int i = 0; i < 8; ++i) v[i] = hy * (hx * a[i] + lx * b[i]) + ly * (hx * c[i] + lx * d[i]);
 }
 
-// grid = (chunks, N).  h, w: resolution of source 0; output resolution H x W = up*h x up*w.
-// `lpp` lanes (a power of two) cooperate on one pixel, so a warp covers 32/lpp pixels per step
-// (narrow maps: 16 channels -> 2 lanes per pixel, 16 pixels per warp step).
+// h, w: resolution of source 0; output resolution H x W = up*h x up*w.  `lpp` lanes (a power of
+// two) cooperate on one pixel, so a warp covers 32/lpp pixels per step (16 channels -> 2 lanes
+// per pixel, 16 pixels per warp step).  With more than 256 channels gridDim.z > 1 and the sSE
+// logit is accumulated with one atomicAdd per (pixel, channel chunk) into a zeroed buffer.
 template <typename T>
-__global__ void __launch_bounds__(kStatsThreads, 2)
+__global__ void __launch_bounds__(kStatsThreads)
 concat_stats_kernel(StatSrc src, int h, int w, int mode, int Ctot, int lpp, const float* __restrict__ w_sse,
                     float b_sse, float inv_hw, T* __restrict__ y, float* __restrict__ chan_mean,
                     float* __restrict__ sse_logit) {
-    extern __shared__ float s_sum[];   // [8 warps * 32/lpp pixel slots][Ctot]
+    __shared__ float s_sum[kStatsThreads / 32][32][8 + 1];
     const int up = mode == EDS_UP_NONE ? 1 : 2;
     const int H = up * h, W = up * w;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int l = lane % lpp, sub = lane / lpp, ppw = 32 / lpp;
     const int n = blockIdx.y;
-    const int C8 = Ctot / 8;
+    const int v8 = blockIdx.z * 32 + l;              // this lane's 8-channel vector
+    const bool live = v8 < Ctot / 8;
+    const bool multi = gridDim.z > 1;
 
-    // per-lane channel ownership: vector r covers channels [(l + lpp r) * 8, +8)
-    const T* sp[kMaxVecPerLane];
-    int sc[kMaxVecPerLane];          // channel count of the owning source (pixel stride)
-    bool is_up[kMaxVecPerLane], live[kMaxVecPerLane];
-    float wv[kMaxVecPerLane][8], acc[kMaxVecPerLane][8];
-#pragma unroll
-    for (int r = 0; r < kMaxVecPerLane; ++r) {
-        const int v8 = l + lpp * r;
-        live[r] = v8 < C8 && (r == 0 || lpp == 32);
-        int c = v8 * 8, k = 0;
-        if (live[r]) {
-            while (k < src.n - 1 && c >= src.ch[k]) { c -= src.ch[k]; ++k; }
-        }
-        sc[r] = live[r] ? src.ch[k] : 0;
-        is_up[r] = live[r] && k == 0;
-        const int64_t img = is_up[r] ? (int64_t)h * w : (int64_t)H * W;
-        sp[r] = live[r] ? reinterpret_cast<const T*>(src.ptr[k]) + (int64_t)n * img * sc[r] + c : nullptr;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            wv[r][i] = (live[r] && w_sse) ? w_sse[v8 * 8 + i] : 0.f;
-            acc[r][i] = 0.f;
-        }
-    }
-
+    int c = v8 * 8, k = 0;
+    if (live)
+        while (k < src.n - 1 && c >= src.ch[k]) { c -= src.ch[k]; ++k; }
+    const int sc = live ? src.ch[k] : 0;             // pixel stride of the owning source
+    const bool is_up = live && k == 0;
     const int n_pix = H * W;
+    const T* sp = live ? reinterpret_cast<const T*>(src.ptr[k]) + (int64_t)n * (is_up ? h * w : n_pix) * sc + c
+                       : nullptr;
+    float wv[8], acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        wv[i] = (live && w_sse) ? w_sse[v8 * 8 + i] : 0.f;
+        acc[i] = 0.f;
+    }
+    const float bias = (blockIdx.z == 0) ? b_sse : 0.f;
+
     const int per = (n_pix + gridDim.x - 1) / gridDim.x;
     const int p_begin = blockIdx.x * per;
     const int p_end = min(n_pix, p_begin + per);
+    const int step = (kStatsThreads / 32) * ppw * kStatsUnroll;
     // the loop bound is warp-uniform (shuffles below); lanes past the end are masked by `ok`
-    for (int pb = p_begin + warp * ppw; pb < p_end; pb += (kStatsThreads / 32) * ppw) {
-        const int p = pb + sub;
-        const bool ok = p < p_end;
-        const int oy = p / W, ox = p - oy * W;
-        float dot = 0.f;
+    for (int pb = p_begin + warp * ppw * kStatsUnroll; pb < p_end; pb += step) {
+        float v[kStatsUnroll][8];
+        int p[kStatsUnroll];
+        bool ok[kStatsUnroll];
 #pragma unroll
-        for (int r = 0; r < kMaxVecPerLane; ++r) {
-            if (!live[r] || !ok) continue;
-            float v[8];
-            if (is_up[r]) load_up2x<T>(sp[r], h, w, sc[r], oy, ox, mode, v);
-            else Vec8<T>::ld(sp[r] + (int64_t)p * sc[r], v);
-            if (y) Vec8<T>::st(y + ((int64_t)n * n_pix + p) * Ctot + (l + lpp * r) * 8, v);
+        for (int u = 0; u < kStatsUnroll; ++u) {        // all loads first: 2 pixels in flight
+            p[u] = pb + u * ppw + sub;
+            ok[u] = live && p[u] < p_end;
+            if (ok[u]) {
+                if (is_up) {
+                    const int oy = p[u] / W, ox = p[u] - oy * W;
+                    load_up2x<T>(sp, h, w, sc, oy, ox, mode, v[u]);
+                } else {
+                    Vec8<T>::ld(sp + (int64_t)p[u] * sc, v[u]);
+                }
+            } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                dot = fmaf(v[i], wv[r][i], dot);
-                acc[r][i] += v[i];
+                for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
             }
         }
-        if (sse_logit) {
-            for (int o = lpp >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-            if (l == 0 && ok) sse_logit[(int64_t)n * n_pix + p] = dot + b_sse;
+#pragma unroll
+        for (int u = 0; u < kStatsUnroll; ++u) {
+            if (ok[u] && y) Vec8<T>::st(y + ((int64_t)n * n_pix + p[u]) * Ctot + v8 * 8, v[u]);
+            float dot = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                dot = fmaf(v[u][i], wv[i], dot);
+                acc[i] += v[u][i];
+            }
+            if (sse_logit) {
+                for (int o = lpp >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+                if (l == 0 && p[u] < p_end) {
+                    float* dst = sse_logit + (int64_t)n * n_pix + p[u];
+                    if (multi) atomicAdd(dst, dot + bias);
+                    else *dst = dot + bias;
+                }
+            }
         }
     }
 
-    // channel sums: (8 warps x ppw pixel slots) -> smem -> one atomicAdd per channel per CTA
-    const int rows = (kStatsThreads / 32) * ppw;
+    // channel sums: 8 warps x 32 lanes -> smem -> one atomicAdd per channel per CTA
 #pragma unroll
-    for (int r = 0; r < kMaxVecPerLane; ++r)
-        if (live[r]) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) s_sum[(warp * ppw + sub) * Ctot + (l + lpp * r) * 8 + i] = acc[r][i];
-        }
+    for (int i = 0; i < 8; ++i) s_sum[warp][lane][i] = acc[i];
     __syncthreads();
-    for (int c = threadIdx.x; c < Ctot; c += kStatsThreads) {
-        float t = 0.f;
-        for (int wi = 0; wi < rows; ++wi) t += s_sum[wi * Ctot + c];
-        atomicAdd(chan_mean + (int64_t)n * Ctot + c, t * inv_hw);
+    // thread t < lpp*8 owns channel (t/8 -> vector, t%8 -> element) of this chunk
+    if (threadIdx.x < lpp * 8) {
+        const int vl = threadIdx.x >> 3, e = threadIdx.x & 7;
+        const int ch = (blockIdx.z * 32 + vl) * 8 + e;
+        if (ch < Ctot) {
+            float t = 0.f;
+            for (int wi = 0; wi < kStatsThreads / 32; ++wi)
+                for (int s = 0; s < ppw; ++s) t += s_sum[wi][s * lpp + vl][e];
+            atomicAdd(chan_mean + (int64_t)n * Ctot + ch, t * inv_hw);
+        }
     }
 }
 
@@ -190,23 +204,26 @@ extern "C" int eds_concat_stats(const void* x0, int N, int h, int w, int C0, int
             Ctot += src.ch[k + 1];
         }
     }
-    EDS_REQUIRE(Ctot <= kMaxVecPerLane * 32 * 8, "concat_stats: %d channels > %d", Ctot, kMaxVecPerLane * 32 * 8);
     const int up = mode == EDS_UP_NONE ? 1 : 2;
     const int n_pix = up * h * up * w;
+    const int c8 = Ctot / 8;
+    int lpp = 32;                                  // lanes per pixel: pow2 >= Ctot/8, capped at a warp
+    while (lpp > 1 && lpp / 2 >= c8) lpp /= 2;
+    const int zchunks = ceil_div(c8, 32);
+    EDS_REQUIRE(zchunks <= 65535, "concat_stats: too many channels");
     cudaError_t e = cudaMemsetAsync(chan_mean, 0, sizeof(float) * (size_t)N * Ctot, as_stream(stream));
+    if (e == cudaSuccess && sse_logit && zchunks > 1)
+        e = cudaMemsetAsync(sse_logit, 0, sizeof(float) * (size_t)N * n_pix, as_stream(stream));
     if (e != cudaSuccess) {
         set_error("concat_stats: memset failed: %s", cudaGetErrorString(e));
         return EDS_ERR_CUDA;
     }
-    int chunks = ceil_div(148 * 8, N);
-    const int max_chunks = ceil_div(n_pix, 256);  // at least 32 pixels per warp
+    int chunks = ceil_div(148 * 16, N * zchunks);
+    const int max_chunks = ceil_div(n_pix, 8 * (32 / lpp) * kStatsUnroll * 4);   // >= 4 steps per warp
     if (chunks > max_chunks) chunks = max_chunks;
     if (chunks < 1) chunks = 1;
-    int lpp = 32;                                  // lanes per pixel: pow2 >= Ctot/8, capped at a warp
-    while (lpp > 1 && lpp / 2 >= Ctot / 8) lpp /= 2;
-    const size_t smem = sizeof(float) * (kStatsThreads / 32) * (32 / lpp) * Ctot;
-    dim3 grid(chunks, N);
-    EDS_DISPATCH_DTYPE(dtype, T, (concat_stats_kernel<T><<<grid, kStatsThreads, smem, as_stream(stream)>>>(
+    dim3 grid(chunks, N, zchunks);
+    EDS_DISPATCH_DTYPE(dtype, T, (concat_stats_kernel<T><<<grid, kStatsThreads, 0, as_stream(stream)>>>(
                                      src, h, w, mode, Ctot, lpp, w_sse, b_sse, 1.0f / (float)n_pix, (T*)y, chan_mean,
                                      sse_logit)));
     return check_launch("concat_stats_kernel");

@@ -162,7 +162,7 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], strid
                                                int(relu), _p(residual), _p(out), _stream()))
         if trace is not None:
             ev1.record()
-            trace.append((2.0 * N * Ho * Wo * Cout * R * S * Cin, ev0, ev1))
+            trace.append((2.0 * N * Ho * Wo * Cout * R * S * Cin, ev0, ev1, (N, H, W_, Cin, Cout, R, stride)))
     elif impl == "simt":
         check(_lib.lib().eds_conv2d_simt(_p(x), N, H, W_, Cin, _p(w), _p(bias), Cout, R, S, stride, pad, int(relu),
                                          _p(residual), _p(out), _dt(x), _stream()))

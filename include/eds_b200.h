@@ -182,7 +182,7 @@ EDS_API int eds_upsample2x_concat(const void* x0, int N, int h, int w, int C0, i
  * already materialised tensor).  Pass 1: concatenate like eds_upsample2x_concat (y may be NULL
  * = statistics only) and, from the same read, produce chan_mean [N][Ctot] fp32 (global average
  * pool for cSE; zeroed inside) and sse_logit [N][H][W] fp32 = w_sse . x + b_sse (may be NULL).
- * Ctot <= 1024. */
+ * Channels beyond 256 are split over gridDim.z (the logit is then accumulated atomically). */
 EDS_API int eds_concat_stats(const void* x0, int N, int h, int w, int C0, int mode,
                              const void* const* skips_host, const int* skip_channels_host, int n_skips,
                              const float* w_sse, float b_sse, void* y, float* chan_mean, float* sse_logit,

@@ -39,6 +39,16 @@ print(f"star 1024^2 d4 (8 views) eager: {ms:.2f} ms -> {8*1872.19/ms:.1f} TFLOP/
 ms1 = timeit(lambda: model(x), n=3, warm=1)
 print(f"star 1024^2 single view eager: {ms1:.2f} ms", flush=True)
 print("max mem GB", torch.cuda.max_memory_allocated()/2**30)
+K.CONV_TRACE = []
+model.forward_tta(x, t, True); torch.cuda.synchronize()
+tr, K.CONV_TRACE = K.CONV_TRACE, None
+agg = {}
+for f, a, b, shp in tr:
+    e = agg.setdefault(shp, [0, 0.0, 0.0]); e[0] += 1; e[1] += a.elapsed_time(b); e[2] += f
+tot = sum(v[1] for v in agg.values())
+print(f"conv launches {len(tr)} total {tot:.2f} ms (event-bracketed, includes launch gaps)")
+for shp, (n, ms, f) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    print(f"  N{shp[0]} {shp[1]}x{shp[2]} C{shp[3]}->{shp[4]} k{shp[5]} s{shp[6]}: x{n} {ms:.3f} ms {f/ms/1e9:.0f} TFLOP/s")
 # per-kernel profile through torch profiler
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
