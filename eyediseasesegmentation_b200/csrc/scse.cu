@@ -155,6 +155,130 @@ concat_stats_kernel(StatSrc src, int h, int w, int mode, int Ctot, int lpp, cons
     }
 }
 
+// Bilinear x2 fast path (>= 256 channels, so a warp = one pixel's 256-channel chunk).  A warp walks
+// one OUTPUT ROW at a time, two output pixels (2i, 2i+1) per step.  For the upsampled source the
+// vertical blend of each low-resolution column is computed once and slides through registers
+// (prev, cur, next), so a step costs 2 vector loads instead of 8 and no index division:
+//     out[2i]   = 0.25 * col(i-1) + 0.75 * col(i)        col(j) = (1-ly) * row_y0[j] + ly * row_y1[j]
+//     out[2i+1] = 0.75 * col(i)   + 0.25 * col(i+1)      (columns clamped at the borders)
+// which is F.interpolate(scale_factor=2, mode="bilinear", align_corners=False) with the two lerps
+// in the other order (fp32 rounding differs by ~1 ulp).  Lanes that own a same-resolution source
+// load pixels 2i, 2i+1 directly; both kinds run the same instruction stream (selects, no branches).
+// grid = (row groups, N, 256-channel chunks).
+template <typename T>
+__global__ void __launch_bounds__(kStatsThreads)
+concat_stats_bilinear_kernel(StatSrc src, int h, int w, int Ctot, const float* __restrict__ w_sse, float b_sse,
+                             float inv_hw, T* __restrict__ y, float* __restrict__ chan_mean,
+                             float* __restrict__ sse_logit) {
+    __shared__ float s_sum[kStatsThreads / 32][32][8 + 1];
+    const int H = 2 * h, W = 2 * w;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = blockIdx.y;
+    const int v8 = blockIdx.z * 32 + lane;
+    const bool live = v8 < Ctot / 8;
+    const bool multi = gridDim.z > 1;
+    int c = v8 * 8, k = 0;
+    if (live)
+        while (k < src.n - 1 && c >= src.ch[k]) { c -= src.ch[k]; ++k; }
+    const int sc = live ? src.ch[k] : 8;
+    const bool is_up = live && k == 0;
+    // dead lanes read lane 0's data of source 0 (valid memory) and never store
+    const T* sp = reinterpret_cast<const T*>(src.ptr[live ? k : 0]) +
+                  (int64_t)n * (is_up || !live ? h * w : H * W) * (live ? sc : src.ch[0]) + (live ? c : 0);
+    const int stride = live ? sc : src.ch[0];
+    float wv[8], acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        wv[i] = (live && w_sse) ? w_sse[v8 * 8 + i] : 0.f;
+        acc[i] = 0.f;
+    }
+    const float bias = (blockIdx.z == 0) ? b_sse : 0.f;
+    const bool up_like = is_up || !live;
+
+    for (int oy = blockIdx.x * (kStatsThreads / 32) + warp; oy < H; oy += gridDim.x * (kStatsThreads / 32)) {
+        const int iy = oy >> 1;
+        int y0, y1;
+        float ly;
+        if (oy & 1) { y0 = iy; y1 = min(iy + 1, h - 1); ly = 0.25f; }
+        else if (iy == 0) { y0 = 0; y1 = min(1, h - 1); ly = 0.f; }
+        else { y0 = iy - 1; y1 = iy; ly = 0.75f; }
+        const float hy = 1.f - ly;
+        // up lanes: two low-res rows; skip lanes: the output row itself (ra = even pixels, rb = odd pixels)
+        const T* ra = up_like ? sp + (int64_t)y0 * w * stride : sp + (int64_t)oy * W * stride;
+        const T* rb = up_like ? sp + (int64_t)y1 * w * stride : ra + stride;
+        const int64_t step = up_like ? stride : 2 * stride;   // element step of ra/rb per iteration
+        float prev[8], cur[8], nxt[8], a[8], b[8];
+        // column 0 (up) or pixels 0,1 (skip)
+        Vec8<T>::ld(ra, a);
+        Vec8<T>::ld(rb, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { cur[i] = hy * a[i] + ly * b[i]; prev[i] = cur[i]; }
+        float s0[8], s1[8];                                   // skip lanes: pixel pair of this step
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s0[i] = a[i]; s1[i] = b[i]; }
+        // prefetch column 1 (up) / pixels 2,3 (skip)
+        int jn = min(1, w - 1);
+        Vec8<T>::ld(ra + (int64_t)jn * step, a);
+        Vec8<T>::ld(rb + (int64_t)jn * step, b);
+        T* yrow = y ? y + ((int64_t)(n * H + oy) * W) * Ctot + v8 * 8 : nullptr;
+        float* lrow = sse_logit ? sse_logit + (int64_t)(n * H + oy) * W : nullptr;
+        for (int i = 0; i < w; ++i) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) nxt[q] = hy * a[q] + ly * b[q];
+            float n0[8], n1[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { n0[q] = a[q]; n1[q] = b[q]; }
+            // issue the loads of the step after next before consuming this one
+            const int j2 = min(i + 2, w - 1);
+            Vec8<T>::ld(ra + (int64_t)j2 * step, a);
+            Vec8<T>::ld(rb + (int64_t)j2 * step, b);
+            float o0[8], o1[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float u0 = 0.25f * prev[q] + 0.75f * cur[q];
+                const float u1 = 0.75f * cur[q] + 0.25f * nxt[q];
+                o0[q] = is_up ? u0 : s0[q];
+                o1[q] = is_up ? u1 : s1[q];
+                prev[q] = cur[q];
+                cur[q] = nxt[q];
+                s0[q] = n0[q];
+                s1[q] = n1[q];
+            }
+            if (live && yrow) {
+                Vec8<T>::st(yrow + (int64_t)(2 * i) * Ctot, o0);
+                Vec8<T>::st(yrow + (int64_t)(2 * i + 1) * Ctot, o1);
+            }
+            float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                d0 = fmaf(o0[q], wv[q], d0);
+                d1 = fmaf(o1[q], wv[q], d1);
+                acc[q] += live ? o0[q] + o1[q] : 0.f;
+            }
+            if (lrow) {
+                d0 = warp_sum(d0);
+                d1 = warp_sum(d1);
+                if (lane == 0) {
+                    if (multi) { atomicAdd(lrow + 2 * i, d0 + bias); atomicAdd(lrow + 2 * i + 1, d1 + bias); }
+                    else { lrow[2 * i] = d0 + bias; lrow[2 * i + 1] = d1 + bias; }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_sum[warp][lane][i] = acc[i];
+    __syncthreads();
+    {
+        const int vl = threadIdx.x >> 3, e = threadIdx.x & 7;      // 256 threads = 32 vectors x 8 elements
+        const int ch = (blockIdx.z * 32 + vl) * 8 + e;
+        if (ch < Ctot) {
+            float t = 0.f;
+            for (int wi = 0; wi < kStatsThreads / 32; ++wi) t += s_sum[wi][vl][e];
+            atomicAdd(chan_mean + (int64_t)n * Ctot + ch, t * inv_hw);
+        }
+    }
+}
+
 // y = x * (cgate[n][c] + sigmoid(logit[n][p])), in place allowed.  grid-stride over (pixel, vec8).
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -217,6 +341,13 @@ extern "C" int eds_concat_stats(const void* x0, int N, int h, int w, int C0, int
     if (e != cudaSuccess) {
         set_error("concat_stats: memset failed: %s", cudaGetErrorString(e));
         return EDS_ERR_CUDA;
+    }
+    if (mode == EDS_UP_BILINEAR && c8 >= 32) {
+        dim3 grid(ceil_div(2 * h, kStatsThreads / 32), N, zchunks);
+        EDS_DISPATCH_DTYPE(dtype, T, (concat_stats_bilinear_kernel<T><<<grid, kStatsThreads, 0, as_stream(stream)>>>(
+                                         src, h, w, Ctot, w_sse, b_sse, 1.0f / (float)n_pix, (T*)y, chan_mean,
+                                         sse_logit)));
+        return check_launch("concat_stats_bilinear_kernel");
     }
     int chunks = ceil_div(148 * 16, N * zchunks);
     const int max_chunks = ceil_div(n_pix, 8 * (32 / lpp) * kStatsUnroll * 4);   // >= 4 steps per warp

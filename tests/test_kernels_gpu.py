@@ -406,7 +406,7 @@ def test_pr_hist_flat_regions_and_accumulate():
 
 
 @pytest.mark.parametrize("C0,skip_ch,mode", [(32, [16, 64], 1), (128, [256, 512], 1), (64, [64], 0), (16, [], 2),
-                                             (32, [], 2), (320, [], 2), (256, [256, 256, 256], 1), (2048, [1024], 0)])
+                                             (32, [], 2), (320, [], 2), (256, [256, 256, 256], 1), (2048, [1024], 0), (64, [256], 1), (512, [512], 1)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_concat_stats_and_scse_scale(C0, skip_ch, mode, dtype):
     """Two-pass SCSE == smp SCSEModule on the concatenated map."""
