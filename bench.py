@@ -154,15 +154,14 @@ def run_b200(args):
         return out
 
     def step_e2e(j):
-        """same through the public host-facing pieces: pinned host image/masks -> device, probability
-        maps and scores back to the host (what tta_patches' generator yields)."""
-        image = host_imgs[j].to(dev, non_blocking=True)
+        """same through the host-facing unit of tta_patches (`_driver.infer_image_host`): pinned host
+        image + mask -> device, probability map and scores back into pinned host memory, one stream
+        synchronisation per lesion map (what tta_patches' generator yields per image)."""
         res = []
         for les in LESIONS:
-            gt = host_masks[j][les].to(dev, non_blocking=True)
-            preds = drv.tiled_probability_map(models[les], tfm, image, S, mean, std, tiles_per_batch=args.tiles)
-            scores = score_device(preds, gt)
-            res.append((preds.cpu(), scores.ap))
+            pred, scores = drv.infer_image_host(models[les], tfm, host_imgs[j], host_masks[j][les], S, mean, std,
+                                                tiles_per_batch=args.tiles, copy=False, slot=les)
+            res.append((pred, scores.ap))
         return res
 
     def barrier():
@@ -220,7 +219,7 @@ def run_b200(args):
                        "l2": "working set per step (>5 GB of activations per tile batch) far exceeds the 126 MB L2",
                        "parallelism": f"images sharded over {world} rank(s); one int64 all-reduce of pooled counts"},
             "e2e": {"value": e2e, "unit": "images/s",
-                    "h2d_bytes_per_step": H * W * 3 + len(LESIONS) * H * W,
+                    "h2d_bytes_per_step": len(LESIONS) * (H * W * 3 + H * W),
                     "d2h_bytes_per_step": len(LESIONS) * (H * W * 4 + 19 * 2 * 8 + 2 * 8 + 16)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_hist": hist_roof,
         }

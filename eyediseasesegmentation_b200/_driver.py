@@ -177,10 +177,60 @@ def tiled_probability_map(model, transforms, image_dev: torch.Tensor, S: int, me
     return preds
 
 
+_PINNED = {}
+
+
+def _pinned(shape, dtype, tag="") -> torch.Tensor:
+    """Reusable page-locked staging buffer (cudaHostAlloc is milliseconds; the copy engine needs
+    pinned memory to run asynchronously at full PCIe rate)."""
+    key = (tuple(shape), dtype, tag)
+    buf = _PINNED.get(key)
+    if buf is None:
+        buf = torch.empty(tuple(shape), dtype=dtype).pin_memory()
+        _PINNED[key] = buf
+    return buf
+
+
+def score_to_host(preds_dev: torch.Tensor, gt_dev: torch.Tensor, copy: bool = True, slot: str = ""):
+    """Histogram + scan while the probability map is in HBM, then ONE synchronisation: the map and the
+    packed scores travel device -> pinned host asynchronously on the current stream.
+    Returns (probability map on the host [ScoredArray], ImageScores); with ``copy=False`` the array
+    aliases the staging buffer of ``slot`` (valid until the next call with the same slot)."""
+    from .aucpr import ImageScores
+    hist, strad = K.pr_hist(preds_dev.reshape(1, -1), gt_dev.reshape(1, -1))
+    ap, roc, counts, totals = K.pr_scan(hist, strad)
+    h_pred = _pinned(preds_dev.shape, torch.float32, "pred" + slot)
+    h_f = _pinned((2,), torch.float64, "apr" + slot)
+    h_c = _pinned(counts.shape, torch.int64, "cnt" + slot)
+    h_t = _pinned(totals.shape, torch.int64, "tot" + slot)
+    h_pred.copy_(preds_dev, non_blocking=True)
+    h_f[0:1].copy_(ap, non_blocking=True)
+    h_f[1:2].copy_(roc, non_blocking=True)
+    h_c.copy_(counts, non_blocking=True)
+    h_t.copy_(totals, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    c = h_c.numpy()
+    scores = ImageScores(float(h_f[0]), float(h_f[1]), c[0, :, 0].copy(), c[0, :, 1].copy(), int(h_t[0, 0]),
+                         int(h_t[0, 1]))
+    arr = h_pred.numpy()
+    return ScoredArray(arr.copy() if copy else arr, scores), scores
+
+
+def infer_image_host(model, transforms, image_host: torch.Tensor, gt_host: torch.Tensor, S: int, mean, std,
+                     tiles_per_batch: int = 6, copy: bool = True, slot: str = ""):
+    """Host-facing unit of the sliding-window path (one iteration of tta.py:190-215 plus its scoring):
+    decoded image ``[H,W,3]`` u8 and mask ``[H,W]`` u8 on the HOST (pinned memory makes the uploads
+    asynchronous) -> (probability map on the host, ImageScores)."""
+    dev = device()
+    image = image_host.to(dev, non_blocking=True)
+    gt = gt_host.to(dev, non_blocking=True)
+    preds = tiled_probability_map(model, transforms, image, S, mean, std, tiles_per_batch)
+    return score_to_host(preds, gt, copy=copy, slot=slot)
+
+
 def scored(preds_dev: torch.Tensor, gt: np.ndarray) -> ScoredArray:
     gt_dev = torch.from_numpy(np.ascontiguousarray(gt)).to(preds_dev.device)
-    scores = score_device(preds_dev, gt_dev)
-    return ScoredArray(preds_dev.cpu().numpy(), scores)
+    return score_to_host(preds_dev, gt_dev)[0]
 
 
 def output_dir(config, logdir) -> Path:

@@ -345,8 +345,13 @@ extern "C" int eds_conv2d_igemm_bf16(const void* x, int N, int H, int W, int C, 
     p.block_k = (C % 64 == 0) ? 64 : (C % 32 == 0 ? 32 : 16);
     p.k_chunks = C / p.block_k;
     // cout tile: the largest multiple of 16 that divides Cout and is <= 256
+    const int k_iters = p.taps * p.k_chunks;
     int bn = 256;
     while (bn > 16 && Cout % bn != 0) bn -= 16;
+    // Short reductions (1x1 convolutions, thin 3x3 layers) spend their time in the fill / epilogue
+    // latency chain, not in the MMAs: a 128-wide cout tile keeps 4 CTAs (TMEM: 4 x 128 columns)
+    // resident per SM so those chains overlap.
+    if (k_iters <= 16 && bn > 128 && Cout % 128 == 0) bn = 128;
     p.block_n = bn;
     p.n_tiles = Cout / bn;
     p.N = N; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.relu = relu;
@@ -379,8 +384,10 @@ extern "C" int eds_conv2d_igemm_bf16(const void* x, int N, int H, int W, int C, 
     p.a_stage_bytes = kTileM * p.block_k * 2;                          // 16 / 8 / 4 KB
     p.b_stage_bytes = (p.block_n * p.block_k * 2 + 1023) & ~1023;
     const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
-    const int budget = stage_bytes >= 40 * 1024 ? 200 * 1024 : 100 * 1024;
-    p.stages = std::max(2, std::min(kMaxStages, budget / stage_bytes));
+    // long reductions: one deep pipeline per SM (wide tiles) or two CTAs x ~100 KB; short ones
+    // keep the whole K extent resident (stages == k_iters) in <= 54 KB so four CTAs fit.
+    const int budget = k_iters <= 16 ? 54 * 1024 : (stage_bytes >= 40 * 1024 ? 200 * 1024 : 100 * 1024);
+    p.stages = std::max(k_iters > 1 ? 2 : 1, std::min(std::min(kMaxStages, k_iters), budget / stage_bytes));
     p.tmem_cols = std::max(32, pow2_ceil(p.block_n));
     const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + (2 * kMaxStages + 1) * 8 + 16;
 

@@ -97,9 +97,9 @@ def tta_patches(logdir, config, args):
         for mask_path in TEST_MASKS:
             img = test_img_dir / re.sub("_" + config["lesion_type"] + ".tif", ".jpg", mask_path.name)
             gt_mask = drv.read_mask(mask_path, 0)
-            image = torch.from_numpy(drv.read_rgb(img)).to(dev)
-            preds = drv.tiled_probability_map(model, transforms, image, resize_size, mean, std)
-            yield drv.scored(preds, gt_mask), gt_mask, mask_path.name
+            pred, _ = drv.infer_image_host(model, transforms, torch.from_numpy(drv.read_rgb(img)),
+                                           torch.from_numpy(gt_mask), resize_size, mean, std)
+            yield pred, gt_mask, mask_path.name
 
     predict_generator = drv.CachedPredictions(produce)
 

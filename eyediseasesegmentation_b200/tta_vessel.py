@@ -71,8 +71,8 @@ def tta_patches(logdir, config, args):
     def produce():
         for mask_path in TEST_MASKS:
             gt_mask = drv.read_mask(mask_path, 50)
-            image = torch.from_numpy(drv.read_rgb(test_img_dir / mask_path.name)).to(dev)
-            preds = drv.tiled_probability_map(model, transforms, image, resize_size, mean, std)
-            yield drv.scored(preds, gt_mask), gt_mask, mask_path.name
+            pred, _ = drv.infer_image_host(model, transforms, torch.from_numpy(drv.read_rgb(test_img_dir / mask_path.name)),
+                                           torch.from_numpy(gt_mask), resize_size, mean, std)
+            yield pred, gt_mask, mask_path.name
 
     _finish(drv.CachedPredictions(produce), logdir, config, as_float=True)
