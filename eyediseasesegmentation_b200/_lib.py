@@ -25,6 +25,12 @@ PR_THRESHOLDS = [0, 0.00001, 0.0001, 0.001, 0.01, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 
 
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
+
+class GatedSrc(C.Structure):
+    """``eds_gated_src`` of include/eds_b200.h."""
+    _fields_ = [("x", C.c_void_p), ("cgate", C.c_void_p), ("sgate", C.c_void_p), ("C", C.c_int)]
+
+
 # name -> argtypes; every function returns int except the two noted below.
 PROTOTYPES = {
     "eds_version": [],
@@ -48,6 +54,10 @@ PROTOTYPES = {
     "eds_upsample2x_concat": [_vp, _i, _i, _i, _i, _i, C.POINTER(_vp), C.POINTER(_i), _i, _vp, _i, _vp],
     "eds_concat_stats": [_vp, _i, _i, _i, _i, _i, C.POINTER(_vp), C.POINTER(_i), _i, _vp, _f, _vp, _vp, _vp, _i, _vp],
     "eds_scse_scale": [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
+    "eds_gated_stats": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp],
+    "eds_sse_finalize": [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp],
+    "eds_concat_gated": [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
+    "eds_apply_gate": [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
     "eds_axial_attention": [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp],
     "eds_mhca_gate": [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
     "eds_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],

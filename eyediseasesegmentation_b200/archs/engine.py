@@ -30,6 +30,27 @@ def _bn_affine(sd, p):
     return scale, shift
 
 
+class Gated:
+    """A map whose SCSE gate is still pending: value = t * (cgate[n,c] + sgate[n,p])."""
+    __slots__ = ("t", "cgate", "sgate")
+
+    def __init__(self, t, cgate, sgate):
+        self.t, self.cgate, self.sgate = t, cgate, sgate
+
+    @property
+    def shape(self):
+        return self.t.shape
+
+
+def _parts(x):
+    return (x.t, x.cgate, x.sgate) if isinstance(x, Gated) else (x, None, None)
+
+
+def _plain(x):
+    """Materialise a pending gate (new tensor; other consumers still hold the ungated map)."""
+    return K.apply_gate(x.t, x.cgate, x.sgate) if isinstance(x, Gated) else x
+
+
 class Engine:
     def __init__(self, arch: str, cfg: dict, sd: Dict[str, torch.Tensor], device: torch.device, precision: str = "bf16"):
         if precision not in ("bf16", "fp32"):
@@ -178,22 +199,40 @@ class Engine:
         if self.keep_features:
             self.features[name] = t
 
+    # SCSE with deferred gates (csrc/scse_gated.cu): a block output keeps its attention2 gate as two
+    # side tensors (Gated) until a concat or the head reads it, and attention1 is applied while the
+    # concat is written -- no map is written twice.
     def _apply_scse(self, name, x):
-        """SCSE on an existing map (attention2): statistics pass + MLP + in-place scale."""
+        """attention2: statistics of the block output -> (x, cgate, sgate), nothing rewritten."""
         if (name + ".sse") not in self.w:
             return x
         w_sse, b_sse = self.w[name + ".sse"]
-        _, mean, logit = K.concat_stats(x, [], _lib.UP_NONE, w_sse, b_sse, write=False)
-        gate = K.se_gate(mean, *self.w[name + ".cse"])
-        return K.scse_scale(x, gate, logit, out=x)
+        N, H, W, C = x.shape
+        mean = torch.empty((N, C), dtype=torch.float32, device=x.device)
+        dot = torch.empty((N, H, W), dtype=torch.float32, device=x.device)
+        K.gated_stats(x, None, None, w_sse, mean, 0, True, dot, False)
+        cgate = K.se_gate(mean, *self.w[name + ".cse"])
+        return Gated(x, cgate, K.sse_finalize(None, dot, _lib.UP_NONE, b_sse))
 
     def _concat_scse(self, name, x, skips):
-        """cat([up2x(x), *skips]) followed by SCSE (attention1): one pass builds the concat and its
-        statistics, the second scales it in place."""
+        """attention1(cat([up2x(x), *skips])): one statistics pass per source at its own resolution,
+        then one pass that writes the gated concat."""
         w_sse, b_sse = self.w[name + ".sse"]
-        cat, mean, logit = K.concat_stats(x, list(skips), self.up_mode, w_sse, b_sse, write=True)
-        gate = K.se_gate(mean, *self.w[name + ".cse"])
-        return K.scse_scale(cat, gate, logit, out=cat)
+        srcs = [_parts(x)] + [_parts(s) for s in skips]
+        x0 = srcs[0][0]
+        N, h, w, _ = x0.shape
+        ctot = sum(t[0].shape[3] for t in srcs)
+        mean = torch.empty((N, ctot), dtype=torch.float32, device=x0.device)
+        dot0 = torch.empty((N, h, w), dtype=torch.float32, device=x0.device)
+        dot1 = torch.empty((N, 2 * h, 2 * w), dtype=torch.float32, device=x0.device)
+        off = 0
+        for k, (t, cg, sg) in enumerate(srcs):
+            c = t.shape[3]
+            K.gated_stats(t, cg, sg, w_sse[off:off + c], mean, off, k == 0, dot0 if k == 0 else dot1, k > 1)
+            off += c
+        cgate = K.se_gate(mean, *self.w[name + ".cse"])
+        sgate = K.sse_finalize(dot0, dot1, self.up_mode, b_sse)
+        return K.concat_gated(srcs, self.up_mode, cgate, sgate)
 
     # ---------------------------------------------------------------- encoders
     def _se_bottleneck(self, p, x, stride):
@@ -260,6 +299,7 @@ class Engine:
 
     # ---------------------------------------------------------------- decoders
     def _mhca_skip(self, p, x, skips: Sequence[torch.Tensor]):
+        skips = [_plain(t) for t in skips]
         skip = skips[0] if len(skips) == 1 else K.upsample2x_concat(skips[0], list(skips[1:]), _lib.UP_NONE)
         cr = skip.shape[3] // 16
         ori = self._cv(skip, p + ".down_sample")
@@ -274,17 +314,21 @@ class Engine:
     def _decoder_block(self, name, x, skips: Sequence[torch.Tensor]):
         p = f"decoder.blocks.{name}"
         if (p + ".down_sample") in self.w:
+            x = _plain(x)
             cat = K.upsample2x_concat(x, [self._mhca_skip(p, x, skips)], self.up_mode)
         else:
             if skips and (p + ".attention1.sse") in self.w:
                 cat = self._concat_scse(p + ".attention1", x, skips)
+            elif isinstance(x, Gated) or any(isinstance(t, Gated) for t in skips):
+                cat = K.concat_gated([_parts(x)] + [_parts(t) for t in skips], self.up_mode)
             else:
                 cat = K.upsample2x_concat(x, list(skips), self.up_mode)
         y = self._cv(cat, p + ".conv1", pad=1, relu=True)
         y = self._cv(y, p + ".conv2", pad=1, relu=True)
         if (p + ".down_sample") not in self.w:
             y = self._apply_scse(p + ".attention2", y)
-        self._keep(name, y)
+        if self.keep_features:
+            self.features[name] = _plain(y)
         return y
 
     def _decode_dense(self, feats: List[torch.Tensor]):
@@ -330,4 +374,4 @@ class Engine:
             self.features = {}
         feats = self._encode(x, aug_maps or IDENTITY_VIEW)
         y = self._decode_unet(feats) if self.arch == "Unet" else self._decode_dense(feats)
-        return K.head_conv3x3(y, *self.w["head"])
+        return K.head_conv3x3(_plain(y), *self.w["head"])

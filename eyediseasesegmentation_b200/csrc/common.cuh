@@ -73,6 +73,39 @@ template <> struct Vec8<float> {
     }
 };
 
+// The same 8 channels as four float2 for the packed fp32 pipe of sm_100 (FFMA2 / FADD2 / FMUL2:
+// two IEEE fp32 operations per instruction, results identical to the scalar forms).
+template <typename T> struct V8;
+template <> struct V8<__nv_bfloat16> {
+    static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float2 (&v)[4]) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(p);
+        const uint32_t u[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = make_float2(__uint_as_float(u[i] << 16), __uint_as_float(u[i] & 0xffff0000u));
+    }
+    static __device__ __forceinline__ void st(__nv_bfloat16* p, const float2 (&v)[4]) {
+        uint4 raw;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[i].x, v[i].y);
+        *reinterpret_cast<uint4*>(p) = raw;
+    }
+};
+template <> struct V8<float> {
+    static __device__ __forceinline__ void ld(const float* p, float2 (&v)[4]) {
+        const float4 a = *reinterpret_cast<const float4*>(p);
+        const float4 b = *reinterpret_cast<const float4*>(p + 4);
+        v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w);
+        v[2] = make_float2(b.x, b.y); v[3] = make_float2(b.z, b.w);
+    }
+    static __device__ __forceinline__ void st(float* p, const float2 (&v)[4]) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+        *reinterpret_cast<float4*>(p + 4) = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
+    }
+};
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ void ld8f(const float* p, float2 (&v)[4]) { V8<float>::ld(p, v); }
+
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {

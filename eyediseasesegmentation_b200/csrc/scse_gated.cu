@@ -1,0 +1,455 @@
+// Decoder concat + SCSE with DEFERRED gates: the gated map is never written twice.
+//
+// Reference: DecoderBlock.forward (src/main/archs/unetplusplusstar.py:151-161; smp SCSEModule, 3P):
+//     x = cat([interpolate(x, 2), *skips]); x = attention1(x); x = conv1(x); x = conv2(x); x = attention2(x)
+// SCSE scales every element by cSE[n][c] + sSE[n][p]; both need a global pass over the map first
+// (channel means, per-pixel w_sse . x).  Instead of materialising a map and then re-writing it
+// scaled (4 full passes per concat in the first version, see scse.cu), a map carries its gate as
+// two small side tensors until somebody reads it:
+//
+//     value[n][p][c] = x[n][p][c] * (cgate[n][c] + sgate[n][p])          "gated source"
+//
+//   eds_gated_stats   one read of ONE source at ITS OWN resolution: channel means of the gated values
+//                     and the per-pixel dot with this source's slice of w_sse.  Bilinear / nearest x2
+//                     upsampling preserves channel means exactly (every low-res pixel carries total
+//                     weight 4) and commutes with the dot, so the upsampled source is read at low res.
+//   eds_sse_finalize  sgate[n][p] = sigmoid(up2x(dot0)[p] + dot1[p] + b)   (tiny, [N][H][W] scalars)
+//   eds_concat_gated  reads the sources again, applies their gates, upsamples source 0, applies the
+//                     concat's own gate and writes the conv input ONCE.
+//
+// Traffic per decoder block: 2 reads of the sources + 1 write of the concat (was 1 read of the sources,
+// 2 writes + 1 read of the concat, and 2 reads + 1 write of the block output for attention2).
+#include "common.cuh"
+
+namespace eds {
+
+constexpr int kGsThreads = 256;
+constexpr int kGsUnroll = 8;      // pixels in flight per lane group (memory-level parallelism)
+
+constexpr int ilog2c(int v) { return v <= 1 ? 0 : 1 + ilog2c(v >> 1); }
+
+// Sum d[0..M) over the lanes of a pixel group whose lane-in-group index differs in bit O and below.
+// While more than one value is held the exchange is a transpose step (each lane keeps half of the
+// values and receives the partner's partial sums of that half), so U values cost about U shuffles
+// instead of U * log2(lanes).  Afterwards the lane holds d[0..max(1, U/LPP)) = totals of pixels
+// u_sel + q.
+template <int O, int M> struct GroupReduce {
+    static __device__ __forceinline__ void run(float* d, int l, int& u_sel) {
+        if constexpr (O > 0) {
+            if constexpr (M > 1) {
+                const bool upper = (l & O) != 0;
+#pragma unroll
+                for (int q = 0; q < M / 2; ++q) {
+                    const float send = upper ? d[q] : d[q + M / 2];
+                    const float keep = upper ? d[q + M / 2] : d[q];
+                    d[q] = keep + __shfl_xor_sync(0xffffffffu, send, O);
+                }
+                if (upper) u_sel += M / 2;
+                GroupReduce<O / 2, M / 2>::run(d, l, u_sel);
+            } else {
+                d[0] += __shfl_xor_sync(0xffffffffu, d[0], O);
+                GroupReduce<O / 2, 1>::run(d, l, u_sel);
+            }
+        }
+    }
+};
+
+// ---- pass A -----------------------------------------------------------------------------------
+// grid = (pixel chunks, N, 256-channel chunks).  LPP lanes (power of two) share one pixel; lane l
+// owns ONE 8-channel vector of every pixel it visits.  With value = v * (cg + s):
+//   dot      = sum_c v*(cg*w) + s * sum_c v*w          (two packed FMA chains)
+//   chan sum = cg * sum_p v + sum_p s*v                 (accA, accB)
+template <typename T, bool GATED, int LPP>
+__global__ void __launch_bounds__(kGsThreads, 2)
+gated_stats_kernel(const T* __restrict__ x, const float* __restrict__ cgate, const float* __restrict__ sgate, int P,
+                   int C, const float* __restrict__ w_sse, float inv_p, float* __restrict__ chan_mean,
+                   int mean_stride, int c_off, float* __restrict__ dot, int accumulate) {
+    constexpr int PPW = 32 / LPP, U = kGsUnroll;
+    constexpr int NS = ilog2c(LPP) < ilog2c(U) ? ilog2c(LPP) : ilog2c(U);   // transpose stages
+    constexpr int MF = U >> NS;                                              // totals left per lane
+    constexpr int PLAIN = ilog2c(LPP) - NS;                                  // replicated low lane bits
+    __shared__ float s_sum[kGsThreads / 32][32][8 + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int l = lane % LPP, sub = lane / LPP;
+    const int n = blockIdx.y;
+    const int v8 = blockIdx.z * 32 + l;
+    const bool live = v8 < C / 8;
+    const bool multi = gridDim.z > 1;
+    const T* xp = x + (int64_t)n * P * C + (live ? v8 * 8 : 0);
+    const float* sg = GATED ? sgate + (int64_t)n * P : nullptr;
+    float2 w2[4], cw2[4], cg2[4], accA[4], accB[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w2[k] = cw2[k] = accA[k] = accB[k] = f2(0.f), cg2[k] = f2(1.f);
+    if (live) {
+        if (w_sse) ld8f(w_sse + v8 * 8, w2);
+        if (GATED) {
+            ld8f(cgate + (int64_t)n * C + v8 * 8, cg2);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) cw2[k] = __fmul2_rn(cg2[k], w2[k]);
+        }
+    }
+    const int per = (P + gridDim.x - 1) / gridDim.x;
+    const int p_begin = blockIdx.x * per;
+    const int p_end = min(P, p_begin + per);
+    constexpr int STEP = (kGsThreads / 32) * PPW * U;
+    for (int pb = p_begin + warp * PPW * U; pb < p_end; pb += STEP) {
+        float2 v[U][4];
+        float sv[U], d[U];
+        // All loads are issued unconditionally (addresses clamped into the chunk) so that ptxas
+        // keeps U vector loads in flight; lanes without a channel vector read vector 0 and are
+        // neutralised by their zero weights, pixels past the end are zeroed in the tail step only.
+        const bool tail = pb + PPW * U > p_end;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int p = min(pb + u * PPW + sub, p_end - 1);
+            V8<T>::ld(xp + (int64_t)p * C, v[u]);
+            sv[u] = GATED ? __ldg(sg + p) : 0.f;
+        }
+        if (tail) {
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (pb + u * PPW + sub >= p_end) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v[u][k] = f2(0.f);
+                }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float2 a = f2(0.f), b = f2(0.f);
+            const float2 s2 = f2(sv[u]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                a = __ffma2_rn(v[u][k], w2[k], a);
+                accA[k] = __fadd2_rn(accA[k], v[u][k]);
+                if (GATED) {
+                    b = __ffma2_rn(v[u][k], cw2[k], b);
+                    accB[k] = __ffma2_rn(s2, v[u][k], accB[k]);
+                }
+            }
+            d[u] = GATED ? (b.x + b.y) + sv[u] * (a.x + a.y) : (a.x + a.y);
+        }
+        if (dot) {
+            int u_sel = 0;
+            GroupReduce<LPP / 2, U>::run(d, l, u_sel);
+            if ((l & ((1 << PLAIN) - 1)) == 0) {
+#pragma unroll
+                for (int q = 0; q < MF; ++q) {
+                    const int p = pb + (u_sel + q) * PPW + sub;
+                    if (p < p_end) {
+                        float* dst = dot + (int64_t)n * P + p;
+                        if (multi) atomicAdd(dst, d[q]);
+                        else *dst = accumulate ? *dst + d[q] : d[q];
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float2 t = GATED ? __ffma2_rn(cg2[k], accA[k], accB[k]) : accA[k];
+        s_sum[warp][lane][2 * k] = t.x;
+        s_sum[warp][lane][2 * k + 1] = t.y;
+    }
+    __syncthreads();
+    if (threadIdx.x < LPP * 8) {
+        const int vl = threadIdx.x >> 3, e = threadIdx.x & 7;
+        const int ch = (blockIdx.z * 32 + vl) * 8 + e;
+        if (ch < C) {
+            float t = 0.f;
+            for (int wi = 0; wi < kGsThreads / 32; ++wi)
+#pragma unroll
+                for (int q = 0; q < PPW; ++q) t += s_sum[wi][q * LPP + vl][e];
+            atomicAdd(chan_mean + (int64_t)n * mean_stride + c_off + ch, t * inv_p);
+        }
+    }
+}
+
+// bilinear(align_corners=False) x2 taps of output index o over a source of length len:
+// out = (1-l)*src[i0] + l*src[i1]
+__device__ __forceinline__ void up2_taps(int o, int len, int& i0, int& i1, float& l) {
+    const int i = o >> 1;
+    if (o & 1) { i0 = i; i1 = min(i + 1, len - 1); l = 0.25f; }
+    else if (i == 0) { i0 = 0; i1 = 0; l = 0.f; }
+    else { i0 = i - 1; i1 = i; l = 0.75f; }
+}
+
+// sgate[n][p] = sigmoid(up(dot0)[p] + dot1[p] + b) over the OUTPUT grid H x W (= up * h x up * w).
+__global__ void __launch_bounds__(256)
+sse_finalize_kernel(const float* __restrict__ dot0, const float* __restrict__ dot1, int N, int h, int w, int mode,
+                    float b, float* __restrict__ sgate) {
+    const int up = mode == EDS_UP_NONE ? 1 : 2;
+    const int H = up * h, W = up * w;
+    const int64_t total = (int64_t)N * H * W;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int ox = (int)(idx % W);
+        const int64_t t = idx / W;
+        const int oy = (int)(t % H);
+        const int n = (int)(t / H);
+        float v = b;
+        if (dot1) v += dot1[idx];
+        if (dot0) {
+            const float* d = dot0 + (int64_t)n * h * w;
+            if (mode == EDS_UP_NONE) v += d[oy * w + ox];
+            else if (mode == EDS_UP_NEAREST) v += d[(oy >> 1) * w + (ox >> 1)];
+            else {
+                int y0, y1, x0, x1;
+                float ly, lx;
+                up2_taps(oy, h, y0, y1, ly);
+                up2_taps(ox, w, x0, x1, lx);
+                const float top = (1.f - lx) * d[y0 * w + x0] + lx * d[y0 * w + x1];
+                const float bot = (1.f - lx) * d[y1 * w + x0] + lx * d[y1 * w + x1];
+                v += (1.f - ly) * top + ly * bot;
+            }
+        }
+        sgate[idx] = sigmoidf_acc(v);
+    }
+}
+
+// ---- pass B -----------------------------------------------------------------------------------
+struct GatedSrc {
+    const void* x;
+    const float* cgate;
+    const float* sgate;
+    int C;
+};
+struct CatSrcs {
+    GatedSrc s[6];
+    int n;
+};
+
+template <typename T>
+__device__ __forceinline__ void ld_gated(const T* p, const float2 (&cg)[4], const float* sg, bool gated,
+                                         float2 (&v)[4]) {
+    V8<T>::ld(p, v);
+    if (gated) {
+        const float2 s2 = f2(__ldg(sg));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = __fmul2_rn(v[k], __fadd2_rn(cg[k], s2));
+    }
+}
+
+// One thread = one 8-channel vector of one 2x2 OUTPUT block (i, j) <- low-res pixel (i, j) of
+// source 0 and its 3x3 neighbourhood (9 loads feed 4 outputs), or the 4 same-resolution pixels of
+// a skip source.  grid.x = N*h rows of blocks, grid.y covers (j, vector) of a row; consecutive
+// threads own consecutive vectors of the same block, so every global access of a warp is a
+// contiguous run.  All lerps / gates run on the packed fp32 pipe.
+// PART 0 writes the channels of the upsampled source 0 (register-heavy: 9 vectors in flight), PART 1 the
+// channels of the same-resolution sources (a light streaming kernel that runs at full occupancy).
+template <typename T, int PART>
+__global__ void __launch_bounds__(256, PART == 0 ? 2 : 4)
+concat_gated_kernel(CatSrcs src, int h, int w, int mode, int Ctot, const float* __restrict__ cgate1,
+                    const float* __restrict__ sgate1, T* __restrict__ y) {
+    const uint32_t C8a = (uint32_t)src.s[0].C / 8;
+    const uint32_t C8 = PART == 0 ? C8a : (uint32_t)Ctot / 8 - C8a;     // vectors per pixel of this part
+    const uint32_t col = blockIdx.y * blockDim.x + threadIdx.x;
+    if (col >= (uint32_t)w * C8) return;
+    const int j = (int)(col / C8);
+    const int c8 = (int)(col - (uint32_t)j * C8) + (PART == 0 ? 0 : (int)C8a);
+    const int n = (int)(blockIdx.x / (uint32_t)h);
+    const int i = (int)(blockIdx.x - (uint32_t)n * h);
+    const int H = 2 * h, W = 2 * w;
+    int c = c8 * 8, k = 0;
+    if (PART == 1)
+        while (k < src.n - 1 && c >= src.s[k].C) { c -= src.s[k].C; ++k; }
+    const GatedSrc s = src.s[k];
+    const bool gated = s.cgate != nullptr;
+    float2 cg[4];
+    if (gated) ld8f(s.cgate + (int64_t)n * s.C + c, cg);
+    float2 o[4][4];
+    if (PART == 0) {
+        const T* xp = reinterpret_cast<const T*>(s.x) + (int64_t)n * h * w * s.C + c;
+        const float* sg = s.sgate + (int64_t)n * h * w;      // only dereferenced when gated
+        if (mode == EDS_UP_NEAREST) {
+            ld_gated<T>(xp + (int64_t)(i * w + j) * s.C, cg, sg + i * w + j, gated, o[0]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o[1][q] = o[2][q] = o[3][q] = o[0][q];
+        } else {
+            const int r[3] = {max(i - 1, 0) * w, i * w, min(i + 1, h - 1) * w};
+            const int cc[3] = {max(j - 1, 0), j, min(j + 1, w - 1)};
+            float2 top[3][4], bot[3][4];
+            const float2 q25 = f2(0.25f), q75 = f2(0.75f);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                float2 v0[4], v1[4], v2[4];
+                ld_gated<T>(xp + (int64_t)(r[0] + cc[a]) * s.C, cg, sg + r[0] + cc[a], gated, v0);
+                ld_gated<T>(xp + (int64_t)(r[1] + cc[a]) * s.C, cg, sg + r[1] + cc[a], gated, v1);
+                ld_gated<T>(xp + (int64_t)(r[2] + cc[a]) * s.C, cg, sg + r[2] + cc[a], gated, v2);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 m = __fmul2_rn(q75, v1[q]);
+                    top[a][q] = __ffma2_rn(q25, v0[q], m);
+                    bot[a][q] = __ffma2_rn(q25, v2[q], m);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 mt = __fmul2_rn(q75, top[1][q]), mb = __fmul2_rn(q75, bot[1][q]);
+                o[0][q] = __ffma2_rn(q25, top[0][q], mt);
+                o[1][q] = __ffma2_rn(q25, top[2][q], mt);
+                o[2][q] = __ffma2_rn(q25, bot[0][q], mb);
+                o[3][q] = __ffma2_rn(q25, bot[2][q], mb);
+            }
+        }
+    } else {
+        const T* xp = reinterpret_cast<const T*>(s.x) + (int64_t)n * H * W * s.C + c;
+        const float* sg = s.sgate + (int64_t)n * H * W;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const int p = (2 * i + (d >> 1)) * W + 2 * j + (d & 1);
+            ld_gated<T>(xp + (int64_t)p * s.C, cg, sg + p, gated, o[d]);
+        }
+    }
+    const int64_t p00 = ((int64_t)n * H + 2 * i) * W + 2 * j;     // output pixel (2i, 2j)
+    if (cgate1) {
+        float2 g1[4];
+        ld8f(cgate1 + (int64_t)n * Ctot + c8 * 8, g1);
+        const float2 s01 = *reinterpret_cast<const float2*>(sgate1 + p00);       // (2i, 2j), (2i, 2j+1)
+        const float2 s23 = *reinterpret_cast<const float2*>(sgate1 + p00 + W);   // (2i+1, 2j), (2i+1, 2j+1)
+        const float sd[4] = {s01.x, s01.y, s23.x, s23.y};
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const float2 s1 = f2(sd[d]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o[d][q] = __fmul2_rn(o[d][q], __fadd2_rn(g1[q], s1));
+        }
+    }
+    T* yp = y + p00 * Ctot + c8 * 8;
+    V8<T>::st(yp, o[0]);
+    V8<T>::st(yp + Ctot, o[1]);
+    V8<T>::st(yp + (int64_t)W * Ctot, o[2]);
+    V8<T>::st(yp + (int64_t)W * Ctot + Ctot, o[3]);
+}
+
+// y = x * (cgate[n][c] + sgate[n][p]) for an already materialised map (gate = probabilities).
+template <typename T>
+__global__ void __launch_bounds__(256)
+apply_gate_kernel(const T* __restrict__ x, const float* __restrict__ cgate, const float* __restrict__ sgate, int HW,
+                  int C8, int64_t total, T* __restrict__ y) {
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pix = idx / C8;
+        const int c8 = (int)(idx - pix * C8);
+        const int n = (int)(pix / HW);
+        const float s = __ldg(sgate + pix);
+        const float4* g4 = reinterpret_cast<const float4*>(cgate + (int64_t)n * C8 * 8 + c8 * 8);
+        const float4 g0 = __ldg(g4), g1 = __ldg(g4 + 1);
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        float v[8];
+        Vec8<T>::ld(x + idx * 8, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] *= g[i] + s;
+        Vec8<T>::st(y + idx * 8, v);
+    }
+}
+
+}  // namespace eds
+
+using namespace eds;
+
+extern "C" int eds_gated_stats(const void* x, const float* cgate, const float* sgate, int N, int P, int C,
+                               const float* w_sse, float* chan_mean, int mean_stride, int c_off, int zero_mean,
+                               float* dot, int accumulate, int dtype, void* stream) {
+    EDS_REQUIRE(x && chan_mean, "gated_stats: null pointer");
+    EDS_REQUIRE((cgate == nullptr) == (sgate == nullptr), "gated_stats: cgate and sgate come together");
+    EDS_REQUIRE(N > 0 && N <= 65535 && P > 0 && C > 0 && C % 8 == 0, "gated_stats: bad shape N=%d P=%d C=%d", N, P, C);
+    EDS_REQUIRE(mean_stride >= c_off + C && c_off >= 0 && c_off % 8 == 0, "gated_stats: bad mean layout");
+    EDS_REQUIRE(!dot || w_sse, "gated_stats: dot requested without w_sse");
+    const int c8 = C / 8;
+    int lpp = 32;
+    while (lpp > 1 && lpp / 2 >= c8) lpp /= 2;
+    const int zchunks = ceil_div(c8, 32);
+    EDS_REQUIRE(zchunks <= 65535, "gated_stats: too many channels");
+    cudaError_t e = cudaSuccess;
+    if (zero_mean) e = cudaMemsetAsync(chan_mean, 0, sizeof(float) * (size_t)N * mean_stride, as_stream(stream));
+    if (e == cudaSuccess && dot && zchunks > 1 && !accumulate)
+        e = cudaMemsetAsync(dot, 0, sizeof(float) * (size_t)N * P, as_stream(stream));
+    if (e != cudaSuccess) {
+        set_error("gated_stats: memset failed: %s", cudaGetErrorString(e));
+        return EDS_ERR_CUDA;
+    }
+    int chunks = ceil_div(148 * 12, N * zchunks);
+    const int max_chunks = ceil_div(P, 8 * (32 / lpp) * kGsUnroll);
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    dim3 grid(chunks, N, zchunks);
+#define EDS_GS_LAUNCH(T, G, L)                                                                                   \
+    gated_stats_kernel<T, G, L><<<grid, kGsThreads, 0, as_stream(stream)>>>(                                     \
+        (const T*)x, cgate, sgate, P, C, w_sse, 1.0f / (float)P, chan_mean, mean_stride, c_off, dot, accumulate)
+#define EDS_GS_LPP(T, G)                                                                                         \
+    switch (lpp) {                                                                                               \
+        case 1: EDS_GS_LAUNCH(T, G, 1); break;                                                                   \
+        case 2: EDS_GS_LAUNCH(T, G, 2); break;                                                                   \
+        case 4: EDS_GS_LAUNCH(T, G, 4); break;                                                                   \
+        case 8: EDS_GS_LAUNCH(T, G, 8); break;                                                                   \
+        case 16: EDS_GS_LAUNCH(T, G, 16); break;                                                                 \
+        default: EDS_GS_LAUNCH(T, G, 32); break;                                                                 \
+    }
+    EDS_DISPATCH_DTYPE(dtype, T, {
+        if (cgate) { EDS_GS_LPP(T, true) } else { EDS_GS_LPP(T, false) }
+    });
+#undef EDS_GS_LPP
+#undef EDS_GS_LAUNCH
+    return check_launch("gated_stats_kernel");
+}
+
+extern "C" int eds_sse_finalize(const float* dot0, const float* dot1, int N, int h, int w, int mode, float b_sse,
+                                float* sgate, void* stream) {
+    EDS_REQUIRE(sgate && (dot0 || dot1), "sse_finalize: null pointer");
+    EDS_REQUIRE(mode == EDS_UP_NEAREST || mode == EDS_UP_BILINEAR || mode == EDS_UP_NONE, "sse_finalize: bad mode %d",
+                mode);
+    EDS_REQUIRE(N > 0 && h > 0 && w > 0, "sse_finalize: bad shape");
+    const int up = mode == EDS_UP_NONE ? 1 : 2;
+    const int64_t total = (int64_t)N * up * h * up * w;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    sse_finalize_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(dot0, dot1, N, h, w, mode, b_sse, sgate);
+    return check_launch("sse_finalize_kernel");
+}
+
+extern "C" int eds_concat_gated(const eds_gated_src* srcs, int n_srcs, int N, int h, int w, int mode,
+                                const float* cgate, const float* sgate, void* y, int dtype, void* stream) {
+    EDS_REQUIRE(srcs && y, "concat_gated: null pointer");
+    EDS_REQUIRE(n_srcs >= 1 && n_srcs <= 6, "concat_gated: n_srcs=%d not in 1..6", n_srcs);
+    EDS_REQUIRE(mode == EDS_UP_NEAREST || mode == EDS_UP_BILINEAR, "concat_gated: mode %d (nearest / bilinear x2 only)",
+                mode);
+    EDS_REQUIRE((cgate == nullptr) == (sgate == nullptr), "concat_gated: cgate and sgate come together");
+    EDS_REQUIRE(N > 0 && h > 0 && w > 0, "concat_gated: bad shape");
+    CatSrcs cs;
+    cs.n = n_srcs;
+    int Ctot = 0;
+    for (int k = 0; k < 6; ++k) {
+        if (k < n_srcs) {
+            EDS_REQUIRE(srcs[k].x && srcs[k].C > 0 && srcs[k].C % 8 == 0, "concat_gated: bad source %d", k);
+            EDS_REQUIRE((srcs[k].cgate == nullptr) == (srcs[k].sgate == nullptr),
+                        "concat_gated: source %d: cgate and sgate come together", k);
+            cs.s[k].x = srcs[k].x; cs.s[k].cgate = srcs[k].cgate; cs.s[k].sgate = srcs[k].sgate; cs.s[k].C = srcs[k].C;
+            Ctot += srcs[k].C;
+        } else {
+            cs.s[k].x = nullptr; cs.s[k].cgate = nullptr; cs.s[k].sgate = nullptr; cs.s[k].C = 0;
+        }
+    }
+    EDS_REQUIRE((int64_t)w * (Ctot / 8) < (1ll << 24) && (int64_t)N * h < (1ll << 31), "concat_gated: map too large");
+    const int c8a = cs.s[0].C / 8, c8b = Ctot / 8 - c8a;
+    dim3 grid_a((unsigned)(N * h), (unsigned)ceil_div(w * c8a, 256));
+    EDS_DISPATCH_DTYPE(dtype, T, (concat_gated_kernel<T, 0><<<grid_a, 256, 0, as_stream(stream)>>>(
+                                     cs, h, w, mode, Ctot, cgate, sgate, (T*)y)));
+    if (c8b > 0) {
+        dim3 grid_b((unsigned)(N * h), (unsigned)ceil_div(w * c8b, 256));
+        EDS_DISPATCH_DTYPE(dtype, T, (concat_gated_kernel<T, 1><<<grid_b, 256, 0, as_stream(stream)>>>(
+                                         cs, h, w, mode, Ctot, cgate, sgate, (T*)y)));
+    }
+    return check_launch("concat_gated_kernel");
+}
+
+extern "C" int eds_apply_gate(const void* x, const float* cgate, const float* sgate, int N, int HW, int C, void* y,
+                              int dtype, void* stream) {
+    EDS_REQUIRE(x && cgate && sgate && y, "apply_gate: null pointer");
+    EDS_REQUIRE(C % 8 == 0 && C > 0 && N > 0 && HW > 0, "apply_gate: bad shape");
+    const int64_t total = (int64_t)N * HW * (C / 8);
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    EDS_DISPATCH_DTYPE(dtype, T, (apply_gate_kernel<T><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+                                     (const T*)x, cgate, sgate, HW, C / 8, total, (T*)y)));
+    return check_launch("apply_gate_kernel");
+}

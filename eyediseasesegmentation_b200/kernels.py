@@ -302,6 +302,69 @@ def scse_scale(x: torch.Tensor, cgate: torch.Tensor, logit: torch.Tensor, out: O
     return out
 
 
+# ------------------------------------------------- SCSE with deferred gates (scse_gated.cu)
+def gated_stats(x: torch.Tensor, cgate: Optional[torch.Tensor], sgate: Optional[torch.Tensor],
+                w_sse: Optional[torch.Tensor], mean: torch.Tensor, c_off: int = 0, zero_mean: bool = False,
+                dot: Optional[torch.Tensor] = None, accumulate: bool = False) -> None:
+    """Pass A over one (possibly gated) source [N,h,w,C]: mean[:, c_off:c_off+C] += channel means of the
+    gated values; dot [N,h,w] (+)= per-pixel dot with w_sse (this source's slice, contiguous)."""
+    _chk(x, cgate, sgate, w_sse, mean, dot)
+    N, h, w, Cc = x.shape
+    assert mean.dtype == torch.float32 and mean.shape[0] == N
+    if w_sse is not None:
+        assert w_sse.numel() == Cc and w_sse.dtype == torch.float32
+    if dot is not None:
+        assert dot.shape == (N, h, w) and dot.dtype == torch.float32
+    check(_lib.lib().eds_gated_stats(_p(x), _p(cgate), _p(sgate), N, h * w, Cc, _p(w_sse), _p(mean), mean.shape[1],
+                                     c_off, int(zero_mean), _p(dot), int(accumulate), _dt(x), _stream()))
+
+
+def sse_finalize(dot0: Optional[torch.Tensor], dot1: Optional[torch.Tensor], mode: int, b_sse: float,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """sigmoid(up(dot0) + dot1 + b) -> [N,H,W] fp32 (in place over dot1 by default)."""
+    _chk(dot0, dot1, out)
+    up = 1 if mode == _lib.UP_NONE else 2
+    if dot0 is not None:
+        N, h, w = dot0.shape
+    else:
+        N, H, W_ = dot1.shape
+        h, w = H // up, W_ // up
+    if out is None:
+        out = dot1 if dot1 is not None else torch.empty((N, up * h, up * w), dtype=torch.float32, device=dot0.device)
+    assert out.shape == (N, up * h, up * w)
+    check(_lib.lib().eds_sse_finalize(_p(dot0), _p(dot1), N, h, w, mode, float(b_sse), _p(out), _stream()))
+    return out
+
+
+def concat_gated(srcs, mode: int, cgate: Optional[torch.Tensor] = None, sgate: Optional[torch.Tensor] = None,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """srcs: [(x, cgate or None, sgate or None), ...]; source 0 [N,h,w,C0] is upsampled x2, the others are
+    [N,2h,2w,Ck].  -> cat(...) * (cgate[n,c] + sgate[n,p]) as one write."""
+    x0 = srcs[0][0]
+    N, h, w, _ = x0.shape
+    ctot = sum(t[0].shape[3] for t in srcs)
+    arr = (_lib.GatedSrc * len(srcs))()
+    for k, (x, cg, sg) in enumerate(srcs):
+        _chk(x, cg, sg)
+        assert x.dtype == x0.dtype and x.shape[:3] == ((N, h, w) if k == 0 else (N, 2 * h, 2 * w))
+        arr[k].x, arr[k].cgate, arr[k].sgate, arr[k].C = _p(x), _p(cg), _p(sg), x.shape[3]
+    _chk(cgate, sgate, out)
+    if out is None:
+        out = torch.empty((N, 2 * h, 2 * w, ctot), dtype=x0.dtype, device=x0.device)
+    check(_lib.lib().eds_concat_gated(arr, len(srcs), N, h, w, mode, _p(cgate), _p(sgate), _p(out), _dt(x0),
+                                      _stream()))
+    return out
+
+
+def apply_gate(x: torch.Tensor, cgate: torch.Tensor, sgate: torch.Tensor, out: Optional[torch.Tensor] = None):
+    _chk(x, cgate, sgate, out)
+    N, H, W_, Cc = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.lib().eds_apply_gate(_p(x), _p(cgate), _p(sgate), N, H * W_, Cc, _p(out), _dt(x), _stream()))
+    return out
+
+
 def axial_attention(qk: torch.Tensor, v: Optional[torch.Tensor], axis: int, heads: int, dqk: int, dv: int,
                     rel: torch.Tensor, sim_scale: torch.Tensor, out_scale: torch.Tensor, out_shift: torch.Tensor,
                     relu: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -192,6 +192,42 @@ EDS_API int eds_concat_stats(const void* x0, int N, int h, int w, int C0, int mo
 EDS_API int eds_scse_scale(const void* x, const float* cgate, const float* sse_logit, int N, int HW, int C,
                            void* y, int dtype, void* stream);
 
+/* ---- SCSE with deferred gates (the product path of the decoders; scse_gated.cu) ----------------
+ * A "gated source" is a map whose SCSE gate has not been applied yet:
+ *     value[n][p][c] = x[n][p][c] * (cgate[n][c] + sgate[n][p])     (cgate == sgate == NULL: plain map)
+ * with cgate [N][C] fp32 (cSE, smp SCSEModule) and sgate [N][P] fp32 (sSE, already a probability).
+ * Replaces attention1 / attention2 of DecoderBlock.forward (unetplusplusstar.py:151-161). */
+typedef struct {
+    const void* x;        /* [N][P][C] activations */
+    const float* cgate;   /* [N][C] or NULL */
+    const float* sgate;   /* [N][P] or NULL */
+    int C;
+} eds_gated_src;
+
+/* Pass A over ONE source at its own resolution (P pixels):
+ *   chan_mean[n][c_off + c] += mean_p value[n][p][c]      (row stride mean_stride; zero_mean clears
+ *                                                           the whole [N][mean_stride] block first)
+ *   dot[n][p] (+)= sum_c w_sse[c] * value[n][p][c]         (w_sse: this source's C-slice; dot may be
+ *                                                           NULL; accumulate=0 starts a new map) */
+EDS_API int eds_gated_stats(const void* x, const float* cgate, const float* sgate, int N, int P, int C,
+                            const float* w_sse, float* chan_mean, int mean_stride, int c_off, int zero_mean,
+                            float* dot, int accumulate, int dtype, void* stream);
+
+/* sgate[n][p] = sigmoid(up(dot0)[p] + dot1[p] + b_sse) on the output grid (up*h x up*w; mode as in
+ * eds_upsample2x_concat; dot0 [N][h][w] or NULL, dot1 [N][up*h][up*w] or NULL; sgate may alias dot1). */
+EDS_API int eds_sse_finalize(const float* dot0, const float* dot1, int N, int h, int w, int mode, float b_sse,
+                             float* sgate, void* stream);
+
+/* Pass B: y [N][2h][2w][sum C] = cat(up2x(value(src 0)), value(src 1..)) * (cgate[n][c] + sgate[n][p]);
+ * source 0 is [N][h][w][C0] (nearest or bilinear x2), the others [N][2h][2w][Ck]; cgate/sgate NULL =
+ * plain concat of the (gated) sources. */
+EDS_API int eds_concat_gated(const eds_gated_src* srcs, int n_srcs, int N, int h, int w, int mode,
+                             const float* cgate, const float* sgate, void* y, int dtype, void* stream);
+
+/* y = x * (cgate[n][c] + sgate[n][p]) (materialise a gated map; y may alias x). */
+EDS_API int eds_apply_gate(const void* x, const float* cgate, const float* sgate, int N, int HW, int C, void* y,
+                           int dtype, void* stream);
+
 /* Axial attention core (axial_attention_v2.py:100-135,178-213) for one axis.
  * qk: per pixel `heads` groups of [q(dqk) | k(dqk) | (v(dv) if v == NULL)] channels,
  * pixel stride qk_cstride elements; v: optional separate tensor with `heads` groups

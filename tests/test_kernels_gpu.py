@@ -438,3 +438,70 @@ def test_concat_stats_and_scse_scale(C0, skip_ch, mode, dtype):
     assert (y.float() - ref).abs().max().item() < (2e-5 if dtype == torch.float32 else 4e-2)
     y2 = K.scse_scale(cat, cg, logit2, out=cat)   # in place
     assert torch.equal(y2, y)
+
+
+@pytest.mark.parametrize("C0,skip_ch,mode,gated", [
+    (32, [16, 64], 1, (True, False, True)), (128, [256, 512], 1, (True, True, False)), (64, [64], 0, (True, True)),
+    (256, [256, 256, 256], 1, (False, True, True, False)), (512, [512], 1, (True, False)), (64, [64, 64, 64, 64], 1, (True,) * 5),
+    (512, [256], 1, (False, False)), (32, [], 1, (True,)), (16, [], 0, (True,))])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_deferred_gate_scse(C0, skip_ch, mode, gated, dtype):
+    """gated_stats + sse_finalize + concat_gated == SCSEModule(cat([up2x(g(x0)), g(skips)...])) where
+    g(x) = x * (cgate[n,c] + sgate[n,p]) is the pending attention2 gate of a source."""
+    N, h, w = 2, 6, 5
+    H, W = 2 * h, 2 * w
+    chans = [C0] + list(skip_ch)
+    srcs, ref_parts = [], []
+    for k, c in enumerate(chans):
+        hh, ww = (h, w) if k == 0 else (H, W)
+        x = rnd(N, hh, ww, c, seed=80 + k).to(dtype)
+        if gated[k]:
+            cg = torch.rand(N, c, device=DEV, generator=torch.Generator(DEV).manual_seed(90 + k))
+            sg = torch.rand(N, hh, ww, device=DEV, generator=torch.Generator(DEV).manual_seed(95 + k))
+            val = x.float() * (cg.view(N, 1, 1, c) + sg.unsqueeze(-1))
+        else:
+            cg = sg = None
+            val = x.float()
+        srcs.append((x, cg, sg))
+        ref_parts.append(val)
+    up = nchw(ref_parts[0])
+    up = F.interpolate(up, scale_factor=2, mode="bilinear", align_corners=False) if mode == 1 else \
+        F.interpolate(up, scale_factor=2, mode="nearest")
+    ref_cat = torch.cat([nhwc(up)] + ref_parts[1:], dim=-1)
+    Ct = sum(chans)
+    tol = 2e-5 if dtype == torch.float32 else 4e-2
+    # plain gated concat (no attention1): decoder blocks without a skip
+    plain = K.concat_gated(srcs, mode)
+    assert plain.shape == ref_cat.shape and (plain.float() - ref_cat).abs().max().item() < tol
+    if not skip_ch:
+        return
+    w_sse, b_sse = rnd(Ct, seed=70, scale=0.1), -0.2
+    mean = torch.full((N, Ct), 7.0, device=DEV)                       # zero_mean must clear it
+    dot0 = torch.full((N, h, w), 3.0, device=DEV)
+    dot1 = torch.full((N, H, W), 5.0, device=DEV)
+    off = 0
+    for k, (x, cg, sg) in enumerate(srcs):
+        c = x.shape[3]
+        K.gated_stats(x, cg, sg, w_sse[off:off + c], mean, off, k == 0, dot0 if k == 0 else dot1, k > 1)
+        off += c
+    assert (mean - ref_cat.mean(dim=(1, 2))).abs().max().item() < 1e-4
+    ref_logit = (ref_cat * w_sse).sum(-1) + b_sse
+    sgate = K.sse_finalize(dot0, dot1, mode, b_sse)
+    assert (sgate - torch.sigmoid(ref_logit)).abs().max().item() < 1e-4
+    cgate = torch.rand(N, Ct, device=DEV)
+    y = K.concat_gated(srcs, mode, cgate, sgate)
+    ref = ref_cat * cgate.view(N, 1, 1, Ct) + ref_cat * torch.sigmoid(ref_logit).unsqueeze(-1)
+    assert (y.float() - ref).abs().max().item() < tol
+    # attention2 form: statistics of a plain map, gate kept pending, materialised on demand
+    x = srcs[-1][0]
+    c = x.shape[3]
+    m2 = torch.empty((N, c), device=DEV)
+    d2 = torch.empty((N, H, W), device=DEV)
+    K.gated_stats(x, None, None, w_sse[:c], m2, 0, True, d2, False)
+    assert (m2 - x.float().mean(dim=(1, 2))).abs().max().item() < 1e-4
+    s2 = K.sse_finalize(None, d2, 2, 0.3)
+    assert (s2 - torch.sigmoid((x.float() * w_sse[:c]).sum(-1) + 0.3)).abs().max().item() < 1e-4
+    cg2 = torch.rand(N, c, device=DEV)
+    z = K.apply_gate(x, cg2, s2)
+    refz = x.float() * (cg2.view(N, 1, 1, c) + s2.unsqueeze(-1))
+    assert (z.float() - refz).abs().max().item() < tol
