@@ -18,8 +18,7 @@
 //   D      : 128 TMEM lanes x block_n fp32 columns.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2-5 = epilogue (TMEM -> registers -> bias/residual/ReLU -> bf16 -> global).
-#include "common.cuh"
-#include <cuda.h>
+#include "tc_ptx.cuh"
 #include <algorithm>
 #include <climits>
 #include <cstring>
@@ -47,93 +46,6 @@ struct IgemmParams {
     uint32_t desc_hi;  // upper 32 bits of the smem descriptor (SBO, version, swizzle mode)
     int8_t tap_plane[kMaxTaps], tap_dh[kMaxTaps], tap_dw[kMaxTaps];
 };
-
-// ---- PTX wrappers ------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug becomes a trap (an error the host sees) instead of a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
-            printf("eds conv_igemm: mbarrier timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst)), "r"(cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major swizzled operand descriptor: start address (>>4) | LBO=1 | SBO | version 1 | layout.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t desc_hi) {
-    return (uint64_t)(((saddr & 0x3FFFFu) >> 4) | (1u << 16)) | ((uint64_t)desc_hi << 32);
-}
 
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
@@ -191,24 +103,36 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            int stage = 0;
-            uint32_t phase = 0;
-            const int k_steps = p.block_k / 16;
-            for (int it = 0; it < num_k_iters; ++it) {
-                mbar_wait(&full_bar[stage], phase);
-                tc_fence_after();
-                const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                const uint32_t sb = sa + (uint32_t)p.a_stage_bytes;
-                for (int k = 0; k < k_steps; ++k)
-                    umma_bf16(tmem_base, make_desc(sa + k * 32, p.desc_hi), make_desc(sb + k * 32, p.desc_hi), p.idesc,
-                              (it > 0 || k > 0) ? 1u : 0u);
+        // ===== MMA issuer: the warp stays converged, one elected lane issues =====
+        int stage = 0;
+        uint32_t phase = 0;
+        const int k_steps = p.block_k / 16;
+        const uint32_t lo0 = desc_lo(smem_u32(smem));
+        const uint32_t stage16 = (uint32_t)stage_bytes >> 4, b16 = (uint32_t)p.a_stage_bytes >> 4;
+        const uint32_t dhi = p.desc_hi, idesc = p.idesc;
+        for (int it = 0; it < num_k_iters; ++it) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t a_lo = lo0 + (uint32_t)stage * stage16, b_lo = a_lo + b16;
+                if (k_steps == 4) {
+                    umma_bf16_lohi(tmem_base, a_lo, b_lo, dhi, idesc, it > 0 ? 1u : 0u);
+                    umma_bf16_lohi(tmem_base, a_lo + 2, b_lo + 2, dhi, idesc, 1u);
+                    umma_bf16_lohi(tmem_base, a_lo + 4, b_lo + 4, dhi, idesc, 1u);
+                    umma_bf16_lohi(tmem_base, a_lo + 6, b_lo + 6, dhi, idesc, 1u);
+                } else if (k_steps == 2) {
+                    umma_bf16_lohi(tmem_base, a_lo, b_lo, dhi, idesc, it > 0 ? 1u : 0u);
+                    umma_bf16_lohi(tmem_base, a_lo + 2, b_lo + 2, dhi, idesc, 1u);
+                } else {
+                    umma_bf16_lohi(tmem_base, a_lo, b_lo, dhi, idesc, it > 0 ? 1u : 0u);
+                }
                 umma_commit(&empty_bar[stage]);  // frees the stage once these MMAs have read it
-                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
-            umma_commit(tmem_full_bar);
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
+        if (elect_one()) umma_commit(tmem_full_bar);
+        __syncwarp();
     } else {
         // ===== epilogue: warp q owns TMEM lanes [32q, 32q+32) =====
         const int q = warp & 3;
@@ -301,8 +225,8 @@ static int ilog2(int v) {
 }
 static int pow2_ceil(int v) { return 1 << ilog2(v); }
 
-static int encode(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                  const cuuint32_t* box, CUtensorMapSwizzle swz, const char* what) {
+int tmap_encode_bf16(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                     const cuuint32_t* box, CUtensorMapSwizzle swz, const char* what) {
     cuuint32_t ones[5] = {1, 1, 1, 1, 1};
     CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
                           strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -416,7 +340,7 @@ extern "C" int eds_conv2d_igemm_bf16(const void* x, int N, int H, int W, int C, 
         cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)N};
         cuuint64_t strides[3] = {(cuuint64_t)stride * C * 2, (cuuint64_t)stride * W * C * 2, (cuuint64_t)H * W * C * 2};
         cuuint32_t box[4] = {(cuuint32_t)p.block_k, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TN};
-        if (int rc = encode(&p.a_map[pl], xb + ((int64_t)ph * W + pw) * C, 4, dims, strides, box, swz, "input"))
+        if (int rc = tmap_encode_bf16(&p.a_map[pl], xb + ((int64_t)ph * W + pw) * C, 4, dims, strides, box, swz, "input"))
             return rc;
     }
     if (!plane_used[0]) p.a_map[0] = p.a_map[p.tap_plane[0]];  // keep the prefetch target valid
@@ -424,7 +348,7 @@ extern "C" int eds_conv2d_igemm_bf16(const void* x, int N, int H, int W, int C, 
         cuuint64_t dims[2] = {(cuuint64_t)p.taps * C, (cuuint64_t)Cout};
         cuuint64_t strides[1] = {(cuuint64_t)p.taps * C * 2};
         cuuint32_t box[2] = {(cuuint32_t)p.block_k, (cuuint32_t)p.block_n};
-        if (int rc = encode(&p.b_map, w, 2, dims, strides, box, swz, "weights")) return rc;
+        if (int rc = tmap_encode_bf16(&p.b_map, w, 2, dims, strides, box, swz, "weights")) return rc;
     }
     conv_igemm_kernel<<<(unsigned)n_ctas, kIgemmThreads, smem, as_stream(stream)>>>(p);
     return check_launch("conv_igemm_kernel");

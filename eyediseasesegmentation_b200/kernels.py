@@ -18,6 +18,9 @@ from ._lib import check as _check
 LAUNCHES = [0]
 #: when set to a list, conv2d(impl="tc") appends (algorithmic_flops, start_event, end_event)
 CONV_TRACE = None
+#: 3x3 s1 p1 convolutions with Cout <= 128 on maps at least this large take the halo-reuse kernel
+#: (0 disables it; EDS_HALO_MIN_HW overrides)
+HALO_MIN_HW = int(__import__("os").environ.get("EDS_HALO_MIN_HW", "64"))
 
 
 def check(rc: int) -> None:
@@ -151,15 +154,20 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], strid
         out = torch.empty((N, Ho, Wo, Cout), dtype=x.dtype, device=x.device)
     if impl == "auto":
         impl = "tc" if x.dtype == torch.bfloat16 else "simt"
-    if impl == "tc":
+    if impl in ("tc", "halo"):
         if x.dtype != torch.bfloat16:
             raise TypeError("the tcgen05 kernel takes bf16 activations")
         trace = CONV_TRACE
         if trace is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        check(_lib.lib().eds_conv2d_igemm_bf16(_p(x), N, H, W_, Cin, _p(w), _p(bias), Cout, R, S, stride, pad,
-                                               int(relu), _p(residual), _p(out), _stream()))
+        if impl == "halo" or (impl == "tc" and HALO_MIN_HW and min(H, W_) >= HALO_MIN_HW and
+                              _lib.load().eds_conv3x3_halo_supported(Cin, Cout, R, S, stride, pad)):
+            check(_lib.lib().eds_conv3x3_halo_bf16(_p(x), N, H, W_, Cin, _p(w), _p(bias), Cout, int(relu),
+                                                   _p(residual), _p(out), _stream()))
+        else:
+            check(_lib.lib().eds_conv2d_igemm_bf16(_p(x), N, H, W_, Cin, _p(w), _p(bias), Cout, R, S, stride, pad,
+                                                   int(relu), _p(residual), _p(out), _stream()))
         if trace is not None:
             ev1.record()
             trace.append((2.0 * N * Ho * Wo * Cout * R * S * Cin, ev0, ev1, (N, H, W_, Cin, Cout, R, stride)))

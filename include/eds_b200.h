@@ -192,6 +192,15 @@ EDS_API int eds_concat_stats(const void* x0, int N, int h, int w, int C0, int mo
 EDS_API int eds_scse_scale(const void* x, const float* cgate, const float* sse_logit, int N, int HW, int C,
                            void* y, int dtype, void* stream);
 
+/* 3x3 / stride 1 / pad 1 convolution for narrow outputs (Cout <= 128), same contract as
+ * eds_conv2d_igemm_bf16 (bf16 NHWC in/out, w [Cout][3][3][C] with BN folded, fp32 bias, optional
+ * residual and ReLU): persistent CTAs, halo-slab reuse of the input tile across the nine taps,
+ * double-buffered TMEM accumulators (conv3x3_halo_sm100.cu).  eds_conv3x3_halo_supported returns 1
+ * when a layer shape is eligible. */
+EDS_API int eds_conv3x3_halo_supported(int C, int Cout, int R, int S, int stride, int pad);
+EDS_API int eds_conv3x3_halo_bf16(const void* x, int N, int H, int W, int C, const void* w, const float* bias,
+                                  int Cout, int relu, const void* residual, void* y, void* stream);
+
 /* ---- SCSE with deferred gates (the product path of the decoders; scse_gated.cu) ----------------
  * A "gated source" is a map whose SCSE gate has not been applied yet:
  *     value[n][p][c] = x[n][p][c] * (cgate[n][c] + sgate[n][p])     (cgate == sgate == NULL: plain map)

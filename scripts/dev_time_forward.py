@@ -18,6 +18,20 @@ convs = [  # N,H,W,C,Cout,R  (decoder hot layers at 1024^2, 8 views)
     (8, 512, 512, 448, 64, 3), (8, 512, 512, 64, 64, 3), (8, 1024, 1024, 32, 16, 3), (8, 64, 64, 3072, 256, 3),
     (8, 64, 64, 1024, 512, 1), (8, 32, 32, 512, 2048, 1),
 ]
+halo = [(8, 512, 512, 448, 64), (8, 512, 512, 320, 32), (8, 512, 512, 64, 64), (8, 1024, 1024, 32, 16),
+        (8, 1024, 1024, 16, 16), (8, 256, 256, 896, 64), (8, 128, 128, 128, 128), (8, 256, 256, 64, 64)]
+for (N, H, W, C, Cout) in halo:
+    x = torch.randn(N, H, W, C, device='cuda').bfloat16()
+    w = (torch.randn(Cout, 3, 3, C, device='cuda') / math.sqrt(9*C)).bfloat16()
+    b = torch.zeros(Cout, device='cuda')
+    y = torch.empty(N, H, W, Cout, device='cuda', dtype=torch.bfloat16)
+    fl = 2.0 * N * H * W * C * Cout * 9
+    K.HALO_MIN_HW = 0
+    ms0 = timeit(lambda: K.conv2d(x, w, b, 1, 1, True, None, out=y, impl='tc'))
+    K.HALO_MIN_HW = 64
+    ms1 = timeit(lambda: K.conv2d(x, w, b, 1, 1, True, None, out=y, impl='halo'))
+    print(f"halo N{N} {H}x{W} C{C}->{Cout}: generic {ms0:.3f} ms {fl/ms0/1e9:.0f} TF | halo {ms1:.3f} ms {fl/ms1/1e9:.0f} TF", flush=True)
+    del x, w, y
 for (N, H, W, C, Cout, R) in convs:
     x = torch.randn(N, H, W, C, device='cuda').bfloat16()
     w = (torch.randn(Cout, R, R, C, device='cuda') / math.sqrt(R*R*C)).bfloat16()

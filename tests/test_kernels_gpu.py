@@ -111,6 +111,55 @@ def test_conv_tcgen05_large_k():
     assert rel_err(y, ref) < 4e-3
 
 
+HALO_CASES = [
+    # N, H, W, C, Cout, relu, use_res
+    (2, 64, 64, 64, 64, True, False),      # exact tiles
+    (1, 96, 72, 128, 64, True, False),     # several tiles per SM slot, two channel chunks
+    (3, 40, 20, 64, 32, False, True),      # ragged in H and W, residual, three images
+    (1, 70, 13, 448, 64, True, False),     # long reduction (7 chunks), ragged
+    (2, 64, 64, 32, 16, True, False),      # 64-byte swizzle (block_k 32), narrowest N
+    (1, 66, 30, 16, 16, True, False),      # 32-byte swizzle (block_k 16)
+    (1, 64, 64, 320, 128, True, True),     # widest supported N (two accumulator sets = all of TMEM)
+    (1, 16, 16, 64, 48, True, False),      # map smaller than the 32x8 tile / 34-row slab
+    (5, 32, 8, 96, 64, False, False),      # block_k 32 with 3 chunks, one tile per image
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES)
+def test_conv3x3_halo_bf16(case):
+    """Persistent halo-reuse 3x3 kernel == fp32 convolution of the same bf16 data, and == the generic
+    tcgen05 kernel (every tap / half / accumulator set / tile-edge combination)."""
+    N, H, W, C, Cout, relu, use_res = case
+    x = rnd(N, H, W, C, seed=11).bfloat16()
+    w = rnd(Cout, 3, 3, C, seed=12, scale=1.0 / math.sqrt(9 * C)).bfloat16()
+    b = rnd(Cout, seed=13)
+    res = rnd(N, H, W, Cout, seed=14).bfloat16() if use_res else None
+    y = K.conv2d(x, w, b, 1, 1, relu, res, impl="halo")
+    torch.cuda.synchronize()
+    ref = conv_ref(x, w, b, 1, 1, relu, res)
+    err = (y.float() - ref).abs().max().item()
+    tol = 1e-2 * max(1.0, ref.abs().max().item())
+    assert err < tol, f"halo conv max abs err {err} (tol {tol}), rel {rel_err(y, ref)}"
+    assert rel_err(y, ref) < 4e-3
+    old = K.HALO_MIN_HW
+    K.HALO_MIN_HW = 0
+    try:
+        y2 = K.conv2d(x, w, b, 1, 1, relu, res, impl="tc")
+    finally:
+        K.HALO_MIN_HW = old
+    assert (y.float() - y2.float()).abs().max().item() < tol
+
+
+def test_conv3x3_halo_many_tiles():
+    """More tiles than SMs: every CTA walks several tiles through both accumulator sets."""
+    x = rnd(2, 256, 256, 64, seed=15).bfloat16()
+    w = rnd(64, 3, 3, 64, seed=16, scale=1.0 / 24).bfloat16()
+    y = K.conv2d(x, w, None, 1, 1, True, None, impl="halo")
+    ref = conv_ref(x, w, None, 1, 1, True, None)
+    assert rel_err(y, ref) < 4e-3
+    assert (y.float() - ref).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
+
+
 # --------------------------------------------------------------------------- stem
 def d4_maps(S):
     from eyediseasesegmentation_b200 import ttach_compat as tta
