@@ -17,7 +17,6 @@ namespace eds {
 
 constexpr int kBins = EDS_PR_BINS;
 constexpr int kNT = EDS_PR_NTHRESH;
-constexpr int kBitmapWords = (kBins + 31) / 32;
 constexpr int kHistThreads = 1024;
 
 // Bit pattern of the largest fp32 <= threshold k and the key of that pattern.
@@ -61,8 +60,8 @@ static int ensure_thresholds() {
 
 struct HistSmem {
     uint32_t hist[2 * kBins];
-    uint32_t bitmap[kBitmapWords];
     uint32_t straddle[kNT * 2];
+    uint8_t flag[kBins + 2];      // 1 where the bin shares its key with one of the 19 thresholds
 };
 
 __device__ __forceinline__ void straddle_update(HistSmem* s, int bits, int key, int cls) {
@@ -72,14 +71,20 @@ __device__ __forceinline__ void straddle_update(HistSmem* s, int bits, int key, 
 }
 
 __device__ __forceinline__ void hist_one(HistSmem* s, float p, uint8_t g) {
-    int bits = __float_as_int(p);
-    int key = score_key(bits);
-    int cls = g != 0;
+    const int bits = __float_as_int(p);
+    const int key = score_key(bits);
+    const int cls = g != 0;
     atomicAdd(&s->hist[cls * kBins + key], 1u);
-    if ((s->bitmap[key >> 5] >> (key & 31)) & 1u) straddle_update(s, bits, key, cls);
+    if (s->flag[key]) straddle_update(s, bits, key, cls);
 }
 
+constexpr int kQuadUnroll = 2;    // float4 + uchar4 pairs in flight per thread
+
 // grid = (splits, n_images); each CTA bins a contiguous slice of one image.
+// The loop body is ~12 instructions per pixel (key: shift, subtract, clamp; class offset; one
+// shared-memory atomic; one byte load for the threshold flag), which is what lets one SM retire
+// several pixels per clock: the first version spent 60 instructions per pixel and was bound by
+// instruction issue at ~1 pixel/clk/SM (profiles/r01_probe1_full.md), not by the atomics.
 __global__ void __launch_bounds__(kHistThreads, 1)
 pr_hist_kernel(const float* __restrict__ prob, const uint8_t* __restrict__ gt, int64_t n_pixels,
                uint32_t* __restrict__ g_hist, uint32_t* __restrict__ g_straddle, int vec_ok) {
@@ -88,10 +93,10 @@ pr_hist_kernel(const float* __restrict__ prob, const uint8_t* __restrict__ gt, i
     const int tid = threadIdx.x;
     const int img = blockIdx.y;
     for (int i = tid; i < 2 * kBins; i += kHistThreads) s->hist[i] = 0;
-    for (int i = tid; i < kBitmapWords; i += kHistThreads) s->bitmap[i] = 0;
+    for (int i = tid; i < kBins + 2; i += kHistThreads) s->flag[i] = 0;
     if (tid < kNT * 2) s->straddle[tid] = 0;
     __syncthreads();
-    if (tid < kNT) atomicOr(&s->bitmap[c_thresh.key[tid] >> 5], 1u << (c_thresh.key[tid] & 31));
+    if (tid < kNT) s->flag[c_thresh.key[tid]] = 1;
     __syncthreads();
 
     const float* p_img = prob + (int64_t)img * n_pixels;
@@ -103,54 +108,58 @@ pr_hist_kernel(const float* __restrict__ prob, const uint8_t* __restrict__ gt, i
     int64_t q_end = q_begin + q_per;
     if (q_end > n_quads) q_end = n_quads;
 
-    if (vec_ok) {
-        const float4* p4 = reinterpret_cast<const float4*>(p_img);
-        const uchar4* g4 = reinterpret_cast<const uchar4*>(g_img);
-        for (int64_t q0 = q_begin; q0 < q_end; q0 += kHistThreads) {
-            // whole-warp uniform trip count: q0 is CTA-uniform, predicate per lane
-            const int64_t q = q0 + tid;
-            const bool live = q < q_end;
-            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-            uchar4 g = make_uchar4(0, 0, 0, 0);
-            if (live) {
-                p = __ldg(p4 + q);
-                g = __ldg(g4 + q);
+    if (vec_ok && q_end > q_begin) {
+        const float4* p4 = reinterpret_cast<const float4*>(p_img) + q_begin;
+        const uchar4* g4 = reinterpret_cast<const uchar4*>(g_img) + q_begin;
+        const int nq = (int)(q_end - q_begin);           // < 2^31: a CTA slice is part of one image
+        uint32_t* hist = s->hist;
+        const uint8_t* flag = s->flag;
+        for (int q0 = 0; q0 < nq; q0 += kHistThreads * kQuadUnroll) {
+            float4 p[kQuadUnroll];
+            uchar4 g[kQuadUnroll];
+            // unconditional loads (index clamped into the slice) keep both pairs in flight
+#pragma unroll
+            for (int u = 0; u < kQuadUnroll; ++u) {
+                const int q = min(q0 + u * kHistThreads + tid, nq - 1);
+                p[u] = __ldg(p4 + q);
+                g[u] = __ldg(g4 + q);
             }
-            const int b0 = __float_as_int(p.x), b1 = __float_as_int(p.y);
-            const int b2 = __float_as_int(p.z), b3 = __float_as_int(p.w);
-            const int a0 = (g.x != 0) * kBins + score_key(b0);
-            const int a1 = (g.y != 0) * kBins + score_key(b1);
-            const int a2 = (g.z != 0) * kBins + score_key(b2);
-            const int a3 = (g.w != 0) * kBins + score_key(b3);
-            const bool same4 = (a0 == a1) && (a1 == a2) && (a2 == a3);
-            // warp aggregation for flat regions (background of a fundus image)
-            if (__all_sync(0xffffffffu, same4 && live)) {
-                const int lead = __shfl_sync(0xffffffffu, a0, 0);
-                if (__all_sync(0xffffffffu, a0 == lead)) {
-                    if ((tid & 31) == 0) atomicAdd(&s->hist[lead], 128u);
-                } else {
-                    atomicAdd(&s->hist[a0], 4u);
+#pragma unroll
+            for (int u = 0; u < kQuadUnroll; ++u) {
+                const bool live = q0 + u * kHistThreads + tid < nq;
+                const int b0 = __float_as_int(p[u].x), b1 = __float_as_int(p[u].y);
+                const int b2 = __float_as_int(p[u].z), b3 = __float_as_int(p[u].w);
+                const int k0 = score_key(b0), k1 = score_key(b1), k2 = score_key(b2), k3 = score_key(b3);
+                const int a0 = k0 + (g[u].x ? kBins : 0), a1 = k1 + (g[u].y ? kBins : 0);
+                const int a2 = k2 + (g[u].z ? kBins : 0), a3 = k3 + (g[u].w ? kBins : 0);
+                const bool same4 = (a0 == a1) & (a1 == a2) & (a2 == a3);
+                // flat regions (background of a fundus image): one atomic per thread, or per warp
+                // when the whole warp sees one bin -- same-address atomics would serialise otherwise
+                if (__all_sync(0xffffffffu, same4 && live)) {
+                    const int lead = __shfl_sync(0xffffffffu, a0, 0);
+                    if (__all_sync(0xffffffffu, a0 == lead)) {
+                        if ((tid & 31) == 0) atomicAdd(hist + lead, 128u);
+                    } else {
+                        atomicAdd(hist + a0, 4u);
+                    }
+                } else if (live) {
+                    atomicAdd(hist + a0, 1u);
+                    atomicAdd(hist + a1, 1u);
+                    atomicAdd(hist + a2, 1u);
+                    atomicAdd(hist + a3, 1u);
                 }
-            } else if (live) {
-                atomicAdd(&s->hist[a0], 1u);
-                atomicAdd(&s->hist[a1], 1u);
-                atomicAdd(&s->hist[a2], 1u);
-                atomicAdd(&s->hist[a3], 1u);
-            }
-            if (live) {
-                const int k0 = a0 >= kBins ? a0 - kBins : a0, k1 = a1 >= kBins ? a1 - kBins : a1;
-                const int k2 = a2 >= kBins ? a2 - kBins : a2, k3 = a3 >= kBins ? a3 - kBins : a3;
-                const uint32_t hit = ((s->bitmap[k0 >> 5] >> (k0 & 31)) | (s->bitmap[k1 >> 5] >> (k1 & 31)) |
-                                      (s->bitmap[k2 >> 5] >> (k2 & 31)) | (s->bitmap[k3 >> 5] >> (k3 & 31))) & 1u;
-                if (hit) {
-                    if ((s->bitmap[k0 >> 5] >> (k0 & 31)) & 1u) straddle_update(s, b0, k0, g.x != 0);
-                    if ((s->bitmap[k1 >> 5] >> (k1 & 31)) & 1u) straddle_update(s, b1, k1, g.y != 0);
-                    if ((s->bitmap[k2 >> 5] >> (k2 & 31)) & 1u) straddle_update(s, b2, k2, g.z != 0);
-                    if ((s->bitmap[k3 >> 5] >> (k3 & 31)) & 1u) straddle_update(s, b3, k3, g.w != 0);
+                if (live) {
+                    const uint32_t hit = (uint32_t)flag[k0] | flag[k1] | flag[k2] | flag[k3];
+                    if (hit) {
+                        if (flag[k0]) straddle_update(s, b0, k0, g[u].x != 0);
+                        if (flag[k1]) straddle_update(s, b1, k1, g[u].y != 0);
+                        if (flag[k2]) straddle_update(s, b2, k2, g[u].z != 0);
+                        if (flag[k3]) straddle_update(s, b3, k3, g[u].w != 0);
+                    }
                 }
             }
         }
-    } else {
+    } else if (!vec_ok) {
         int64_t i_end = q_end * 4;
         if (i_end > n_pixels) i_end = n_pixels;
         for (int64_t i = q_begin * 4 + tid; i < i_end; i += kHistThreads) hist_one(s, p_img[i], g_img[i]);
