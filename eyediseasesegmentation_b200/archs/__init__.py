@@ -25,6 +25,22 @@ from .engine import Engine
 __all__ = ["list_models", "get_model", "get_preprocessing_fn", "MODEL_REGISTRY", "B200SegModel", "Unet"]
 
 
+_GRAPH_POOLS: Dict[str, object] = {}
+
+
+def _graphs_enabled() -> bool:
+    return os.environ.get("EDS_CUDA_GRAPHS", "1") != "0"
+
+
+def _graph_pool(device):
+    """One memory pool per device shared by every captured forward: the graphs are replayed one at a time
+    on one stream, so the intermediates of one graph can live in the space another one uses."""
+    key = str(device)
+    if key not in _GRAPH_POOLS:
+        _GRAPH_POOLS[key] = torch.cuda.graph_pool_handle()
+    return _GRAPH_POOLS[key]
+
+
 class B200SegModel(nn.Module):
     """Segmentation network whose forward pass is hand-written CUDA for sm_100a.
 
@@ -76,14 +92,17 @@ class B200SegModel(nn.Module):
         self.precision = os.environ.get("EDS_PRECISION", "bf16")
         self._engine: Optional[Engine] = None
         self._engine_key = None
+        self._graphs = {}
 
-    # ---- any change to the parameters invalidates the prepared (folded) weights
+    # ---- any change to the parameters invalidates the prepared (folded) weights and captured graphs
     def _apply(self, fn, *a, **k):
         self._engine = None
+        self._graphs = {}
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
         self._engine = None
+        self._graphs = {}
         return super().load_state_dict(state_dict, strict=strict, **kw)
 
     def train(self, mode: bool = True):
@@ -95,6 +114,7 @@ class B200SegModel(nn.Module):
         dev = next(self.parameters()).device
         key = (str(dev), self.precision)
         if self._engine is None or self._engine_key != key:
+            self._graphs = {}
             if dev.type != "cuda":
                 raise RuntimeError("B200SegModel runs only on a CUDA (sm_100a) device: call .to('cuda') first; "
                                    "there is no CPU fallback")
@@ -111,11 +131,41 @@ class B200SegModel(nn.Module):
     def forward_tta(self, x: torch.Tensor, transforms, apply_sigmoid: bool = False) -> torch.Tensor:
         """All TTA views in one batched pass: views folded into the stem loader, merged by
         ``eds_tta_merge``.  Returns the mean logits ``[B,1,H,W]`` (what
-        ``SegmentationTTAWrapper.forward`` returns) or the probabilities if apply_sigmoid."""
+        ``SegmentationTTAWrapper.forward`` returns) or the probabilities if apply_sigmoid.
+
+        The ~250 kernel launches of a pass are captured into a CUDA graph the second time a given
+        (input shape, views, precision) is seen and replayed afterwards: at the tile-batch sizes of
+        the drivers a third of the launches are shorter than their host-side issue cost, and the
+        graph removes those gaps (set EDS_CUDA_GRAPHS=0 to run eagerly)."""
         from .. import ttach_compat as tta
         from .. import kernels as K
         B, _, H, W = x.shape
         aug, deaug = tta.view_maps(transforms, H, W)
+        if not x.is_cuda:
+            raise RuntimeError("the B200 networks only run on a CUDA device (no CPU fallback); got a CPU tensor")
+        use_graph = (_graphs_enabled() and K.CONV_TRACE is None and not self.engine().keep_features)
+        if not use_graph:
+            return self._forward_tta_eager(x, aug, deaug, apply_sigmoid)
+        key = (tuple(x.shape), str(x.device), self.precision, tuple(map(tuple, aug)), bool(apply_sigmoid))
+        entry = self._graphs.get(key)
+        if entry is None:                       # first sight: eager (also warms every lazy init)
+            self._graphs[key] = "warm"
+            return self._forward_tta_eager(x, aug, deaug, apply_sigmoid)
+        if entry == "warm":
+            static_x = x.detach().float().contiguous().clone()
+            torch.cuda.current_stream().synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, pool=_graph_pool(x.device)):
+                static_y = self._forward_tta_eager(static_x, aug, deaug, apply_sigmoid)
+            entry = self._graphs[key] = (graph, static_x, static_y)
+        graph, static_x, static_y = entry
+        static_x.copy_(x)
+        graph.replay()
+        return static_y.clone()
+
+    def _forward_tta_eager(self, x, aug, deaug, apply_sigmoid):
+        from .. import kernels as K
+        B, _, H, W = x.shape
         logits = self.engine().run(x, aug)                    # [V*B, classes, H, W]
         if logits.shape[1] != 1 or H != W:
             raise NotImplementedError("fused TTA merge handles square single-class maps")

@@ -118,3 +118,32 @@ def test_no_cpu_fallback():
     model = _build("Unet", dict(encoder_name="resnet34", encoder_weights=None, classes=1))
     with pytest.raises(RuntimeError, match="CUDA"):
         model(_input(1, 64))
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_cuda_graph_replay_equals_eager(precision, monkeypatch):
+    """forward_tta captures a CUDA graph on the second call of a shape; replays (with NEW inputs copied
+    into the static buffer) must reproduce the eager launches (up to the run-to-run jitter of the fp32
+    atomic accumulation of the SE / SCSE channel means), and two models sharing the graph memory pool
+    must not disturb each other."""
+    monkeypatch.setenv("EDS_CUDA_GRAPHS", "1")
+    tfm = tta.aliases.d4_transform()
+    models = []
+    for seed in (1999, 2001):
+        m = _build("unetplusplusstar", star_cfg(8), seed=seed).to("cuda")
+        m.precision = precision
+        models.append(m)
+    xs = [_input(2, 256, seed=s).cuda() for s in (7, 8, 9)]
+    monkeypatch.setenv("EDS_CUDA_GRAPHS", "0")
+    want = [[m.forward_tta(x, tfm, True).clone() for x in xs] for m in models]
+    monkeypatch.setenv("EDS_CUDA_GRAPHS", "1")
+    for rep in range(2):                      # call 1 eager, call 2 captures + replays, then pure replays
+        for mi, m in enumerate(models):
+            for xi, x in enumerate(xs):
+                got = m.forward_tta(x, tfm, True)
+                err = (got - want[mi][xi]).abs().max().item()
+                assert err < (5e-3 if precision == "bf16" else 1e-5), f"model {mi} input {xi} pass {rep}: {err}"
+                # a wrong static-input copy or a clobbered pool would give another input's / model's answer
+                other = (got - want[mi][(xi + 1) % 3]).abs().max().item()
+                assert other > 10 * err + 1e-3
+    assert all(any(isinstance(v, tuple) for v in m._graphs.values()) for m in models), "no graph was captured"
