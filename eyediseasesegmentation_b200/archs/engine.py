@@ -315,14 +315,12 @@ class Engine:
         p = f"decoder.blocks.{name}"
         if (p + ".down_sample") in self.w:
             x = _plain(x)
-            cat = K.upsample2x_concat(x, [self._mhca_skip(p, x, skips)], self.up_mode)
+            cat = K.concat_gated([(x, None, None), (self._mhca_skip(p, x, skips), None, None)], self.up_mode)
         else:
             if skips and (p + ".attention1.sse") in self.w:
                 cat = self._concat_scse(p + ".attention1", x, skips)
-            elif isinstance(x, Gated) or any(isinstance(t, Gated) for t in skips):
-                cat = K.concat_gated([_parts(x)] + [_parts(t) for t in skips], self.up_mode)
             else:
-                cat = K.upsample2x_concat(x, list(skips), self.up_mode)
+                cat = K.concat_gated([_parts(x)] + [_parts(t) for t in skips], self.up_mode)
         y = self._cv(cat, p + ".conv1", pad=1, relu=True)
         y = self._cv(y, p + ".conv2", pad=1, relu=True)
         if (p + ".down_sample") not in self.w:

@@ -312,9 +312,14 @@ def attention_ref(q, k, v, rel, sim_scale, out_scale, out_shift, dqk, dv):
 @pytest.mark.parametrize("axis", [0, 1])
 @pytest.mark.parametrize("cross", [False, True])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_axial_attention(axis, cross, dtype):
-    N, H, W, heads, dqk = 2, 16, 16, 4, 8
-    dv = 16
+@pytest.mark.parametrize("shape", [(2, 16, 16, 4, 16), (1, 64, 64, 8, 64), (2, 32, 32, 4, 16), (1, 19, 19, 8, 64),
+                                   (1, 38, 38, 4, 8), (1, 24, 40, 4, 16), (1, 8, 8, 8, 64), (1, 16, 16, 2, 16)])
+def test_axial_attention(axis, cross, dtype, shape):
+    """bf16 runs the tensor-core kernel (attention_mma.cu) where the shape allows (heads % 4 == 0, L <= 64,
+    incl. lengths that are not multiples of 16 -- base_dim 19 of the vessel configs), fp32 and the
+    2-head case the CUDA-core kernel."""
+    N, H, W, heads, dv = shape
+    dqk = 8
     L = H if axis == 0 else W
     G = 2 * dqk + (0 if cross else dv)
     qk = rnd(N, H, W, heads * G, seed=40, scale=0.5).to(dtype)
