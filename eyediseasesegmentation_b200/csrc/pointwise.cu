@@ -10,9 +10,13 @@ namespace eds {
 // ---------------------------------------------------------------- max pool
 // SENet layer0.pool = MaxPool2d(3, 2, ceil_mode=True) applied at unetplusplusstar.py:347-348,
 // torchvision ResNet maxpool (3,2,pad 1), MHCA init_conv MaxPool2d(2) unetplusplusstar.py:106.
-template <typename T>
-__global__ void maxpool_kernel(const T* __restrict__ x, int N, int H, int W, int C8, int k, int stride, int pad,
-                               int Ho, int Wo, T* __restrict__ y) {
+template <typename T, int K>
+__global__ void __launch_bounds__(256)
+maxpool_kernel(const T* __restrict__ x, int N, int H, int W, int C8, int stride, int pad, int Ho, int Wo,
+               T* __restrict__ y) {
+    // Window coordinates are clamped into the map instead of skipped: a clamped tap repeats a pixel of
+    // the same window (pad < K and the ceil_mode rule keep one row / column of every window inside), so
+    // the maximum is unchanged and all K*K vector loads are issued back to back.
     const int64_t total = (int64_t)N * Ho * Wo * C8;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
@@ -21,21 +25,23 @@ __global__ void maxpool_kernel(const T* __restrict__ x, int N, int H, int W, int
         const int ow = (int)(r % Wo); r /= Wo;
         const int oh = (int)(r % Ho);
         const int n = (int)(r / Ho);
-        float best[8];
+        float v[K * K][8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) best[i] = -FLT_MAX;
-        for (int dy = 0; dy < k; ++dy) {
-            const int iy = oh * stride - pad + dy;
-            if (iy < 0 || iy >= H) continue;
-            for (int dx = 0; dx < k; ++dx) {
-                const int ix = ow * stride - pad + dx;
-                if (ix < 0 || ix >= W) continue;
-                float v[8];
-                Vec8<T>::ld(x + (((int64_t)n * H + iy) * W + ix) * C8 * 8 + c8 * 8, v);
+        for (int dy = 0; dy < K; ++dy) {
+            const int iy = min(max(oh * stride - pad + dy, 0), H - 1);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) best[i] = fmaxf(best[i], v[i]);
+            for (int dx = 0; dx < K; ++dx) {
+                const int ix = min(max(ow * stride - pad + dx, 0), W - 1);
+                Vec8<T>::ld(x + (((int64_t)n * H + iy) * W + ix) * C8 * 8 + c8 * 8, v[dy * K + dx]);
             }
         }
+        float best[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) best[i] = v[0][i];
+#pragma unroll
+        for (int q = 1; q < K * K; ++q)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) best[i] = fmaxf(best[i], v[q][i]);
         Vec8<T>::st(y + idx * 8, best);
     }
 }
@@ -320,22 +326,31 @@ head_conv3x3_kernel(const T* __restrict__ x, int N, int H, int W, int C, const f
         const int ox = (int)(p % W);
         const int oy = (int)((p / W) % H);
         const int n = (int)(p / ((int64_t)W * H));
+        // taps outside the map read a clamped (valid) pixel and are weighted by 0: every load is
+        // unconditional, so the nine taps of a pixel are in flight together
+        const T* xp[9];
+        float valid[9];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const int iy = oy + dy - 1, ix = ox + dx - 1;
+                valid[dy * 3 + dx] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? 1.f : 0.f;
+                xp[dy * 3 + dx] = x + (((int64_t)n * H + min(max(iy, 0), H - 1)) * W + min(max(ix, 0), W - 1)) * C;
+            }
         for (int k = 0; k < classes; ++k) {
             float acc = bias ? bias[k] : 0.f;
-            for (int dy = 0; dy < 3; ++dy) {
-                const int iy = oy + dy - 1;
-                if (iy < 0 || iy >= H) continue;
-                for (int dx = 0; dx < 3; ++dx) {
-                    const int ix = ox + dx - 1;
-                    if (ix < 0 || ix >= W) continue;
-                    const T* xp = x + (((int64_t)n * H + iy) * W + ix) * C;
-                    const float* wp = s_w + (k * 9 + dy * 3 + dx) * C;
-                    for (int c = 0; c < C; c += 8) {
-                        float v[8];
-                        Vec8<T>::ld(xp + c, v);
+            for (int c = 0; c < C; c += 8) {
+                float v[9][8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) acc += v[i] * wp[c + i];
-                    }
+                for (int q = 0; q < 9; ++q) Vec8<T>::ld(xp[q] + c, v[q]);
+#pragma unroll
+                for (int q = 0; q < 9; ++q) {
+                    const float* wp = s_w + (k * 9 + q) * C + c;
+                    float d = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) d = fmaf(v[q][i], wp[i], d);
+                    acc = fmaf(valid[q], d, acc);
                 }
             }
             logits[(((int64_t)n * classes + k) * H + oy) * W + ox] = acc;
@@ -382,8 +397,15 @@ extern "C" int eds_maxpool2d(const void* x, int N, int H, int W, int C, int k, i
     const int Ho = out_size(H), Wo = out_size(W);
     EDS_REQUIRE(Ho > 0 && Wo > 0, "maxpool2d: empty output");
     const int64_t total = (int64_t)N * Ho * Wo * (C / 8);
-    EDS_DISPATCH_DTYPE(dtype, T, (maxpool_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
-                                     (const T*)x, N, H, W, C / 8, k, stride, pad, Ho, Wo, (T*)y)));
+    EDS_REQUIRE(k == 2 || k == 3, "maxpool2d: k=%d (2 and 3 are on the path)", k);
+    EDS_DISPATCH_DTYPE(dtype, T, {
+        if (k == 2)
+            maxpool_kernel<T, 2><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)x, N, H, W, C / 8, stride,
+                                                                                     pad, Ho, Wo, (T*)y);
+        else
+            maxpool_kernel<T, 3><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const T*)x, N, H, W, C / 8, stride,
+                                                                                     pad, Ho, Wo, (T*)y);
+    });
     return check_launch("maxpool_kernel");
 }
 
