@@ -155,12 +155,16 @@ class B200SegModel(nn.Module):
             static_x = x.detach().float().contiguous().clone()
             torch.cuda.current_stream().synchronize()
             graph = torch.cuda.CUDAGraph()
+            launches0 = K.LAUNCHES[0]
             with torch.cuda.graph(graph, pool=_graph_pool(x.device)):
                 static_y = self._forward_tta_eager(static_x, aug, deaug, apply_sigmoid)
-            entry = self._graphs[key] = (graph, static_x, static_y)
-        graph, static_x, static_y = entry
+            n_kernels = K.LAUNCHES[0] - launches0          # kernel nodes of the graph
+            K.LAUNCHES[0] = launches0                       # capture launched nothing
+            entry = self._graphs[key] = (graph, static_x, static_y, n_kernels)
+        graph, static_x, static_y, n_kernels = entry
         static_x.copy_(x)
         graph.replay()
+        K.LAUNCHES[0] += n_kernels
         return static_y.clone()
 
     def _forward_tta_eager(self, x, aug, deaug, apply_sigmoid):
