@@ -16,8 +16,9 @@
 //            tensor maps), so every tap is still a dense box.
 //   B tile : TMA box [block_k][block_n] of the [Cout][taps*C] weight matrix.
 //   D      : 128 TMEM lanes x block_n fp32 columns.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2-5 = epilogue (TMEM -> registers -> bias/residual/ReLU -> bf16 -> global).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2-9 = epilogue (TMEM -> registers -> bias/residual/ReLU -> bf16 -> swizzled shared memory ->
+// one TMA bulk tensor store per 64-channel group).
 #include "tc_ptx.cuh"
 #include <algorithm>
 #include <climits>
@@ -26,7 +27,7 @@
 
 namespace eds {
 
-constexpr int kIgemmThreads = 192;
+constexpr int kIgemmThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kMaxTaps = 9;
 constexpr int kMaxStages = 8;
 constexpr int kTileM = 128;
@@ -41,41 +42,52 @@ struct IgemmParams {
     int tw_log2, th_log2, TW, TH, TN;
     int tiles_w, tiles_h;
     int N, Ho, Wo, Cout, relu;
+    int total_tiles;
+    CUtensorMap y_map;      // output [Cout][Wo][Ho][N], box [st_ch][TW][TH][TN]
+    int st_ch, st_bytes, st_bufs, st_mode;   // epilogue staging: channels per TMA store, bytes per buffer, buffers per half, swizzle mode
     int stages, a_stage_bytes, b_stage_bytes, tmem_cols;
     uint32_t idesc;
     uint32_t desc_hi;  // upper 32 bits of the smem descriptor (SBO, version, swizzle mode)
     int8_t tap_plane[kMaxTaps], tap_dh[kMaxTaps], tap_dw[kMaxTaps];
 };
 
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent: grid = min(#tiles, #SMs); CTA i walks tiles i, i + grid, ... (cout tile fastest, so CTAs
+// running side by side share their input tile in L2).  The TMA ring runs across tile boundaries and
+// the accumulator is double-buffered in TMEM (2 x block_n columns), so the epilogue of tile t
+// overlaps the main loop of tile t + 1 and the per-CTA set-up (barriers, TMEM allocation,
+// descriptor prefetch) is paid once per SM instead of once per tile.
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     // operand stages need 1024 B alignment for the 128B swizzle atom
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint8_t* staging = smem + (size_t)p.stages * stage_bytes;          // [2 halves][st_bufs][st_bytes]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + (size_t)2 * p.st_bufs * p.st_bytes);
     uint64_t* empty_bar = full_bar + kMaxStages;
-    uint64_t* tmem_full_bar = empty_bar + kMaxStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* tmem_full_bar = empty_bar + kMaxStages;      // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tile = blockIdx.x % p.n_tiles;
-    int m_tile = blockIdx.x / p.n_tiles;
-    const int tile_w = m_tile % p.tiles_w;
-    m_tile /= p.tiles_w;
-    const int tile_h = m_tile % p.tiles_h;
-    const int tile_n = m_tile / p.tiles_h;
-    const int w0 = tile_w * p.TW, h0 = tile_h * p.TH, n0 = tile_n * p.TN;
     const int num_k_iters = p.taps * p.k_chunks;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&p.b_map);
         prefetch_tmap(&p.a_map[0]);
+        prefetch_tmap(&p.y_map);
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(tmem_full_bar, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tmem_full_bar[b], 1);
+            mbar_init(&tmem_empty_bar[b], 8);      // one arrival per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -90,16 +102,26 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
             // ===== TMA producer =====
             int stage = 0;
             uint32_t phase = 0;
-            for (int it = 0; it < num_k_iters; ++it) {
-                const int tap = it / p.k_chunks, kc = it - tap * p.k_chunks;
-                mbar_wait(&empty_bar[stage], phase ^ 1u);
-                mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(kTileM * p.block_k * 2 + p.block_n * p.block_k * 2));
-                uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                uint8_t* sb = sa + p.a_stage_bytes;
-                tma_load_4d(sa, &p.a_map[p.tap_plane[tap]], &full_bar[stage], kc * p.block_k, w0 + p.tap_dw[tap],
-                            h0 + p.tap_dh[tap], n0);
-                tma_load_2d(sb, &p.b_map, &full_bar[stage], tap * p.C + kc * p.block_k, n_tile * p.block_n);
-                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int n_tile = tile % p.n_tiles;
+                int m_tile = tile / p.n_tiles;
+                const int tile_w = m_tile % p.tiles_w;
+                m_tile /= p.tiles_w;
+                const int tile_h = m_tile % p.tiles_h;
+                const int tile_n = m_tile / p.tiles_h;
+                const int w0 = tile_w * p.TW, h0 = tile_h * p.TH, n0 = tile_n * p.TN;
+                for (int it = 0; it < num_k_iters; ++it) {
+                    const int tap = it / p.k_chunks, kc = it - tap * p.k_chunks;
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    mbar_arrive_expect_tx(&full_bar[stage],
+                                          (uint32_t)(kTileM * p.block_k * 2 + p.block_n * p.block_k * 2));
+                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                    uint8_t* sb = sa + p.a_stage_bytes;
+                    tma_load_4d(sa, &p.a_map[p.tap_plane[tap]], &full_bar[stage], kc * p.block_k, w0 + p.tap_dw[tap],
+                                h0 + p.tap_dh[tap], n0);
+                    tma_load_2d(sb, &p.b_map, &full_bar[stage], tap * p.C + kc * p.block_k, n_tile * p.block_n);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
             }
         }
     } else if (warp == 1) {
@@ -110,76 +132,134 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
         const uint32_t lo0 = desc_lo(smem_u32(smem));
         const uint32_t stage16 = (uint32_t)stage_bytes >> 4, b16 = (uint32_t)p.a_stage_bytes >> 4;
         const uint32_t dhi = p.desc_hi, idesc = p.idesc;
-        for (int it = 0; it < num_k_iters; ++it) {
-            mbar_wait(&full_bar[stage], phase);
+        int t = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
+            const int buf = t & 1;
+            mbar_wait(&tmem_empty_bar[buf], (uint32_t)(((t >> 1) & 1) ^ 1));     // epilogue drained this buffer
             tc_fence_after();
-            if (elect_one()) {
-                const uint32_t a_lo = lo0 + (uint32_t)stage * stage16, b_lo = a_lo + b16;
-                if (k_steps == 4) {
-                    umma_bf16_lohi(tmem_base, a_lo, b_lo, dhi, idesc, it > 0 ? 1u : 0u);
-                    umma_bf16_lohi(tmem_base, a_lo + 2, b_lo + 2, dhi, idesc, 1u);
-                    umma_bf16_lohi(tmem_base, a_lo + 4, b_lo + 4, dhi, idesc, 1u);
-                    umma_bf16_lohi(tmem_base, a_lo + 6, b_lo + 6, dhi, idesc, 1u);
-                } else if (k_steps == 2) {
-                    umma_bf16_lohi(tmem_base, a_lo, b_lo, dhi, idesc, it > 0 ? 1u : 0u);
-                    umma_bf16_lohi(tmem_base, a_lo + 2, b_lo + 2, dhi, idesc, 1u);
-                } else {
-                    umma_bf16_lohi(tmem_base, a_lo, b_lo, dhi, idesc, it > 0 ? 1u : 0u);
+            const uint32_t d = tmem_base + (uint32_t)(buf * p.block_n);
+            for (int it = 0; it < num_k_iters; ++it) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t a_lo = lo0 + (uint32_t)stage * stage16, b_lo = a_lo + b16;
+                    if (k_steps == 4) {
+                        umma_bf16_lohi(d, a_lo, b_lo, dhi, idesc, it > 0 ? 1u : 0u);
+                        umma_bf16_lohi(d, a_lo + 2, b_lo + 2, dhi, idesc, 1u);
+                        umma_bf16_lohi(d, a_lo + 4, b_lo + 4, dhi, idesc, 1u);
+                        umma_bf16_lohi(d, a_lo + 6, b_lo + 6, dhi, idesc, 1u);
+                    } else if (k_steps == 2) {
+                        umma_bf16_lohi(d, a_lo, b_lo, dhi, idesc, it > 0 ? 1u : 0u);
+                        umma_bf16_lohi(d, a_lo + 2, b_lo + 2, dhi, idesc, 1u);
+                    } else {
+                        umma_bf16_lohi(d, a_lo, b_lo, dhi, idesc, it > 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees the stage once these MMAs have read it
                 }
-                umma_commit(&empty_bar[stage]);  // frees the stage once these MMAs have read it
+                __syncwarp();
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
+            if (elect_one()) umma_commit(&tmem_full_bar[buf]);
             __syncwarp();
-            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        if (elect_one()) umma_commit(tmem_full_bar);
-        __syncwarp();
     } else {
-        // ===== epilogue: warp q owns TMEM lanes [32q, 32q+32) =====
+        // ===== epilogue: 8 warps; warp w may only touch TMEM lanes [32 (w % 4), +32), so two warps share
+        // a lane quadrant and the two "halves" (4 warps = 128 rows each) take alternate channel groups.
+        // A group of st_ch channels of the 128-pixel tile is staged in shared memory in the TMA
+        // swizzle and leaves as ONE bulk tensor store (coalesced, clipped at the map edge by TMA).
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int m = q * 32 + lane;
         const int tw = m & (p.TW - 1);
         const int th = (m >> p.tw_log2) & (p.TH - 1);
         const int tn = m >> (p.tw_log2 + p.th_log2);
-        const int ow = w0 + tw, oh = h0 + th, on = n0 + tn;
-        const bool valid = ow < p.Wo && oh < p.Ho && on < p.N;
-        const int co0 = n_tile * p.block_n;
-        const int64_t off = (((int64_t)on * p.Ho + oh) * p.Wo + ow) * p.Cout + co0;
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        for (int c = 0; c < p.block_n; c += 16) {
-            uint32_t r[16];
-            tmem_ld16(taddr + (uint32_t)c, r);
-            if (valid) {
-                float v[16];
+        const int n_groups = p.block_n / p.st_ch;
+        const int row_bytes = p.st_ch * 2;
+        // 16-byte chunk j of row m lives at chunk j ^ swz(m): 128B mode m & 7, 64B (m >> 1) & 3, 32B (m >> 2) & 1
+        const uint32_t swz = p.st_mode == 0 ? (uint32_t)(m & 7) : (p.st_mode == 1 ? (uint32_t)((m >> 1) & 3) : (uint32_t)((m >> 2) & 1));
+        uint8_t* my_stage = staging + (size_t)half * p.st_bufs * p.st_bytes;
+        const bool issuer = (warp - 2) % 4 == 0 && lane == 0;      // first warp of the half
+        int t = 0, sbuf = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
+            const int buf = t & 1;
+            const int n_tile = tile % p.n_tiles;
+            int m_tile = tile / p.n_tiles;
+            const int tile_w = m_tile % p.tiles_w;
+            m_tile /= p.tiles_w;
+            const int tile_h = m_tile % p.tiles_h;
+            const int tile_n = m_tile / p.tiles_h;
+            const int w0 = tile_w * p.TW, h0 = tile_h * p.TH, n0 = tile_n * p.TN;
+            const int ow = w0 + tw, oh = h0 + th, on = n0 + tn;
+            const bool valid = ow < p.Wo && oh < p.Ho && on < p.N;
+            const int co0 = n_tile * p.block_n;
+            const int64_t off = (((int64_t)on * p.Ho + oh) * p.Wo + ow) * p.Cout + co0;
+            mbar_wait(&tmem_full_bar[buf], (uint32_t)((t >> 1) & 1));
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.block_n);
+            for (int grp = half; grp < n_groups; grp += 2) {
+                uint8_t* sdst = my_stage + (size_t)sbuf * p.st_bytes;
+                // the store that last read this buffer must have finished reading it
+                if (issuer) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(0) : "memory");
+                if (p.st_bufs == 2 && issuer) {}   // (with two buffers the wait below is on the older group)
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+                for (int c16 = 0; c16 < p.st_ch; c16 += 16) {
+                    const int c = grp * p.st_ch + c16;
+                    uint32_t r[16];
+                    tmem_ld16(taddr + (uint32_t)c, r);
+                    float v[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-                if (p.bias) {
-                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + co0 + c);
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+                    if (p.bias) {
+                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + co0 + c);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 b = __ldg(b4 + i);
-                        v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 b = __ldg(b4 + i);
+                            v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+                        }
                     }
-                }
-                if (p.residual) {
-                    float r0[8], r1[8];
-                    Vec8<__nv_bfloat16>::ld(p.residual + off + c, r0);
-                    Vec8<__nv_bfloat16>::ld(p.residual + off + c + 8, r1);
+                    if (p.residual && valid) {
+                        float r0[8], r1[8];
+                        Vec8<__nv_bfloat16>::ld(p.residual + off + c, r0);
+                        Vec8<__nv_bfloat16>::ld(p.residual + off + c + 8, r1);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) { v[i] += r0[i]; v[8 + i] += r1[i]; }
-                }
-                if (p.relu) {
+                        for (int i = 0; i < 8; ++i) { v[i] += r0[i]; v[8 + i] += r1[i]; }
+                    }
+                    if (p.relu) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-                }
-                float o0[8], o1[8];
+                        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+                    }
+                    uint4 o0, o1;
+                    {
+                        __nv_bfloat162* h0p = reinterpret_cast<__nv_bfloat162*>(&o0);
+                        __nv_bfloat162* h1p = reinterpret_cast<__nv_bfloat162*>(&o1);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { o0[i] = v[i]; o1[i] = v[8 + i]; }
-                Vec8<__nv_bfloat16>::st(p.y + off + c, o0);
-                Vec8<__nv_bfloat16>::st(p.y + off + c + 8, o1);
+                        for (int i = 0; i < 4; ++i) {
+                            h0p[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                            h1p[i] = __floats2bfloat162_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
+                        }
+                    }
+                    const uint32_t j = (uint32_t)c16 >> 3;          // 16-byte chunk index of the first 8 channels
+                    uint8_t* rowp = sdst + (size_t)m * row_bytes;
+                    *reinterpret_cast<uint4*>(rowp + ((j ^ swz) << 4)) = o0;
+                    *reinterpret_cast<uint4*>(rowp + (((j + 1) ^ swz) << 4)) = o1;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+                if (issuer) {
+                    asm volatile(
+                        "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                        ::"l"(&p.y_map), "r"(smem_u32(sdst)), "r"(co0 + grp * p.st_ch), "r"(w0), "r"(h0), "r"(n0)
+                        : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                if (p.st_bufs == 2) sbuf ^= 1;
             }
+            // this warp's TMEM reads of the buffer are complete (tcgen05.wait::ld inside tmem_ld16)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cta(&tmem_empty_bar[buf]);
         }
+        if (issuer) asm volatile("cp.async.bulk.wait_group %0;" ::"n"(0) : "memory");    // stores complete before exit
     }
 
     tc_fence_before();
@@ -194,6 +274,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 static EncodeTiledFn g_encode = nullptr;
 static std::once_flag g_igemm_once;
 static int g_igemm_init_rc = EDS_OK;
+static int g_num_sms = 148;
 
 static void igemm_init_once() {
     void* fn = nullptr;
@@ -211,6 +292,10 @@ static void igemm_init_once() {
         set_error("conv_igemm: cannot opt in to 227 KB shared memory: %s", cudaGetErrorString(e));
         g_igemm_init_rc = EDS_ERR_CUDA;
     }
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+        g_num_sms = sms;
 }
 
 int igemm_init() {
@@ -270,12 +355,10 @@ extern "C" int eds_conv2d_igemm_bf16(const void* x, int N, int H, int W, int C, 
     p.k_chunks = C / p.block_k;
     // cout tile: the largest multiple of 16 that divides Cout and is <= 256
     const int k_iters = p.taps * p.k_chunks;
+    // cout tile: the largest multiple of 16 that divides Cout and is <= 256 (two accumulators of
+    // block_n fp32 columns fit the 512 columns of TMEM)
     int bn = 256;
     while (bn > 16 && Cout % bn != 0) bn -= 16;
-    // Short reductions (1x1 convolutions, thin 3x3 layers) spend their time in the fill / epilogue
-    // latency chain, not in the MMAs: a 128-wide cout tile keeps 4 CTAs (TMEM: 4 x 128 columns)
-    // resident per SM so those chains overlap.
-    if (k_iters <= 16 && bn > 128 && Cout % 128 == 0) bn = 128;
     p.block_n = bn;
     p.n_tiles = Cout / bn;
     p.N = N; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.relu = relu;
@@ -308,12 +391,18 @@ extern "C" int eds_conv2d_igemm_bf16(const void* x, int N, int H, int W, int C, 
     p.a_stage_bytes = kTileM * p.block_k * 2;                          // 16 / 8 / 4 KB
     p.b_stage_bytes = (p.block_n * p.block_k * 2 + 1023) & ~1023;
     const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
-    // long reductions: one deep pipeline per SM (wide tiles) or two CTAs x ~100 KB; short ones
-    // keep the whole K extent resident (stages == k_iters) in <= 54 KB so four CTAs fit.
-    const int budget = k_iters <= 16 ? 54 * 1024 : (stage_bytes >= 40 * 1024 ? 200 * 1024 : 100 * 1024);
-    p.stages = std::max(k_iters > 1 ? 2 : 1, std::min(std::min(kMaxStages, k_iters), budget / stage_bytes));
-    p.tmem_cols = std::max(32, pow2_ceil(p.block_n));
-    const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + (2 * kMaxStages + 1) * 8 + 16;
+    // epilogue staging: groups of st_ch channels (<= 128 B rows so the TMA swizzle applies)
+    p.st_ch = (p.block_n % 64 == 0) ? 64 : (p.block_n % 32 == 0 ? 32 : 16);
+    p.st_mode = p.st_ch == 64 ? 0 : (p.st_ch == 32 ? 1 : 2);
+    p.st_bytes = kTileM * p.st_ch * 2;                                 // 16 / 8 / 4 KB
+    p.st_bufs = 1;
+    // one persistent CTA per SM: the rest of the shared memory is one TMA ring
+    const int ring_budget = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/ - 2 * p.st_bufs * p.st_bytes;
+    p.stages = std::max(2, std::min(kMaxStages, ring_budget / stage_bytes));
+    p.tmem_cols = std::max(32, pow2_ceil(2 * p.block_n));
+    p.total_tiles = (int)n_ctas;
+    const size_t smem = (size_t)p.stages * stage_bytes + (size_t)2 * p.st_bufs * p.st_bytes + 1024 /*align slack*/ +
+                        (2 * kMaxStages + 4) * 8 + 16;
 
     // input tensor maps: one per (row parity, col parity) plane that a tap touches
     bool plane_used[4] = {false, false, false, false};
@@ -350,6 +439,15 @@ extern "C" int eds_conv2d_igemm_bf16(const void* x, int N, int H, int W, int C, 
         cuuint32_t box[2] = {(cuuint32_t)p.block_k, (cuuint32_t)p.block_n};
         if (int rc = tmap_encode_bf16(&p.b_map, w, 2, dims, strides, box, swz, "weights")) return rc;
     }
-    conv_igemm_kernel<<<(unsigned)n_ctas, kIgemmThreads, smem, as_stream(stream)>>>(p);
+    const unsigned grid = (unsigned)std::min<int64_t>(n_ctas, g_num_sms);
+    {
+        const CUtensorMapSwizzle yswz = p.st_mode == 0 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                       : p.st_mode == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+        cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)Wo * Cout * 2, (cuuint64_t)Ho * Wo * Cout * 2};
+        cuuint32_t box[4] = {(cuuint32_t)p.st_ch, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TN};
+        if (int rc = tmap_encode_bf16(&p.y_map, y, 4, dims, strides, box, yswz, "output")) return rc;
+    }
+    conv_igemm_kernel<<<grid, kIgemmThreads, smem, as_stream(stream)>>>(p);
     return check_launch("conv_igemm_kernel");
 }
