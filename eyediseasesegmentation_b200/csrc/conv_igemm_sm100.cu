@@ -22,6 +22,7 @@
 #include "tc_ptx.cuh"
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -44,6 +45,7 @@ struct IgemmParams {
     int N, Ho, Wo, Cout, relu;
     int total_tiles;
     CUtensorMap y_map;      // output [Cout][Wo][Ho][N], box [st_ch][TW][TH][TN]
+    int debug;              // developer timing switches (EDS_IGEMM_DEBUG): 1 = no bulk store, 2 = empty epilogue
     int st_ch, st_bytes, st_bufs, st_mode;   // epilogue staging: channels per TMA store, bytes per buffer, buffers per half, swizzle mode
     int stages, a_stage_bytes, b_stage_bytes, tmem_cols;
     uint32_t idesc;
@@ -196,25 +198,35 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
             mbar_wait(&tmem_full_bar[buf], (uint32_t)((t >> 1) & 1));
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.block_n);
-            for (int grp = half; grp < n_groups; grp += 2) {
+            for (int grp = half; grp < n_groups && !(p.debug & 2); grp += 2) {
                 uint8_t* sdst = my_stage + (size_t)sbuf * p.st_bytes;
-                // the store that last read this buffer must have finished reading it
-                if (issuer) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(0) : "memory");
-                if (p.st_bufs == 2 && issuer) {}   // (with two buffers the wait below is on the older group)
+                // all TMEM loads of the group are issued before the single wait
+                uint32_t r[4][16];
+                const int n16 = p.st_ch >> 4;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (i < n16) tmem_ld16_nowait(taddr + (uint32_t)(grp * p.st_ch + i * 16), r[i]);
+                // the store that last read this staging buffer must have finished reading it
+                if (issuer) {
+                    if (p.st_bufs == 2) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(1) : "memory");
+                    else asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(0) : "memory");
+                }
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
-                for (int c16 = 0; c16 < p.st_ch; c16 += 16) {
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (i >= n16) break;
+                    const int c16 = i * 16;
                     const int c = grp * p.st_ch + c16;
-                    uint32_t r[16];
-                    tmem_ld16(taddr + (uint32_t)c, r);
                     float v[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+                    for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[i][e]);
                     if (p.bias) {
                         const float4* b4 = reinterpret_cast<const float4*>(p.bias + co0 + c);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float4 b = __ldg(b4 + i);
-                            v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+                        for (int e = 0; e < 4; ++e) {
+                            const float4 bb = __ldg(b4 + e);
+                            v[4 * e] += bb.x; v[4 * e + 1] += bb.y; v[4 * e + 2] += bb.z; v[4 * e + 3] += bb.w;
                         }
                     }
                     if (p.residual && valid) {
@@ -222,20 +234,20 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
                         Vec8<__nv_bfloat16>::ld(p.residual + off + c, r0);
                         Vec8<__nv_bfloat16>::ld(p.residual + off + c + 8, r1);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) { v[i] += r0[i]; v[8 + i] += r1[i]; }
+                        for (int e = 0; e < 8; ++e) { v[e] += r0[e]; v[8 + e] += r1[e]; }
                     }
                     if (p.relu) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+                        for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
                     }
                     uint4 o0, o1;
                     {
                         __nv_bfloat162* h0p = reinterpret_cast<__nv_bfloat162*>(&o0);
                         __nv_bfloat162* h1p = reinterpret_cast<__nv_bfloat162*>(&o1);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            h0p[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-                            h1p[i] = __floats2bfloat162_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
+                        for (int e = 0; e < 4; ++e) {
+                            h0p[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+                            h1p[e] = __floats2bfloat162_rn(v[8 + 2 * e], v[8 + 2 * e + 1]);
                         }
                     }
                     const uint32_t j = (uint32_t)c16 >> 3;          // 16-byte chunk index of the first 8 channels
@@ -245,7 +257,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
-                if (issuer) {
+                if (issuer && !(p.debug & 1)) {
                     asm volatile(
                         "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                         ::"l"(&p.y_map), "r"(smem_u32(sdst)), "r"(co0 + grp * p.st_ch), "r"(w0), "r"(h0), "r"(n0)
@@ -254,7 +266,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
                 }
                 if (p.st_bufs == 2) sbuf ^= 1;
             }
-            // this warp's TMEM reads of the buffer are complete (tcgen05.wait::ld inside tmem_ld16)
+            // this warp's TMEM reads of the buffer are complete (tcgen05.wait::ld above)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cta(&tmem_empty_bar[buf]);
@@ -275,6 +287,7 @@ static EncodeTiledFn g_encode = nullptr;
 static std::once_flag g_igemm_once;
 static int g_igemm_init_rc = EDS_OK;
 static int g_num_sms = 148;
+static CUtensorMapL2promotion g_l2_promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
 
 static void igemm_init_once() {
     void* fn = nullptr;
@@ -287,6 +300,11 @@ static void igemm_init_once() {
         return;
     }
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    if (const char* pr = getenv("EDS_L2_PROMO")) {
+        const int v = atoi(pr);
+        g_l2_promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                     : v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    }
     e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
         set_error("conv_igemm: cannot opt in to 227 KB shared memory: %s", cudaGetErrorString(e));
@@ -314,7 +332,7 @@ int tmap_encode_bf16(CUtensorMap* map, const void* base, int rank, const cuuint6
                      const cuuint32_t* box, CUtensorMapSwizzle swz, const char* what) {
     cuuint32_t ones[5] = {1, 1, 1, 1, 1};
     CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
-                          strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, g_l2_promo,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("conv_igemm: cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
@@ -362,6 +380,7 @@ extern "C" int eds_conv2d_igemm_bf16(const void* x, int N, int H, int W, int C, 
     p.block_n = bn;
     p.n_tiles = Cout / bn;
     p.N = N; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.relu = relu;
+    if (const char* dbg = getenv("EDS_IGEMM_DEBUG")) p.debug = atoi(dbg);
 
     // pixel tile TN x TH x TW = 128 minimising the number of tiles (ties -> wider rows)
     int best_tiles = INT32_MAX, best_tw = 8;
@@ -395,7 +414,7 @@ extern "C" int eds_conv2d_igemm_bf16(const void* x, int N, int H, int W, int C, 
     p.st_ch = (p.block_n % 64 == 0) ? 64 : (p.block_n % 32 == 0 ? 32 : 16);
     p.st_mode = p.st_ch == 64 ? 0 : (p.st_ch == 32 ? 1 : 2);
     p.st_bytes = kTileM * p.st_ch * 2;                                 // 16 / 8 / 4 KB
-    p.st_bufs = 1;
+    p.st_bufs = k_iters <= 8 ? 2 : 1;      // short reductions are store-bound: overlap the bulk store with the next group
     // one persistent CTA per SM: the rest of the shared memory is one TMA ring
     const int ring_budget = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/ - 2 * p.st_bufs * p.st_bytes;
     p.stages = std::max(2, std::min(kMaxStages, ring_budget / stage_bytes));
