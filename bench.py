@@ -215,6 +215,7 @@ def run_b200(args):
         peak_src = "measured (MEASURED_PEAKS.json, sustained)" if peaks else "fallback (B200_PROFILING.md)"
         roof = conv_roofline(models["EX"], tfm, dev_imgs[0], mean, std, args.tiles, tensor_peak, peak_src)
         hist_roof = hist_roofline(dev, hbm_peak, peak_src)
+        blend_roof = blend_roofline(dev, hbm_peak, peak_src)
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -229,6 +230,7 @@ def run_b200(args):
                     "h2d_bytes_per_step": len(LESIONS) * (H * W * 3 + H * W),
                     "d2h_bytes_per_step": len(LESIONS) * (H * W * 4 + 19 * 2 * 8 + 2 * 8 + 16)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_hist": hist_roof,
+            "roofline_blend": blend_roof,
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(sample_only=True)
@@ -283,6 +285,52 @@ def hist_roofline(dev, peak, peak_src):
     gbs = n_img * H * W * 5 / (ms / 1e3) / 1e9
     return {"kernel": "pr_hist_kernel", "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s",
             "frac": gbs / peak, "traffic": None, "launch_ms": ms, "images_per_launch": n_img, "peak_source": peak_src}
+
+
+def blend_roofline(dev, peak, peak_src):
+    """TTA merge (de-augment + mean + sigmoid over V*B logit maps) and the x2 bilinear overwrite-paste of
+    the B tiles, at the bench shape (V=8, B=6, S=1024); algorithmic bytes = V*B*S^2*4 read + B*S^2*4 write
+    for the merge, B*(S^2*4 read + (2S)^2*4 write) for the paste."""
+    import torch
+    from eyediseasesegmentation_b200 import kernels as K, ttach_compat as tta
+    from eyediseasesegmentation_b200.util import make_grid
+    V, B = VIEWS, TILES
+    _, deaug = tta.view_maps(tta.aliases.d4_transform(), S, S)
+    logits = torch.randn((V, B, S, S), device=dev)
+    prob = torch.empty((B, S, S), device=dev)
+    preds = torch.zeros((H, W), device=dev)
+    slices = make_grid((H, W), window=2 * S, min_overlap=32)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)        # > L2
+
+    def run():
+        K.tta_merge(logits, deaug, True, out=prob)
+        for j, (x1, _, y1, _) in enumerate(slices):
+            K.resize_paste(prob[j], preds, (0, 0, S, S), (int(x1), int(y1)), (2 * S, 2 * S))
+
+    run()
+    torch.cuda.synchronize()
+    t_merge, t_all = [], []
+    for _ in range(5):
+        flush.zero_()
+        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a.record()
+        K.tta_merge(logits, deaug, True, out=prob)
+        b.record()
+        for j, (x1, _, y1, _) in enumerate(slices):
+            K.resize_paste(prob[j], preds, (0, 0, S, S), (int(x1), int(y1)), (2 * S, 2 * S))
+        c.record()
+        torch.cuda.synchronize()
+        t_merge.append(a.elapsed_time(b))
+        t_all.append(a.elapsed_time(c))
+    ms_merge, ms_all = sorted(t_merge)[2], sorted(t_all)[2]
+    bytes_merge = V * B * S * S * 4 + B * S * S * 4
+    bytes_paste = B * (S * S * 4 + 4 * S * S * 4)
+    gbs = bytes_merge / (ms_merge / 1e3) / 1e9
+    return {"kernel": "tta_merge_kernel", "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s",
+            "frac": gbs / peak, "traffic": None, "launch_ms": ms_merge, "peak_source": peak_src,
+            "l2": "256 MB written between repetitions (flush)",
+            "with_paste": {"kernels": "tta_merge_kernel + 6 x resize_paste_kernel", "ms": ms_all,
+                           "achieved": (bytes_merge + bytes_paste) / (ms_all / 1e3) / 1e9, "unit": "GB/s"}}
 
 
 # ------------------------------------------------------------------------------ CPU baseline / reference arm

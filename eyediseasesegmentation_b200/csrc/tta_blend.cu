@@ -16,73 +16,106 @@ struct ViewMaps {
     int m[8][6];
 };
 
-// One CTA = one 32x32 output tile of one image.  Views whose map transposes the axes
-// are staged through shared memory so that both the global read and the accumulate
-// stay coalesced.  The sum runs in view order in fp32, like ttach's Merger.
+// One CTA = one 32x32 output tile of one image.  All V loads of a thread are issued before the first
+// use (addresses clamped into the tile, so no load is conditional) -- 8 x 4 B in flight per thread;
+// views whose map transposes the axes are read along THEIR rows (coalesced) and turned through one
+// shared-memory tile per view.  The sum runs in view order in fp32, like ttach's Merger.
 __global__ void __launch_bounds__(1024)
 tta_merge_kernel(const float* __restrict__ logits, int V, int B, int S, ViewMaps maps, int apply_sigmoid,
                  float* __restrict__ prob) {
-    __shared__ float tile[32][33];
+    __shared__ float tile[8][32][33];
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int b = blockIdx.z;
     const int i = blockIdx.y * 32 + ty;  // output row
     const int j = blockIdx.x * 32 + tx;  // output col
     const bool inside = i < S && j < S;
-    float acc = 0.f;
-    for (int v = 0; v < V; ++v) {
-        const int* m = maps.m[v];
-        const float* src = logits + ((int64_t)v * B + b) * S * S;
-        float val = 0.f;
-        if (m[1] == 0) {  // rows map to rows: direct coalesced read
-            if (inside) val = __ldg(src + (int64_t)(m[0] * i + m[2]) * S + (m[4] * j + m[5]));
-        } else {  // transposing view: thread (ty,tx) fetches the value of output (row tx, col ty)
-            const int io = blockIdx.y * 32 + tx;
-            const int jo = blockIdx.x * 32 + ty;
-            float t = 0.f;
-            if (io < S && jo < S) t = __ldg(src + (int64_t)(m[1] * jo + m[2]) * S + (m[3] * io + m[5]));
-            __syncthreads();
-            tile[tx][ty] = t;
-            __syncthreads();
-            val = tile[ty][tx];
+    const int ic = min(i, S - 1), jc = min(j, S - 1);
+    // transposing views: thread (ty,tx) fetches the value of output (row tx, col ty) of the tile
+    const int io = min(blockIdx.y * 32 + tx, S - 1), jo = min(blockIdx.x * 32 + ty, S - 1);
+    float val[8];
+    bool any_t = false;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        val[v] = 0.f;
+        if (v < V) {
+            const int* m = maps.m[v];
+            const float* src = logits + ((int64_t)v * B + b) * S * S;
+            if (m[1] == 0) {
+                val[v] = __ldg(src + (int64_t)(m[0] * ic + m[2]) * S + (m[4] * jc + m[5]));
+            } else {
+                val[v] = __ldg(src + (int64_t)(m[1] * jo + m[2]) * S + (m[3] * io + m[5]));
+                any_t = true;
+            }
         }
-        acc = (v == 0) ? val : acc + val;
     }
+    if (any_t) {                       // CTA-uniform (the maps are kernel parameters)
+#pragma unroll
+        for (int v = 0; v < 8; ++v)
+            if (v < V && maps.m[v][1] != 0) tile[v][tx][ty] = val[v];
+        __syncthreads();
+#pragma unroll
+        for (int v = 0; v < 8; ++v)
+            if (v < V && maps.m[v][1] != 0) val[v] = tile[v][ty][tx];
+    }
+    float acc = val[0];
+#pragma unroll
+    for (int v = 1; v < 8; ++v)
+        if (v < V) acc += val[v];
     if (inside) {
-        float mean = acc / (float)V;
+        const float mean = acc / (float)V;
         prob[((int64_t)b * S + i) * S + j] = apply_sigmoid ? sigmoidf_acc(mean) : mean;
     }
 }
 
-// One thread per output pixel; coordinate arithmetic follows cv2's resizeLinear for
-// CV_32F (double coordinates, float weights, horizontal pass then vertical pass).
-__global__ void resize_paste_kernel(const float* __restrict__ src, int src_w, int crop_y, int crop_x, int crop_h,
-                                    int crop_w, float* __restrict__ dst, int dst_h, int dst_w, int dst_y,
-                                    int dst_x, int out_h, int out_w, double scale_y, double scale_x) {
-    const int ox = blockIdx.x * blockDim.x + threadIdx.x;
-    const int oy = blockIdx.y * blockDim.y + threadIdx.y;
-    if (ox >= out_w || oy >= out_h) return;
-    const int gy = dst_y + oy, gx = dst_x + ox;
-    if (gy < 0 || gy >= dst_h || gx < 0 || gx >= dst_w) return;
-    // source coordinate in double, fraction rounded to float once (matches cv2 4.x to 2e-7;
-    // rounding the coordinate itself to float would cost 5e-5 at x ~ 1000)
-    const double dy = (oy + 0.5) * scale_y - 0.5;
-    int sy = (int)floor(dy);
-    float fy = (float)(dy - (double)sy);
-    if (sy < 0) { sy = 0; fy = 0.f; }
-    if (sy >= crop_h - 1) { sy = crop_h - 1; fy = 0.f; }
-    const double dx = (ox + 0.5) * scale_x - 0.5;
-    int sx = (int)floor(dx);
-    float fx = (float)(dx - (double)sx);
-    if (sx < 0) { sx = 0; fx = 0.f; }
-    if (sx >= crop_w - 1) { sx = crop_w - 1; fx = 0.f; }
-    const int sy1 = sy + 1 < crop_h ? sy + 1 : crop_h - 1;
-    const int sx1 = sx + 1 < crop_w ? sx + 1 : crop_w - 1;
-    const float* r0 = src + (int64_t)(crop_y + sy) * src_w + crop_x;
-    const float* r1 = src + (int64_t)(crop_y + sy1) * src_w + crop_x;
-    const float a0 = 1.f - fx, a1 = fx, b0 = 1.f - fy, b1 = fy;
-    const float h0 = __fadd_rn(__fmul_rn(__ldg(r0 + sx), a0), __fmul_rn(__ldg(r0 + sx1), a1));
-    const float h1 = __fadd_rn(__fmul_rn(__ldg(r1 + sx), a0), __fmul_rn(__ldg(r1 + sx1), a1));
-    dst[(int64_t)gy * dst_w + gx] = __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, b1));
+// Bilinear resize + overwrite paste.  Coordinate arithmetic follows cv2's resizeLinear for CV_32F
+// (double coordinates, float weights, horizontal pass then vertical pass).  A CTA covers a 64 x 32
+// block of the output; its 64 column and 32 row coordinates are computed ONCE in double precision
+// (fp64 is a trickle pipe on this chip) into shared memory, then every thread produces 8 pixels.
+constexpr int kPasteBX = 64, kPasteBY = 32;
+__global__ void __launch_bounds__(256)
+resize_paste_kernel(const float* __restrict__ src, int src_w, int crop_y, int crop_x, int crop_h,
+                    int crop_w, float* __restrict__ dst, int dst_h, int dst_w, int dst_y,
+                    int dst_x, int out_h, int out_w, double scale_y, double scale_x) {
+    __shared__ int s_i0[kPasteBX + kPasteBY], s_i1[kPasteBX + kPasteBY];
+    __shared__ float s_f[kPasteBX + kPasteBY];
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int bx0 = blockIdx.x * kPasteBX, by0 = blockIdx.y * kPasteBY;
+    if (tid < kPasteBX + kPasteBY) {
+        // source coordinate in double, fraction rounded to float once (matches cv2 4.x to 2e-7;
+        // rounding the coordinate itself to float would cost 5e-5 at x ~ 1000)
+        const bool is_x = tid < kPasteBX;
+        const int o = is_x ? bx0 + tid : by0 + (tid - kPasteBX);
+        const int lim = is_x ? crop_w : crop_h;
+        const double d = (o + 0.5) * (is_x ? scale_x : scale_y) - 0.5;
+        int s0 = (int)floor(d);
+        float f = (float)(d - (double)s0);
+        if (s0 < 0) { s0 = 0; f = 0.f; }
+        if (s0 >= lim - 1) { s0 = lim - 1; f = 0.f; }
+        s_i0[tid] = s0;
+        s_i1[tid] = s0 + 1 < lim ? s0 + 1 : lim - 1;
+        s_f[tid] = f;
+    }
+    __syncthreads();
+    const int lx = tid & 63;                 // column inside the block
+    const int ox = bx0 + lx;
+    const int gx = dst_x + ox;
+    if (ox >= out_w || gx < 0 || gx >= dst_w) return;
+    const int sx = s_i0[lx], sx1 = s_i1[lx];
+    const float a1 = s_f[lx], a0 = 1.f - a1;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int ly = (tid >> 6) + 4 * k;   // 4 rows per pass, 8 passes
+        const int oy = by0 + ly;
+        const int gy = dst_y + oy;
+        if (oy >= out_h || gy < 0 || gy >= dst_h) continue;
+        const int sy = s_i0[kPasteBX + ly], sy1 = s_i1[kPasteBX + ly];
+        const float b1 = s_f[kPasteBX + ly], b0 = 1.f - b1;
+        const float* r0 = src + (int64_t)(crop_y + sy) * src_w + crop_x;
+        const float* r1 = src + (int64_t)(crop_y + sy1) * src_w + crop_x;
+        const float h0 = __fadd_rn(__fmul_rn(__ldg(r0 + sx), a0), __fmul_rn(__ldg(r0 + sx1), a1));
+        const float h1 = __fadd_rn(__fmul_rn(__ldg(r1 + sx), a0), __fmul_rn(__ldg(r1 + sx1), a1));
+        dst[(int64_t)gy * dst_w + gx] = __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, b1));
+    }
 }
 
 struct PreLut {
@@ -151,7 +184,7 @@ extern "C" int eds_resize_paste_f32(const float* src, int src_h, int src_w, int 
     EDS_REQUIRE(crop_y >= 0 && crop_x >= 0 && crop_y + crop_h <= src_h && crop_x + crop_w <= src_w,
                 "resize_paste: crop [%d:%d,%d:%d] outside %dx%d source", crop_y, crop_y + crop_h, crop_x,
                 crop_x + crop_w, src_h, src_w);
-    dim3 block(32, 8), grid(ceil_div(out_w, 32), ceil_div(out_h, 8));
+    dim3 block(64, 4), grid(ceil_div(out_w, kPasteBX), ceil_div(out_h, kPasteBY));
     resize_paste_kernel<<<grid, block, 0, as_stream(stream)>>>(src, src_w, crop_y, crop_x, crop_h, crop_w, dst,
                                                              dst_h, dst_w, dst_y, dst_x, out_h, out_w,
                                                              (double)crop_h / out_h, (double)crop_w / out_w);
