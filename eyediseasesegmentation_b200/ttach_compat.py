@@ -222,6 +222,11 @@ def view_maps(transforms: Compose, H: int, W: int):
     returns (aug, deaug): aug[v] maps augmented-image pixels to source pixels,
     deaug[v] maps merged-output pixels to pixels of view v's network output.
     """
+    # cached on the Compose object: pushing two 1024^2 coordinate grids through 8 views costs tens of
+    # milliseconds of host time (hundreds with OMP_NUM_THREADS=1 under torchrun) and never changes
+    cache = transforms.__dict__.setdefault("_eds_view_maps", {})
+    if (H, W) in cache:
+        return cache[(H, W)]
     grid = torch.stack(torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")).float()[None]
     aug, deaug = [], []
     for t in transforms:
@@ -232,6 +237,7 @@ def view_maps(transforms: Compose, H: int, W: int):
         out_grid = torch.stack(torch.meshgrid(torch.arange(a.shape[2]), torch.arange(a.shape[3]),
                                               indexing="ij")).float()[None]
         deaug.append(_fit_map(t.deaugment_mask(out_grid)[0]))
+    cache[(H, W)] = (aug, deaug)
     return aug, deaug
 
 
