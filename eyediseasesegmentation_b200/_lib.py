@@ -38,6 +38,7 @@ PROTOTYPES = {
     "eds_init": [],
     "eds_pr_hist_f32": [_vp, _vp, _i64, _i, _vp, _vp, _i, _vp],
     "eds_pr_scan": [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp],
+    "eds_confusion_u8": [_vp, _vp, _i64, _i, _i, _i, _vp, _vp],
     "eds_tta_merge": [_vp, _i, _i, _i, C.POINTER(_i), _i, _vp, _vp],
     "eds_resize_paste_f32": [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "eds_preprocess_tile_u8": [_vp, _i, _i, _i, _i, _i, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp, _vp],

@@ -82,6 +82,19 @@ def pr_scan(hist: torch.Tensor, straddle: torch.Tensor):
     return ap, roc, counts, totals
 
 
+def confusion_counts(pred: torch.Tensor, gt: torch.Tensor, thr_pred: int = 50, thr_gt: int = 50,
+                     counts: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """pred, gt [n_img, n_px] u8 -> counts [n_img, 3] i64 = (true_p, actual_p, pred_p) of the masks
+    binarised with ``x > thr`` (accumulates into ``counts`` when given)."""
+    _chk(pred, gt, counts)
+    assert pred.dtype == torch.uint8 and gt.dtype == torch.uint8 and pred.shape == gt.shape and pred.dim() == 2
+    n_img, n_px = pred.shape
+    if counts is None:
+        counts = torch.zeros((n_img, 3), dtype=torch.int64, device=pred.device)
+    check(_lib.lib().eds_confusion_u8(_p(pred), _p(gt), n_px, n_img, int(thr_pred), int(thr_gt), _p(counts), _stream()))
+    return counts
+
+
 # ------------------------------------------------------------- TTA and paste
 def tta_merge(logits: torch.Tensor, deaug_maps: Sequence[Sequence[int]], apply_sigmoid: bool = True,
               out: Optional[torch.Tensor] = None) -> torch.Tensor:

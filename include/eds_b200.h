@@ -256,6 +256,12 @@ EDS_API int eds_axial_attention(const void* qk, int qk_cstride, const void* v, i
 EDS_API int eds_mhca_gate(const void* ori, const void* att, int N, int h, int w, int C, void* y, int dtype,
                   void* stream);
 
+/* Confusion counts of two uint8 masks binarised with `x > thr` (stat_result.py:30-57,
+ * stat_result_vessel.py): counts[img][3] += { sum(gt & pred), sum(gt), sum(pred) } over n_pixels
+ * bytes per image (the caller zeroes counts). */
+EDS_API int eds_confusion_u8(const uint8_t* pred, const uint8_t* gt, int64_t n_pixels, int n_images, int thr_pred,
+                             int thr_gt, uint64_t* counts, void* stream);
+
 /* dtype conversion helpers for weights / debugging (n elements). */
 EDS_API int eds_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
 EDS_API int eds_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream);

@@ -100,7 +100,7 @@ _loaded = {}
 
 def load():
     """-> namespace with the reference modules: unetplusplusstar, axial_attention_v2,
-    deep_supunetplusplus, aucpr, base_utils, smp (the shimmed package)."""
+    deep_supunetplusplus, aucpr, base_utils, stat_result, stat_result_vessel, smp (the shimmed package)."""
     if _loaded:
         return types.SimpleNamespace(**_loaded)
     if not available():
@@ -121,6 +121,15 @@ def load():
     _module("refmain.util", lesion_dict=_loaded["base_utils"].lesion_dict)
     _loaded["aucpr"] = _load("refmain", "aucpr", os.path.join(main, "aucpr.py"))
     _loaded["smp"] = sys.modules["segmentation_models_pytorch"]
+    # stat_result.py does `from .util import lesion_dict` and `from ..data import NormalTransform` (unused)
+    refsrc = _module("refsrc")
+    refsrc.__path__ = [os.path.join(REFERENCE_ROOT, "src")]
+    refsrc_main = _module("refsrc.main")
+    refsrc_main.__path__ = [main]
+    _module("refsrc.main.util", lesion_dict=_loaded["base_utils"].lesion_dict)
+    _module("refsrc.data", NormalTransform=object)
+    _loaded["stat_result"] = _load("refsrc.main", "stat_result", os.path.join(main, "stat_result.py"))
+    _loaded["stat_result_vessel"] = _load("refsrc.main", "stat_result_vessel", os.path.join(main, "stat_result_vessel.py"))
     return types.SimpleNamespace(**_loaded)
 
 

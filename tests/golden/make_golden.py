@@ -84,6 +84,15 @@ def main():
         pre[str(ds)] = {"mean": mean, "std": std, "out": fn(sample).astype(np.float32).reshape(-1).tolist()}
     json.dump({"preprocessing": pre, "registry": ref_loader.registry_names()},
               open(os.path.join(HERE, "registry_preprocessing.json"), "w"))
+    # 5. stat_result.export_result (lesion + vessel twins) of the reference on a seeded mask set
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        lesion_cfg, vessel_cfg = helpers.make_stat_case(tmp, seed=0)
+        ref.stat_result.export_result("EX/exp", lesion_cfg)
+        ref.stat_result_vessel.export_result("vexp", vessel_cfg)
+        stat = {"lesion": helpers.read_stat_csvs(os.path.join(tmp, "out", "IDRiD", "result_assessment", "EX", "exp")),
+                "vessel": helpers.read_stat_csvs(os.path.join(tmp, "out", "DRIVE", "result_assessment", "vexp"))}
+    json.dump(stat, open(os.path.join(HERE, "stat_result.json"), "w"), indent=1)
     print("golden fixtures written to", HERE)
 
 

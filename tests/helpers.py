@@ -99,3 +99,71 @@ def synth_scoring_case(seed, shape=(96, 160), n_images=5):
             gt[:] = 0
         items.append((prob, gt, f"img{i}"))
     return items
+
+
+def make_stat_case(root, seed=0, n_images=6, shape=(120, 168)):
+    """Synthetic mask set for export_result (stat_result.py): ground truth under
+    <root>/masks/<lesion dir>/IDRiD_NN_EX.tif, saved predictions under <root>/out/IDRiD/tta/EX/exp/IDRiD_NN.jpg
+    (lesion layout) and <root>/vmasks/NN_manual1.png with predictions of the same name (vessel layout).
+    Grey levels around the `> 50` threshold, an image without positives, one without predictions,
+    one where both are empty and one all-positive ground truth exercise every branch of :55-79."""
+    import numpy as np
+    from pathlib import Path
+    from PIL import Image
+    from eyediseasesegmentation_b200.util import lesion_dict
+    rng = np.random.default_rng(seed)
+    root = Path(root)
+    gt_dir = root / "masks" / lesion_dict["EX"].dir_name
+    pred_dir = root / "out" / "IDRiD" / "tta" / "EX" / "exp"
+    vgt_dir = root / "vmasks"
+    vpred_dir = root / "out" / "DRIVE" / "tta" / "vexp"
+    for d in (gt_dir, pred_dir, vgt_dir, vpred_dir):
+        d.mkdir(parents=True, exist_ok=True)
+    levels = np.array([0, 30, 50, 51, 128, 255], dtype=np.uint8)
+    for i in range(n_images):
+        gt = levels[rng.integers(0, len(levels), size=shape)]
+        blob = rng.random((shape[0] // 8, shape[1] // 8)) < 0.3
+        pred = (np.kron(blob, np.ones((8, 8), dtype=np.uint8)) * 255).astype(np.uint8)
+        if i == 1:
+            gt[:] = 0
+        if i == 2:
+            pred[:] = 0
+        if i == 3:
+            gt[:] = 0
+            pred[:] = 0
+        if i == 4:
+            gt[:] = 255
+        Image.fromarray(gt, "L").save(gt_dir / f"IDRiD_{i:02d}_EX.tif")
+        Image.fromarray(pred, "L").save(pred_dir / f"IDRiD_{i:02d}.jpg", quality=95)
+        Image.fromarray(gt, "L").save(vgt_dir / f"{i:02d}_manual1.png")
+        Image.fromarray(pred, "L").save(vpred_dir / f"{i:02d}_manual1.png")
+    lesion_cfg = {"test_mask_path": root / "masks", "lesion_type": "EX", "out_dir": str(root / "out"),
+                  "dataset_name": "IDRiD"}
+    vessel_cfg = {"test_mask_path": vgt_dir, "lesion_type": "Vessel_DRIVE", "out_dir": str(root / "out"),
+                  "dataset_name": "DRIVE"}
+    return lesion_cfg, vessel_cfg
+
+
+def read_stat_csvs(directory):
+    """{metric: {row name: text of the value}} of the five CSVs export_result writes."""
+    import os
+    out = {}
+    for name in ("sn", "ppv", "sp", "iou", "dice"):
+        rows = {}
+        for line in open(os.path.join(directory, name + ".csv")).read().splitlines():
+            key, val = line.rsplit(",", 1)
+            rows[key] = val
+        out[name] = rows
+    return out
+
+
+def assert_stat_csvs_equal(got, want):
+    """Per-image rows byte for byte; the 'Avg:' row to 1e-12 (np.mean follows os.listdir order, which
+    is a property of the file system, not of the code)."""
+    for name in want:
+        assert set(got[name]) == set(want[name]), name
+        for key, val in want[name].items():
+            if key == "Avg:":
+                assert abs(float(got[name][key]) - float(val)) <= 1e-12 * max(1.0, abs(float(val))), (name, key)
+            else:
+                assert got[name][key] == val, (name, key, got[name][key], val)

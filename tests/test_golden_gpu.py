@@ -133,3 +133,44 @@ def test_tta_merge_linearity_full_tile():
     assert (mab - (ma + mb)).abs().max().item() < 1e-5
     const = K.tta_merge(torch.full((V, 1, S, S), 0.25, device="cuda"), deaug, False)
     assert torch.all(const == 0.25)
+
+
+def test_confusion_counts_bit_exact():
+    """eds_confusion_u8 == numpy on `x > 50` masks: aligned and ragged sizes, several images per launch,
+    accumulation into existing counters."""
+    import numpy as np
+    import torch
+    from eyediseasesegmentation_b200 import kernels as K
+    rng = np.random.default_rng(5)
+    for n_img, n_px in ((1, 16), (3, 1000), (2, 2848 * 4288), (1, 12345)):
+        pred = rng.integers(0, 256, size=(n_img, n_px), dtype=np.uint8)
+        gt = rng.integers(40, 62, size=(n_img, n_px), dtype=np.uint8)       # dense around the threshold
+        got = K.confusion_counts(torch.from_numpy(pred).cuda(), torch.from_numpy(gt).cuda())
+        bp, bg = pred > 50, gt > 50
+        want = np.stack([(bp & bg).sum(1), bg.sum(1), bp.sum(1)], axis=1)
+        assert np.array_equal(got.cpu().numpy(), want)
+        again = K.confusion_counts(torch.from_numpy(pred).cuda(), torch.from_numpy(gt).cuda(), counts=got)
+        assert np.array_equal(again.cpu().numpy(), 2 * want)
+    # unaligned base pointers take the scalar path
+    base_p = torch.from_numpy(rng.integers(0, 256, size=4099, dtype=np.uint8)).cuda()
+    base_g = torch.from_numpy(rng.integers(0, 256, size=4099, dtype=np.uint8)).cuda()
+    got = K.confusion_counts(base_p[3:].view(1, -1), base_g[3:].view(1, -1), 100, 7)
+    bp, bg = base_p[3:].cpu().numpy() > 100, base_g[3:].cpu().numpy() > 7
+    assert got.cpu().numpy().tolist() == [[int((bp & bg).sum()), int(bg.sum()), int(bp.sum())]]
+
+
+def test_export_result_writes_the_reference_csvs(tmp_path):
+    """stat_result.export_result / stat_result_vessel.export_result on the GPU reproduce the CSV files of
+    the reference (golden fixture) for the seeded mask set."""
+    import json
+    import os
+    import helpers
+    from eyediseasesegmentation_b200 import stat_result, stat_result_vessel
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "stat_result.json")))
+    lesion_cfg, vessel_cfg = helpers.make_stat_case(tmp_path, seed=0)
+    stat_result.export_result("EX/exp", lesion_cfg)
+    stat_result_vessel.export_result("vexp", vessel_cfg)
+    helpers.assert_stat_csvs_equal(
+        helpers.read_stat_csvs(tmp_path / "out" / "IDRiD" / "result_assessment" / "EX" / "exp"), golden["lesion"])
+    helpers.assert_stat_csvs_equal(
+        helpers.read_stat_csvs(tmp_path / "out" / "DRIVE" / "result_assessment" / "vexp"), golden["vessel"])

@@ -195,3 +195,28 @@ def test_two_rank_sharding_reduces_to_single_process_answer(tmp_path):
         assert r["roc"] == pytest.approx(scoring.get_aucroc(items), abs=1e-12)
         assert tuple(r["pr"]) == scoring.pr_curve(items)["thresholds"]
         assert r["rocthr"] == scoring.roc_curve(items)["threshold"]
+
+
+def test_stat_metrics_from_counts_follow_the_reference_formulas():
+    """Host half of export_result: the five metrics from (true_p, actual_p, pred_p, n) -- including the
+    empty-mask branches -- equal the reference's expressions evaluated on numpy masks (stat_result.py:55-79)."""
+    import numpy as np
+    from eyediseasesegmentation_b200.stat_result import metrics_from_counts, EPS
+    rng = np.random.default_rng(3)
+    cases = [(rng.random((40, 56)) < 0.2, rng.random((40, 56)) < 0.3), (np.zeros((8, 8), bool), rng.random((8, 8)) < 0.5),
+             (rng.random((8, 8)) < 0.5, np.zeros((8, 8), bool)), (np.zeros((8, 8), bool), np.zeros((8, 8), bool)),
+             (np.ones((8, 8), bool), rng.random((8, 8)) < 0.5)]
+    for gt_b, pred_b in cases:
+        arr_gt, arr_pred = gt_b.astype(np.uint8), pred_b.astype(np.uint8)
+        true_p, actual_p, pred_p = np.sum(arr_gt & arr_pred), np.sum(arr_gt), np.sum(arr_pred)
+        false_p = pred_p - true_p
+        actual_n = arr_gt.size - actual_p
+        true_n = actual_n - false_p
+        union = actual_p + false_p
+        want = (1 if actual_p == 0 else float(true_p) / float(actual_p),
+                1 if pred_p == 0 else float(true_p) / float(pred_p),
+                1 if actual_n == 0 else float(true_n) / float(actual_n),
+                (true_p + EPS * (union == 0).astype("float")) / (actual_p + false_p + EPS),
+                (2 * true_p + EPS * (union == 0).astype("float")) / (true_p + actual_p + false_p + EPS))
+        got = metrics_from_counts(int(true_p), int(actual_p), int(pred_p), arr_gt.size)
+        assert all(str(float(a)) == str(float(b)) for a, b in zip(got, want))

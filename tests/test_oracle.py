@@ -149,3 +149,27 @@ def test_histogram_key_keeps_ap_within_budget():
             worst = max(worst, abs(a - b))
     # 20 K-pixel images are the hard case (one tie is worth 1/n_pos); the budget is 1e-3
     assert worst < 5e-4, worst
+
+
+def test_stat_result_oracle_matches_reference_csvs(tmp_path):
+    """oracle/stat_result.py reproduces the CSV files the reference's own export_result wrote for the
+    seeded mask set (tests/golden/stat_result.json, generated by make_golden.py); in the build
+    container the reference itself is run again next to it."""
+    import json
+    import helpers
+    from oracle import stat_result as osr
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "stat_result.json")))
+    lesion_cfg, vessel_cfg = helpers.make_stat_case(tmp_path, seed=0)
+    gt_dir = str(lesion_cfg["test_mask_path"] / "3. Hard Exudates")
+    osr.export_result(gt_dir, lesion_cfg["out_dir"] + "/IDRiD/tta/EX/exp", osr.lesion_pred_name("IDRiD", "EX"),
+                      str(tmp_path / "o_lesion"))
+    osr.export_result(str(vessel_cfg["test_mask_path"]), vessel_cfg["out_dir"] + "/DRIVE/tta/vexp", lambda n: n,
+                      str(tmp_path / "o_vessel"))
+    helpers.assert_stat_csvs_equal(helpers.read_stat_csvs(tmp_path / "o_lesion"), golden["lesion"])
+    helpers.assert_stat_csvs_equal(helpers.read_stat_csvs(tmp_path / "o_vessel"), golden["vessel"])
+    from oracle import ref_loader
+    if ref_loader.available():
+        ref = ref_loader.load()
+        ref.stat_result.export_result("EX/exp", lesion_cfg)
+        helpers.assert_stat_csvs_equal(
+            helpers.read_stat_csvs(tmp_path / "out" / "IDRiD" / "result_assessment" / "EX" / "exp"), golden["lesion"])
