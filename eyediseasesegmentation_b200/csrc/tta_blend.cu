@@ -16,54 +16,66 @@ struct ViewMaps {
     int m[8][6];
 };
 
-// One CTA = one 32x32 output tile of one image.  All V loads of a thread are issued before the first
-// use (addresses clamped into the tile, so no load is conditional) -- 8 x 4 B in flight per thread;
-// views whose map transposes the axes are read along THEIR rows (coalesced) and turned through one
-// shared-memory tile per view.  The sum runs in view order in fp32, like ttach's Merger.
-__global__ void __launch_bounds__(1024)
+// One CTA (32 x 8 threads) = one 32x32 output tile of one image; a thread owns 4 rows of its column.
+// All 4 x V loads of a thread are issued before the first use (addresses clamped into the tile, so no
+// load is conditional) -- 32 x 4 B in flight per thread; views whose map transposes the axes are read
+// along THEIR rows (coalesced) and turned through one shared-memory tile per view.  The sum runs in
+// view order in fp32, like ttach's Merger.
+__global__ void __launch_bounds__(256)
 tta_merge_kernel(const float* __restrict__ logits, int V, int B, int S, ViewMaps maps, int apply_sigmoid,
                  float* __restrict__ prob) {
     __shared__ float tile[8][32][33];
-    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tx = threadIdx.x, ty = threadIdx.y;       // 32 x 8
     const int b = blockIdx.z;
-    const int i = blockIdx.y * 32 + ty;  // output row
-    const int j = blockIdx.x * 32 + tx;  // output col
-    const bool inside = i < S && j < S;
-    const int ic = min(i, S - 1), jc = min(j, S - 1);
-    // transposing views: thread (ty,tx) fetches the value of output (row tx, col ty) of the tile
-    const int io = min(blockIdx.y * 32 + tx, S - 1), jo = min(blockIdx.x * 32 + ty, S - 1);
-    float val[8];
+    const int j = blockIdx.x * 32 + tx;                 // output col
+    const int jc = min(j, S - 1);
+    float val[4][8];
     bool any_t = false;
 #pragma unroll
-    for (int v = 0; v < 8; ++v) {
-        val[v] = 0.f;
-        if (v < V) {
-            const int* m = maps.m[v];
-            const float* src = logits + ((int64_t)v * B + b) * S * S;
-            if (m[1] == 0) {
-                val[v] = __ldg(src + (int64_t)(m[0] * ic + m[2]) * S + (m[4] * jc + m[5]));
-            } else {
-                val[v] = __ldg(src + (int64_t)(m[1] * jo + m[2]) * S + (m[3] * io + m[5]));
-                any_t = true;
+    for (int r = 0; r < 4; ++r) {
+        const int rr = ty + 8 * r;                       // row inside the tile
+        const int ic = min(blockIdx.y * 32 + rr, S - 1);
+        // transposing views: thread (rr,tx) fetches the value of output (row tx, col rr) of the tile
+        const int io = min(blockIdx.y * 32 + tx, S - 1), jo = min(blockIdx.x * 32 + rr, S - 1);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            val[r][v] = 0.f;
+            if (v < V) {
+                const int* m = maps.m[v];
+                const float* src = logits + ((int64_t)v * B + b) * S * S;
+                if (m[1] == 0) {
+                    val[r][v] = __ldg(src + (int64_t)(m[0] * ic + m[2]) * S + (m[4] * jc + m[5]));
+                } else {
+                    val[r][v] = __ldg(src + (int64_t)(m[1] * jo + m[2]) * S + (m[3] * io + m[5]));
+                    any_t = true;
+                }
             }
         }
     }
     if (any_t) {                       // CTA-uniform (the maps are kernel parameters)
 #pragma unroll
-        for (int v = 0; v < 8; ++v)
-            if (v < V && maps.m[v][1] != 0) tile[v][tx][ty] = val[v];
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int v = 0; v < 8; ++v)
+                if (v < V && maps.m[v][1] != 0) tile[v][tx][ty + 8 * r] = val[r][v];
         __syncthreads();
 #pragma unroll
-        for (int v = 0; v < 8; ++v)
-            if (v < V && maps.m[v][1] != 0) val[v] = tile[v][ty][tx];
-    }
-    float acc = val[0];
+        for (int r = 0; r < 4; ++r)
 #pragma unroll
-    for (int v = 1; v < 8; ++v)
-        if (v < V) acc += val[v];
-    if (inside) {
-        const float mean = acc / (float)V;
-        prob[((int64_t)b * S + i) * S + j] = apply_sigmoid ? sigmoidf_acc(mean) : mean;
+            for (int v = 0; v < 8; ++v)
+                if (v < V && maps.m[v][1] != 0) val[r][v] = tile[v][ty + 8 * r][tx];
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = blockIdx.y * 32 + ty + 8 * r;
+        float acc = val[r][0];
+#pragma unroll
+        for (int v = 1; v < 8; ++v)
+            if (v < V) acc += val[r][v];
+        if (i < S && j < S) {
+            const float mean = acc / (float)V;
+            prob[((int64_t)b * S + i) * S + j] = apply_sigmoid ? sigmoidf_acc(mean) : mean;
+        }
     }
 }
 
@@ -171,7 +183,7 @@ extern "C" int eds_tta_merge(const float* logits, int V, int B, int S, const int
         }
         for (int q = 0; q < 6; ++q) maps.m[v][q] = m[q];
     }
-    dim3 block(32, 32), grid(ceil_div(S, 32), ceil_div(S, 32), B);
+    dim3 block(32, 8), grid(ceil_div(S, 32), ceil_div(S, 32), B);
     tta_merge_kernel<<<grid, block, 0, as_stream(stream)>>>(logits, V, B, S, maps, apply_sigmoid, prob);
     return check_launch("tta_merge_kernel");
 }
