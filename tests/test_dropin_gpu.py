@@ -1,0 +1,134 @@
+"""Drop-in drivers end to end, from files on disk to files on disk: ``tta_patches(logdir, config, args)``
+(src/main/tta.py:150-238) and its vessel twin (tta_vessel.py:138-229) with the reference's config keys,
+checkpoint location and output layout, followed by ``export_result`` (stat_result.py) on what they wrote --
+the exact sequence of pipeline.py:63-107.  The checker is the oracle pipeline (oracle/pipeline.py +
+oracle/scoring.py) run on the same files."""
+import os
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+pytestmark = pytest.mark.gpu
+
+from eyediseasesegmentation_b200 import stat_result, tta as eds_tta, tta_vessel as eds_tta_vessel  # noqa: E402
+from oracle import nets, pipeline, scoring  # noqa: E402
+import helpers  # noqa: E402
+
+S = 128
+NAME, CFG = "unetplusplus_deepsup", dict(encoder_name="resnet34", encoder_weights=None, classes=1)
+
+
+def _fundus(h, w, seed):
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+    yy, xx = np.mgrid[:h, :w]
+    img[(yy - h / 2) ** 2 + (xx - w / 2) ** 2 > (0.48 * min(h, w)) ** 2] = 0
+    return img
+
+
+def _checkpoint(tmp_path, sd):
+    logdir = tmp_path / "models" / "IDRiD" / "EX" / "exp1"
+    (logdir / "checkpoints").mkdir(parents=True)
+    torch.save({"model_state_dict": sd}, logdir / "checkpoints" / "best.pth")
+    return logdir
+
+
+@pytest.fixture()
+def fp32_mode(monkeypatch):
+    monkeypatch.setenv("EDS_PRECISION", "fp32")
+
+
+def test_tta_patches_from_disk_to_disk(tmp_path, fp32_mode):
+    model = helpers.build_product_model(NAME, CFG)
+    sd = model.state_dict()
+    logdir = _checkpoint(tmp_path, sd)
+    img_dir = tmp_path / "data" / "images"
+    mask_root = tmp_path / "data" / "masks"
+    mask_dir = mask_root / "3. Hard Exudates"
+    img_dir.mkdir(parents=True)
+    mask_dir.mkdir(parents=True)
+    rng = np.random.default_rng(11)
+    shapes = [(300, 420), (280, 300), (330, 290)]
+    for i, (h, w) in enumerate(shapes):
+        Image.fromarray(_fundus(h, w, 20 + i)).save(img_dir / f"IDRiD_{i:02d}.jpg", quality=95)
+        gt = (np.kron(rng.random((h // 10 + 1, w // 10 + 1)) < 0.08, np.ones((10, 10)))[:h, :w] * 255).astype(np.uint8)
+        if i == 2:
+            gt[:] = 0                                     # an image without positives (aucpr.py:22)
+        Image.fromarray(gt, "L").save(mask_dir / f"IDRiD_{i:02d}_EX.tif")
+    out_dir = tmp_path / "outputs"
+    config = {"dataset_name": "IDRiD", "lesion_type": "EX", "gray": False, "scale_size": S, "val_batch_size": 2,
+              "model_name": NAME, "model_params": dict(CFG), "test_img_path": img_dir, "test_mask_path": mask_root,
+              "out_dir": str(out_dir), "data_type": "tile"}
+    eds_tta.tta_patches(str(logdir), config, {"best": "true", "tta": "d4", "createprob": "false", "optim_thres": 0})
+
+    # ---- oracle on the same files
+    mean, std = pipeline.DATASET_STATS["IDRiD"]
+    items = []
+    for mp in sorted(mask_dir.glob("*.*")):
+        image = np.asarray(Image.open(img_dir / mp.name.replace("_EX.tif", ".jpg")).convert("RGB")).astype("uint8")
+        gt = (np.asarray(Image.open(mp).convert("L")) > 0).astype(np.uint8)
+        pred = pipeline.tiled_probability_map(image, lambda t: nets.unetplusplus_forward(sd, t), S, mean, std, "d4")
+        items.append((pred, gt, mp.name))
+    t3 = scoring.pr_curve(items)["thresholds"][2]          # the one tta.py:221,226 uses
+    written = out_dir / "IDRiD" / "tta" / "EX" / "exp1"
+    assert sorted(p.name for p in written.iterdir()) == [f"IDRiD_{i:02d}.jpg" for i in range(len(shapes))]
+    for pred, _, name in items:
+        got = np.asarray(Image.open(written / name.replace("_EX.tif", ".jpg")).convert("L")) > 127
+        want = pred > t3
+        assert got.shape == want.shape
+        # JPEG ringing and probabilities within 1e-4 of the threshold may flip isolated pixels
+        assert np.mean(got != want) < 5e-3, name
+
+    # ---- pipeline.py:107: the per-image metrics of the masks just written
+    stat_result.export_result("EX/exp1", config)
+    rows = helpers.read_stat_csvs(out_dir / "IDRiD" / "result_assessment" / "EX" / "exp1")
+    assert set(rows["dice"]) == {f"IDRiD_{i:02d}_EX.tif" for i in range(len(shapes))} | {"Avg:"}
+
+
+def test_vessel_test_tta_from_disk_to_disk(tmp_path, fp32_mode):
+    """tta_vessel.test_tta (tta_vessel.py:55-136): whole pre-padded square images through the PROPOSED
+    network (base_dim 8 -> 256^2), D4 TTA, ROC scoring, masks written under the image's own name;
+    then stat_result_vessel.export_result on them."""
+    from eyediseasesegmentation_b200 import stat_result_vessel
+    name, cfg = "unetplusplusstar", helpers.star_cfg(8)
+    model = helpers.build_product_model(name, cfg)
+    sd = model.state_dict()
+    logdir = tmp_path / "models" / "DRIVE" / "Vessel_DRIVE" / "vexp"
+    (logdir / "checkpoints").mkdir(parents=True)
+    torch.save({"model_state_dict": sd}, logdir / "checkpoints" / "last.pth")
+    img_dir, mask_dir = tmp_path / "vdata" / "images", tmp_path / "vdata" / "masks"
+    img_dir.mkdir(parents=True)
+    mask_dir.mkdir(parents=True)
+    rng = np.random.default_rng(12)
+    for i in range(3):
+        Image.fromarray(_fundus(256, 256, 40 + i)).save(img_dir / f"{i:02d}_test.jpg", quality=95)
+        gt = (np.kron(rng.random((32, 32)) < 0.15, np.ones((8, 8))) * 255).astype(np.uint8)
+        Image.fromarray(gt, "L").save(mask_dir / f"{i:02d}_test.jpg", quality=100)
+    out_dir = tmp_path / "voutputs"
+    config = {"dataset_name": "DRIVE", "lesion_type": "Vessel_DRIVE", "gray": False, "scale_size": 256,
+              "val_batch_size": 1, "model_name": name, "model_params": dict(cfg), "test_img_path": img_dir,
+              "test_mask_path": mask_dir, "out_dir": str(out_dir), "data_type": "all"}
+    eds_tta_vessel.test_tta(str(logdir), config, {"best": "false", "tta": "d4"})
+
+    mean, std = pipeline.DATASET_STATS["IDRiD"]          # tta_vessel.py:73 passes dataset_name=None
+    items = []
+    for ip in sorted(img_dir.glob("*.jpg")):
+        image = np.asarray(Image.open(ip).convert("RGB")).astype("uint8")
+        gt = (np.asarray(Image.open(mask_dir / ip.name).convert("L")) > 50).astype(np.uint8)
+        x = torch.from_numpy(pipeline.preprocess(image, mean, std).transpose(2, 0, 1)).float()[None]
+        with torch.no_grad():
+            logit = nets.tta_mean_logits(lambda t: nets.unetplusplusstar_forward(sd, t, 8), x, "d4")[0, 0]
+        items.append((torch.sigmoid(logit).numpy(), gt, ip.name))
+    t = scoring.roc_curve(items)["threshold"]
+    written = out_dir / "DRIVE" / "tta" / "Vessel_DRIVE" / "vexp"
+    assert sorted(p.name for p in written.iterdir()) == sorted(n for _, _, n in items)
+    for pred, _, n in items:
+        got = np.asarray(Image.open(written / n).convert("L")) > 127
+        assert np.mean(got != (pred > t)) < 5e-3, n
+    config["test_mask_path"] = mask_dir
+    stat_result_vessel.export_result("Vessel_DRIVE/vexp", config)
+    rows = helpers.read_stat_csvs(out_dir / "DRIVE" / "result_assessment" / "Vessel_DRIVE" / "vexp")
+    assert set(rows["sn"]) == {n for _, _, n in items} | {"Avg:"}
