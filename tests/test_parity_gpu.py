@@ -30,6 +30,7 @@ def _input(b, s, seed=7):
 CASES = [
     ("unetplusplusstar", star_cfg(8), 256, 2),
     ("unetplusplusstar", star_cfg(16), 512, 1),
+    ("unetplusplusstar", star_cfg(19), 608, 1),   # BASELINE config 5: DRIVE 584x565 padded to 608^2 (odd base_dim)
     ("unetplusplus_deepsup", dict(encoder_name="se_resnet50", encoder_weights=None, classes=1,
                                   decoder_attention_type="scse", deep_supervision=True), 256, 2),
     ("unetplusplus_deepsup", dict(encoder_name="resnet34", encoder_weights=None, classes=1), 256, 2),
