@@ -19,6 +19,7 @@ PR_KEY_SHIFT = 13
 PR_KEY_BIAS = (103 << 10) - 1
 PR_BINS = 24 * 1024 + 2
 PR_NTHRESH = 19
+STEM_PACKED_ELEMS = 64 * 184
 #: thresholds of the reference's pooled PR / ROC curves (src/main/aucpr.py:53,128)
 PR_THRESHOLDS = [0, 0.00001, 0.0001, 0.001, 0.01, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9,
                  0.99, 0.999, 0.9999, 0.99999, 1]
@@ -43,6 +44,8 @@ PROTOTYPES = {
     "eds_resize_paste_f32": [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "eds_preprocess_tile_u8": [_vp, _i, _i, _i, _i, _i, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp, _vp],
     "eds_stem_conv7x7s2": [_vp, _i, _i, _i, _i, C.POINTER(_i), _vp, _vp, _vp, _i, _vp],
+    "eds_stem_pack_weights": [_vp, _vp, _vp],
+    "eds_stem_conv7x7s2_mma": [_vp, _i, _i, _i, _i, C.POINTER(_i), _vp, _vp, _vp, _vp],
     "eds_conv2d_igemm_bf16": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "eds_conv3x3_halo_supported": [_i, _i, _i, _i, _i, _i],
     "eds_conv3x3_halo_bf16": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp],

@@ -117,6 +117,8 @@ class Engine:
         scale, shift = _bn_affine(sd, stem_bn)
         w = sd[stem_conv + ".weight"].float() * scale.view(-1, 1, 1, 1)
         self.w["stem"] = (w.permute(2, 3, 1, 0).contiguous(), shift.contiguous())
+        if self.act_dtype == torch.bfloat16:      # tensor-core stem: operand packed once
+            self.w["stem.packed"] = K.stem_pack_weights(self.w["stem"][0])
 
         if self.senet:
             n_layers = 3 if self.arch == "unetplusplusstar" else 4
@@ -274,7 +276,10 @@ class Engine:
         return self._cv(x, p + ".out", relu=True, residual=x_in)
 
     def _encode(self, x, aug_maps):
-        f1 = K.stem_conv(x, aug_maps, *self.w["stem"], dtype=self.act_dtype)
+        if "stem.packed" in self.w:
+            f1 = K.stem_conv_mma(x, aug_maps, self.w["stem.packed"], self.w["stem"][1])
+        else:
+            f1 = K.stem_conv(x, aug_maps, *self.w["stem"], dtype=self.act_dtype)
         if self.senet:
             y = K.maxpool2d(f1, 3, 2, 0, True)
             f2 = self._senet_layer(1, y, 1)

@@ -317,7 +317,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 head_conv3x3_kernel(const T* __restrict__ x, int N, int H, int W, int C, const float* __restrict__ w,
                     const float* __restrict__ bias, int classes, float* __restrict__ logits) {
-    extern __shared__ float s_w[];  // [classes][9][C]
+    extern __shared__ __align__(16) float s_w[];  // [classes][9][C]
     for (int i = threadIdx.x; i < classes * 9 * C; i += blockDim.x) s_w[i] = w[i];
     __syncthreads();
     const int64_t total = (int64_t)N * H * W;
@@ -346,10 +346,18 @@ head_conv3x3_kernel(const T* __restrict__ x, int N, int H, int W, int C, const f
                 for (int q = 0; q < 9; ++q) Vec8<T>::ld(xp[q] + c, v[q]);
 #pragma unroll
                 for (int q = 0; q < 9; ++q) {
-                    const float* wp = s_w + (k * 9 + q) * C + c;
-                    float d = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) d = fmaf(v[q][i], wp[i], d);
+                    // 8 weights per two 128-bit shared loads (one scalar load per multiply made this
+                    // kernel LDS-bound)
+                    const float4* wp = reinterpret_cast<const float4*>(s_w + (k * 9 + q) * C + c);
+                    const float4 w0 = wp[0], w1 = wp[1];
+                    float d = v[q][0] * w0.x;
+                    d = fmaf(v[q][1], w0.y, d);
+                    d = fmaf(v[q][2], w0.z, d);
+                    d = fmaf(v[q][3], w0.w, d);
+                    d = fmaf(v[q][4], w1.x, d);
+                    d = fmaf(v[q][5], w1.y, d);
+                    d = fmaf(v[q][6], w1.z, d);
+                    d = fmaf(v[q][7], w1.w, d);
                     acc = fmaf(valid[q], d, acc);
                 }
             }

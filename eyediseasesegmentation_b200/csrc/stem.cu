@@ -8,6 +8,7 @@
 // Cin = 3 makes this a CUDA-core kernel (K = 147 is too ragged for a UMMA tile);
 // it is ~0.3 % of the network's FLOPs.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace eds {
 
@@ -105,17 +106,18 @@ stem_conv_kernel(const float* __restrict__ x, int B, int H, int W, StemViews vie
     }
 }
 
+int stem_conv_mma_launch(const float* x, int B, int H, int W, int V, const int* maps, const void* w_packed,
+                         const float* bias, void* y, cudaStream_t stream);   // stem_mma.cu
+int stem_pack_launch(const float* w, void* out, cudaStream_t stream);
+
 }  // namespace eds
 
 using namespace eds;
 
-extern "C" int eds_stem_conv7x7s2(const float* x, int B, int H, int W, int V, const int* aug_maps_host,
-                                  const float* w, const float* bias, void* y, int dtype, void* stream) {
-    EDS_REQUIRE(x && w && bias && y && aug_maps_host, "stem_conv: null pointer");
+static int stem_check_views(int B, int V, int H, int W, const int* aug_maps_host, StemViews* views) {
     EDS_REQUIRE(B >= 1 && V >= 1 && V <= 8 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0,
                 "stem_conv: bad shape B=%d V=%d H=%d W=%d", B, V, H, W);
     EDS_REQUIRE((int64_t)B * V <= 65535, "stem_conv: B*V too large");
-    StemViews views;
     for (int v = 0; v < V; ++v) {
         const int* m = aug_maps_host + v * 6;
         const bool straight = m[1] == 0 && m[3] == 0 && (m[0] == 1 || m[0] == -1) && (m[4] == 1 || m[4] == -1);
@@ -127,8 +129,16 @@ extern "C" int eds_stem_conv7x7s2(const float* x, int B, int H, int W, int V, co
             const int r = m[0] * i + m[1] * j + m[2], c = m[3] * i + m[4] * j + m[5];
             EDS_REQUIRE(r >= 0 && r < H && c >= 0 && c < W, "stem_conv: view %d map leaves the image", v);
         }
-        for (int q = 0; q < 6; ++q) views.m[v][q] = m[q];
+        for (int q = 0; q < 6; ++q) views->m[v][q] = m[q];
     }
+    return EDS_OK;
+}
+
+extern "C" int eds_stem_conv7x7s2(const float* x, int B, int H, int W, int V, const int* aug_maps_host,
+                                  const float* w, const float* bias, void* y, int dtype, void* stream) {
+    EDS_REQUIRE(x && w && bias && y && aug_maps_host, "stem_conv: null pointer");
+    StemViews views;
+    if (int rc = stem_check_views(B, V, H, W, aug_maps_host, &views)) return rc;
     const size_t smem = sizeof(float) * (kStemK * 64 + 3 * kStemPatch * kStemPatch);
     dim3 grid(ceil_div(W / 2, kStemTile), ceil_div(H / 2, kStemTile), B * V);
     cudaError_t e = cudaSuccess;
@@ -142,4 +152,19 @@ extern "C" int eds_stem_conv7x7s2(const float* x, int B, int H, int W, int V, co
         return EDS_ERR_CUDA;
     }
     return check_launch("stem_conv_kernel");
+}
+
+extern "C" int eds_stem_pack_weights(const float* w, void* w_packed, void* stream) {
+    EDS_REQUIRE(w && w_packed, "stem_pack_weights: null pointer");
+    EDS_REQUIRE(((uintptr_t)w_packed & 15) == 0, "stem_pack_weights: output must be 16-byte aligned");
+    return stem_pack_launch(w, w_packed, as_stream(stream));
+}
+
+extern "C" int eds_stem_conv7x7s2_mma(const float* x, int B, int H, int W, int V, const int* aug_maps_host,
+                                      const void* w_packed, const float* bias, void* y, void* stream) {
+    EDS_REQUIRE(x && w_packed && bias && y && aug_maps_host, "stem_conv_mma: null pointer");
+    EDS_REQUIRE((((uintptr_t)w_packed | (uintptr_t)y) & 15) == 0, "stem_conv_mma: pointers must be 16-byte aligned");
+    StemViews views;
+    if (int rc = stem_check_views(B, V, H, W, aug_maps_host, &views)) return rc;
+    return stem_conv_mma_launch(x, B, H, W, V, aug_maps_host, w_packed, bias, y, as_stream(stream));
 }

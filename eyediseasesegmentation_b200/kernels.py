@@ -146,6 +146,30 @@ def stem_conv(x: torch.Tensor, aug_maps, w: torch.Tensor, bias: torch.Tensor, dt
     return out
 
 
+def stem_pack_weights(w: torch.Tensor) -> torch.Tensor:
+    """w [7,7,3,64] fp32 -> packed bf16 operand of the tensor-core stem (once per model)."""
+    _chk(w)
+    assert w.shape == (7, 7, 3, 64) and w.dtype == torch.float32
+    out = torch.empty(_lib.STEM_PACKED_ELEMS, dtype=torch.bfloat16, device=w.device)
+    check(_lib.lib().eds_stem_pack_weights(_p(w), _p(out), _stream()))
+    return out
+
+
+def stem_conv_mma(x: torch.Tensor, aug_maps, w_packed: torch.Tensor, bias: torch.Tensor,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [B,3,H,W] fp32 NCHW -> [V*B, H/2, W/2, 64] bf16 on the tensor cores."""
+    _chk(x, w_packed, bias, out)
+    B, Cin, H, W = x.shape
+    assert Cin == 3 and x.dtype == torch.float32 and w_packed.dtype == torch.bfloat16
+    assert w_packed.numel() == _lib.STEM_PACKED_ELEMS
+    V = len(aug_maps)
+    if out is None:
+        out = torch.empty((V * B, H // 2, W // 2, 64), dtype=torch.bfloat16, device=x.device)
+    flat = _lib.int_array([v for m in aug_maps for v in m])
+    check(_lib.lib().eds_stem_conv7x7s2_mma(_p(x), B, H, W, V, flat, _p(w_packed), _p(bias), _p(out), _stream()))
+    return out
+
+
 def conv_out_hw(H: int, W: int, R: int, stride: int, pad: int):
     return (H + 2 * pad - R) // stride + 1, (W + 2 * pad - R) // stride + 1
 

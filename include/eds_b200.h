@@ -121,6 +121,15 @@ EDS_API int eds_preprocess_tile_u8(const uint8_t* img, int img_h, int img_w, int
 EDS_API int eds_stem_conv7x7s2(const float* x, int B, int H, int W, int V, const int* aug_maps_host,
                        const float* w, const float* bias, void* y, int dtype, void* stream);
 
+/* The same stem on the tensor cores for bf16 outputs (stem_mma.cu): weights are packed once with
+ * eds_stem_pack_weights (w [7][7][3][64] fp32 -> EDS_STEM_PACKED_ELEMS bf16: [64 couts][184], K ordered
+ * (c, r, s') with the 7 horizontal taps padded to 8), then every call is
+ * im2col-in-shared-memory + mma.sync.m16n8k16.  y: [V*B][H/2][W/2][64] bf16. */
+#define EDS_STEM_PACKED_ELEMS (64 * 184)
+EDS_API int eds_stem_pack_weights(const float* w, void* w_packed, void* stream);
+EDS_API int eds_stem_conv7x7s2_mma(const float* x, int B, int H, int W, int V, const int* aug_maps_host,
+                                   const void* w_packed, const float* bias, void* y, void* stream);
+
 /* Implicit-GEMM convolution on the tcgen05 tensor cores (bf16 in, fp32 accumulate in
  * TMEM, TMA-staged NHWC tiles).  x: [N][H][W][C] bf16, w: [Cout][R][S][C] bf16 (BN
  * folded), bias: [Cout] fp32 or NULL, residual: [N][Ho][Wo][Cout] bf16 or NULL (added

@@ -183,6 +183,25 @@ def test_stem_conv_views():
     assert (y - ref).abs().max().item() < 1e-4
     yb = K.stem_conv(x, aug, w.permute(2, 3, 1, 0).contiguous(), b, torch.bfloat16)
     assert rel_err(yb, ref) < 5e-3
+    # tensor-core stem (bf16 operands): against the fp32 reference and, tightly, against the same
+    # convolution of the bf16-rounded operands
+    ym = K.stem_conv_mma(x, aug, K.stem_pack_weights(w.permute(2, 3, 1, 0).contiguous()), b)
+    assert ym.shape == ref.shape and rel_err(ym, ref) < 8e-3
+    xr, wr = x.bfloat16().float(), w.bfloat16().float()
+    ref_r = torch.cat([nhwc(F.relu(F.conv2d(t.augment_image(xr), wr, b, stride=2, padding=3))) for t in tfm], 0)
+    assert rel_err(ym, ref_r) < 4e-3
+
+
+@pytest.mark.parametrize("B,S", [(1, 32), (3, 96), (2, 608)])
+def test_stem_conv_mma_ragged_tiles(B, S):
+    """Sizes that are not multiples of the 8 x 16 output tile, one view."""
+    x = rnd(B, 3, S, S, seed=17)
+    w = rnd(64, 3, 7, 7, seed=18, scale=0.1)
+    b = rnd(64, seed=19)
+    ident = [(1, 0, 0, 0, 1, 0)]
+    ym = K.stem_conv_mma(x, ident, K.stem_pack_weights(w.permute(2, 3, 1, 0).contiguous()), b)
+    ref = nhwc(F.relu(F.conv2d(x.bfloat16().float(), w.bfloat16().float(), b, stride=2, padding=3)))
+    assert ym.shape == ref.shape and rel_err(ym, ref) < 4e-3
 
 
 # -------------------------------------------------------------------- pointwise
