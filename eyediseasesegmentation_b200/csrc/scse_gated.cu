@@ -229,25 +229,30 @@ __device__ __forceinline__ void ld_gated(const T* p, const float2 (&cg)[4], cons
     }
 }
 
-// One thread = one 8-channel vector of one 2x2 OUTPUT block (i, j) <- low-res pixel (i, j) of
-// source 0 and its 3x3 neighbourhood (9 loads feed 4 outputs), or the 4 same-resolution pixels of
-// a skip source.  grid.x = N*h rows of blocks, grid.y covers (j, vector) of a row; consecutive
-// threads own consecutive vectors of the same block, so every global access of a warp is a
-// contiguous run.  All lerps / gates run on the packed fp32 pipe.
-// PART 0 writes the channels of the upsampled source 0 (register-heavy: 9 vectors in flight), PART 1 the
-// channels of the same-resolution sources (a light streaming kernel that runs at full occupancy).
+// One thread = one 8-channel vector of a 2 x 4 OUTPUT block = two adjacent low-res pixels (i, 2jj),
+// (i, 2jj+1) of source 0 and their 3 x 4 neighbourhood (12 loads feed 8 outputs; the vertical lerps of
+// the two inner columns are shared), or the 8 same-resolution pixels of a skip source.  Index arithmetic
+// and bf16 unpacking were most of the instructions of the 2 x 2 version; the wider block halves them
+// per output.  grid.x = N*h rows of blocks, grid.y covers (jj, vector) of a row; consecutive threads own
+// consecutive vectors of the same block, so every global access of a warp is a contiguous run.  All
+// lerps / gates run on the packed fp32 pipe.
+// PART 0 writes the channels of the upsampled source 0 (register-heavy: 12 vectors in flight), PART 1 the
+// channels of the same-resolution sources (a light streaming kernel).
 template <typename T, int PART>
-__global__ void __launch_bounds__(256, PART == 0 ? 2 : 4)
+__global__ void __launch_bounds__(256, 2)
 concat_gated_kernel(CatSrcs src, int h, int w, int mode, int Ctot, const float* __restrict__ cgate1,
                     const float* __restrict__ sgate1, T* __restrict__ y) {
     const uint32_t C8a = (uint32_t)src.s[0].C / 8;
     const uint32_t C8 = PART == 0 ? C8a : (uint32_t)Ctot / 8 - C8a;     // vectors per pixel of this part
+    const uint32_t wp = (uint32_t)(w + 1) / 2;                          // column pairs per low-res row
     const uint32_t col = blockIdx.y * blockDim.x + threadIdx.x;
-    if (col >= (uint32_t)w * C8) return;
-    const int j = (int)(col / C8);
-    const int c8 = (int)(col - (uint32_t)j * C8) + (PART == 0 ? 0 : (int)C8a);
+    if (col >= wp * C8) return;
+    const int jj = (int)(col / C8);
+    const int c8 = (int)(col - (uint32_t)jj * C8) + (PART == 0 ? 0 : (int)C8a);
     const int n = (int)(blockIdx.x / (uint32_t)h);
     const int i = (int)(blockIdx.x - (uint32_t)n * h);
+    const int j0 = 2 * jj;
+    const bool second = j0 + 1 < w;                 // odd widths: the last pair has one column
     const int H = 2 * h, W = 2 * w;
     int c = c8 * 8, k = 0;
     if (PART == 1)
@@ -256,21 +261,26 @@ concat_gated_kernel(CatSrcs src, int h, int w, int mode, int Ctot, const float* 
     const bool gated = s.cgate != nullptr;
     float2 cg[4];
     if (gated) ld8f(s.cgate + (int64_t)n * s.C + c, cg);
-    float2 o[4][4];
+    float2 o[8][4];                                 // [row * 4 + column of the block][channel pair]
     if (PART == 0) {
         const T* xp = reinterpret_cast<const T*>(s.x) + (int64_t)n * h * w * s.C + c;
         const float* sg = s.sgate + (int64_t)n * h * w;      // only dereferenced when gated
         if (mode == EDS_UP_NEAREST) {
-            ld_gated<T>(xp + (int64_t)(i * w + j) * s.C, cg, sg + i * w + j, gated, o[0]);
+            const int p0 = i * w + j0, p1 = i * w + min(j0 + 1, w - 1);
+            ld_gated<T>(xp + (int64_t)p0 * s.C, cg, sg + p0, gated, o[0]);
+            ld_gated<T>(xp + (int64_t)p1 * s.C, cg, sg + p1, gated, o[2]);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) o[1][q] = o[2][q] = o[3][q] = o[0][q];
+            for (int q = 0; q < 4; ++q) {
+                o[1][q] = o[4][q] = o[5][q] = o[0][q];
+                o[3][q] = o[6][q] = o[7][q] = o[2][q];
+            }
         } else {
             const int r[3] = {max(i - 1, 0) * w, i * w, min(i + 1, h - 1) * w};
-            const int cc[3] = {max(j - 1, 0), j, min(j + 1, w - 1)};
-            float2 top[3][4], bot[3][4];
+            const int cc[4] = {max(j0 - 1, 0), j0, min(j0 + 1, w - 1), min(j0 + 2, w - 1)};
+            float2 top[4][4], bot[4][4];
             const float2 q25 = f2(0.25f), q75 = f2(0.75f);
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
+            for (int a = 0; a < 4; ++a) {
                 float2 v0[4], v1[4], v2[4];
                 ld_gated<T>(xp + (int64_t)(r[0] + cc[a]) * s.C, cg, sg + r[0] + cc[a], gated, v0);
                 ld_gated<T>(xp + (int64_t)(r[1] + cc[a]) * s.C, cg, sg + r[1] + cc[a], gated, v1);
@@ -284,41 +294,64 @@ concat_gated_kernel(CatSrcs src, int h, int w, int mode, int Ctot, const float* 
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float2 mt = __fmul2_rn(q75, top[1][q]), mb = __fmul2_rn(q75, bot[1][q]);
-                o[0][q] = __ffma2_rn(q25, top[0][q], mt);
-                o[1][q] = __ffma2_rn(q25, top[2][q], mt);
-                o[2][q] = __ffma2_rn(q25, bot[0][q], mb);
-                o[3][q] = __ffma2_rn(q25, bot[2][q], mb);
+                const float2 t1 = __fmul2_rn(q75, top[1][q]), t2 = __fmul2_rn(q75, top[2][q]);
+                const float2 b1 = __fmul2_rn(q75, bot[1][q]), b2 = __fmul2_rn(q75, bot[2][q]);
+                o[0][q] = __ffma2_rn(q25, top[0][q], t1);
+                o[1][q] = __ffma2_rn(q25, top[2][q], t1);
+                o[2][q] = __ffma2_rn(q25, top[1][q], t2);
+                o[3][q] = __ffma2_rn(q25, top[3][q], t2);
+                o[4][q] = __ffma2_rn(q25, bot[0][q], b1);
+                o[5][q] = __ffma2_rn(q25, bot[2][q], b1);
+                o[6][q] = __ffma2_rn(q25, bot[1][q], b2);
+                o[7][q] = __ffma2_rn(q25, bot[3][q], b2);
             }
         }
     } else {
         const T* xp = reinterpret_cast<const T*>(s.x) + (int64_t)n * H * W * s.C + c;
         const float* sg = s.sgate + (int64_t)n * H * W;
 #pragma unroll
-        for (int d = 0; d < 4; ++d) {
-            const int p = (2 * i + (d >> 1)) * W + 2 * j + (d & 1);
+        for (int d = 0; d < 8; ++d) {
+            // columns 2, 3 of the block do not exist for the last pair of an odd width: clamp the address
+            const int px = min(2 * j0 + (d & 3), W - 1);
+            const int p = (2 * i + (d >> 2)) * W + px;
             ld_gated<T>(xp + (int64_t)p * s.C, cg, sg + p, gated, o[d]);
         }
     }
-    const int64_t p00 = ((int64_t)n * H + 2 * i) * W + 2 * j;     // output pixel (2i, 2j)
+    const int64_t p00 = ((int64_t)n * H + 2 * i) * W + 2 * j0;     // output pixel (2i, 2 j0)
     if (cgate1) {
         float2 g1[4];
         ld8f(cgate1 + (int64_t)n * Ctot + c8 * 8, g1);
-        const float2 s01 = *reinterpret_cast<const float2*>(sgate1 + p00);       // (2i, 2j), (2i, 2j+1)
-        const float2 s23 = *reinterpret_cast<const float2*>(sgate1 + p00 + W);   // (2i+1, 2j), (2i+1, 2j+1)
-        const float sd[4] = {s01.x, s01.y, s23.x, s23.y};
+        float sd[8];
+        {
+            const float2 a0 = *reinterpret_cast<const float2*>(sgate1 + p00);
+            const float2 a1 = *reinterpret_cast<const float2*>(sgate1 + p00 + W);
+            sd[0] = a0.x; sd[1] = a0.y; sd[4] = a1.x; sd[5] = a1.y;
+            sd[2] = sd[3] = sd[6] = sd[7] = 0.f;
+            if (second) {
+                const float2 b0 = *reinterpret_cast<const float2*>(sgate1 + p00 + 2);
+                const float2 b1 = *reinterpret_cast<const float2*>(sgate1 + p00 + W + 2);
+                sd[2] = b0.x; sd[3] = b0.y; sd[6] = b1.x; sd[7] = b1.y;
+            }
+        }
 #pragma unroll
-        for (int d = 0; d < 4; ++d) {
+        for (int d = 0; d < 8; ++d) {
             const float2 s1 = f2(sd[d]);
 #pragma unroll
             for (int q = 0; q < 4; ++q) o[d][q] = __fmul2_rn(o[d][q], __fadd2_rn(g1[q], s1));
         }
     }
     T* yp = y + p00 * Ctot + c8 * 8;
+    T* yq = yp + (int64_t)W * Ctot;
     V8<T>::st(yp, o[0]);
     V8<T>::st(yp + Ctot, o[1]);
-    V8<T>::st(yp + (int64_t)W * Ctot, o[2]);
-    V8<T>::st(yp + (int64_t)W * Ctot + Ctot, o[3]);
+    V8<T>::st(yq, o[4]);
+    V8<T>::st(yq + Ctot, o[5]);
+    if (second) {
+        V8<T>::st(yp + 2 * Ctot, o[2]);
+        V8<T>::st(yp + 3 * Ctot, o[3]);
+        V8<T>::st(yq + 2 * Ctot, o[6]);
+        V8<T>::st(yq + 3 * Ctot, o[7]);
+    }
 }
 
 // y = x * (cgate[n][c] + sgate[n][p]) for an already materialised map (gate = probabilities).
@@ -431,11 +464,12 @@ extern "C" int eds_concat_gated(const eds_gated_src* srcs, int n_srcs, int N, in
     }
     EDS_REQUIRE((int64_t)w * (Ctot / 8) < (1ll << 24) && (int64_t)N * h < (1ll << 31), "concat_gated: map too large");
     const int c8a = cs.s[0].C / 8, c8b = Ctot / 8 - c8a;
-    dim3 grid_a((unsigned)(N * h), (unsigned)ceil_div(w * c8a, 256));
+    const int wp = (w + 1) / 2;
+    dim3 grid_a((unsigned)(N * h), (unsigned)ceil_div(wp * c8a, 256));
     EDS_DISPATCH_DTYPE(dtype, T, (concat_gated_kernel<T, 0><<<grid_a, 256, 0, as_stream(stream)>>>(
                                      cs, h, w, mode, Ctot, cgate, sgate, (T*)y)));
     if (c8b > 0) {
-        dim3 grid_b((unsigned)(N * h), (unsigned)ceil_div(w * c8b, 256));
+        dim3 grid_b((unsigned)(N * h), (unsigned)ceil_div(wp * c8b, 256));
         EDS_DISPATCH_DTYPE(dtype, T, (concat_gated_kernel<T, 1><<<grid_b, 256, 0, as_stream(stream)>>>(
                                          cs, h, w, mode, Ctot, cgate, sgate, (T*)y)));
     }
