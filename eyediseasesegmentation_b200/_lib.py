@@ -63,6 +63,9 @@ PROTOTYPES = {
     "eds_gated_stats": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp],
     "eds_sse_finalize": [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp],
     "eds_concat_gated": [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
+    "eds_concat_gated_split": [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp],
+    "eds_conv2d_igemm_bf16_2src": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "eds_conv3x3_halo_bf16_2src": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp],
     "eds_apply_gate": [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
     "eds_axial_attention": [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp],
     "eds_mhca_gate": [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],

@@ -195,7 +195,15 @@ class Engine:
     # ---------------------------------------------------------------- kernels
     def _cv(self, x, name, stride=1, pad=0, relu=False, residual=None):
         w, b = self.w[name]
+        if isinstance(x, tuple):        # (upsampled part, skip part) of a decoder concat: two-input K loop
+            return K.conv2d(x[0], w, b, stride, pad, relu, residual, impl=self.conv_impl, x1=x[1])
         return K.conv2d(x, w, b, stride, pad, relu, residual, impl=self.conv_impl)
+
+    def _split_ok(self, srcs):
+        """The tensor-core convolutions can read the concat as two dense maps when both channel counts are
+        multiples of 16 (bf16 path only; the fp32 parity path keeps one map)."""
+        return (self.conv_impl == "tc" and len(srcs) >= 2 and srcs[0][0].shape[3] % 16 == 0 and
+                sum(t[0].shape[3] for t in srcs[1:]) % 16 == 0)
 
     def _keep(self, name, t):
         if self.keep_features:
@@ -234,6 +242,8 @@ class Engine:
             off += c
         cgate = K.se_gate(mean, *self.w[name + ".cse"])
         sgate = K.sse_finalize(dot0, dot1, self.up_mode, b_sse)
+        if self._split_ok(srcs):
+            return K.concat_gated_split(srcs, self.up_mode, cgate, sgate)
         return K.concat_gated(srcs, self.up_mode, cgate, sgate)
 
     # ---------------------------------------------------------------- encoders
@@ -320,12 +330,19 @@ class Engine:
         p = f"decoder.blocks.{name}"
         if (p + ".down_sample") in self.w:
             x = _plain(x)
-            cat = K.concat_gated([(x, None, None), (self._mhca_skip(p, x, skips), None, None)], self.up_mode)
+            skip = self._mhca_skip(p, x, skips)
+            if self._split_ok([(x, None, None), (skip, None, None)]):
+                # the gated skip is already a dense map: only the upsampled half is written
+                cat = (K.concat_gated([(x, None, None)], self.up_mode), skip)
+            else:
+                cat = K.concat_gated([(x, None, None), (skip, None, None)], self.up_mode)
         else:
             if skips and (p + ".attention1.sse") in self.w:
                 cat = self._concat_scse(p + ".attention1", x, skips)
             else:
-                cat = K.concat_gated([_parts(x)] + [_parts(t) for t in skips], self.up_mode)
+                srcs = [_parts(x)] + [_parts(t) for t in skips]
+                cat = K.concat_gated_split(srcs, self.up_mode) if self._split_ok(srcs) else \
+                    K.concat_gated(srcs, self.up_mode)
         y = self._cv(cat, p + ".conv1", pad=1, relu=True)
         y = self._cv(y, p + ".conv2", pad=1, relu=True)
         if (p + ".down_sample") not in self.w:

@@ -34,6 +34,8 @@ constexpr int kTileRows = 32, kTileCols = 8, kSlabRows = kTileRows + 2;
 
 struct HaloParams {
     CUtensorMap a_map;
+    CUtensorMap a_map1;     // optional second input (channels C0.. of the concatenated K axis)
+    int k_split;            // channel chunks served by a_map
     CUtensorMap b_map;
     const float* bias;
     const __nv_bfloat16* residual;
@@ -103,7 +105,11 @@ conv3x3_halo_kernel(const __grid_constant__ HaloParams p) {
                                                   (uint32_t)((kSlabRows * p.atom_bytes) + 3 * p.bn * p.block_k * 2));
                             uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
                             uint8_t* sb = sa + p.a_slab_bytes;
-                            tma_load_4d(sa, &p.a_map, &full_bar[stage], kc * p.block_k, w0 + dwi - 1, h0 - 1, n);
+                            if (kc < p.k_split)
+                                tma_load_4d(sa, &p.a_map, &full_bar[stage], kc * p.block_k, w0 + dwi - 1, h0 - 1, n);
+                            else
+                                tma_load_4d(sa, &p.a_map1, &full_bar[stage], (kc - p.k_split) * p.block_k, w0 + dwi - 1,
+                                            h0 - 1, n);
                             for (int dhi = 0; dhi < 3; ++dhi)
                                 tma_load_2d(sb + dhi * p.b_tap_bytes, &p.b_map, &full_bar[stage],
                                             (dhi * 3 + dwi) * p.C + kc * p.block_k, 0);
@@ -260,9 +266,13 @@ extern "C" int eds_conv3x3_halo_supported(int C, int Cout, int R, int S, int str
            Cout <= 128;
 }
 
-extern "C" int eds_conv3x3_halo_bf16(const void* x, int N, int H, int W, int C, const void* w, const float* bias,
-                                     int Cout, int relu, const void* residual, void* y, void* stream) {
+static int halo_launch(const void* x, int C0, const void* x1, int C1, int N, int H, int W, const void* w,
+                       const float* bias, int Cout, int relu, const void* residual, void* y, void* stream) {
+    const int C = C0 + C1;
     EDS_REQUIRE(x && w && y, "conv3x3_halo: null pointer");
+    EDS_REQUIRE(C0 >= 16 && C0 % 16 == 0 && C1 >= 0 && C1 % 16 == 0 && (x1 != nullptr) == (C1 > 0),
+                "conv3x3_halo: C0=%d C1=%d must be multiples of 16", C0, C1);
+    EDS_REQUIRE((((uintptr_t)x1) & 15) == 0, "conv3x3_halo: pointers must be 16-byte aligned");
     EDS_REQUIRE(N > 0 && H > 0 && W > 0, "conv3x3_halo: bad shape N=%d H=%d W=%d", N, H, W);
     EDS_REQUIRE(eds_conv3x3_halo_supported(C, Cout, 3, 3, 1, 1),
                 "conv3x3_halo: C=%d Cout=%d outside the supported range (multiples of 16, Cout <= 128)", C, Cout);
@@ -278,8 +288,9 @@ extern "C" int eds_conv3x3_halo_bf16(const void* x, int N, int H, int W, int C, 
     p.residual = (const __nv_bfloat16*)residual;
     p.y = (__nv_bfloat16*)y;
     p.C = C;
-    p.block_k = (C % 64 == 0) ? 64 : (C % 32 == 0 ? 32 : 16);
+    p.block_k = ((C0 | C1) % 64 == 0) ? 64 : ((C0 | C1) % 32 == 0 ? 32 : 16);   // divides both inputs
     p.k_chunks = C / p.block_k;
+    p.k_split = C0 / p.block_k;
     p.bn = Cout;
     p.N = N; p.H = H; p.W = W; p.relu = relu;
     if (const char* dbg = getenv("EDS_HALO_DEBUG")) p.debug = atoi(dbg);
@@ -308,10 +319,17 @@ extern "C" int eds_conv3x3_halo_bf16(const void* x, int N, int H, int W, int C, 
                 p.tmem_cols);
 
     {
-        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-        cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+        cuuint64_t dims[4] = {(cuuint64_t)C0, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)C0 * 2, (cuuint64_t)W * C0 * 2, (cuuint64_t)H * W * C0 * 2};
         cuuint32_t box[4] = {(cuuint32_t)p.block_k, (cuuint32_t)kTileCols, (cuuint32_t)kSlabRows, 1u};
         if (int rc = tmap_encode_bf16(&p.a_map, x, 4, dims, strides, box, swz, "halo input")) return rc;
+        p.a_map1 = p.a_map;
+    }
+    if (x1) {
+        cuuint64_t dims[4] = {(cuuint64_t)C1, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)C1 * 2, (cuuint64_t)W * C1 * 2, (cuuint64_t)H * W * C1 * 2};
+        cuuint32_t box[4] = {(cuuint32_t)p.block_k, (cuuint32_t)kTileCols, (cuuint32_t)kSlabRows, 1u};
+        if (int rc = tmap_encode_bf16(&p.a_map1, x1, 4, dims, strides, box, swz, "halo second input")) return rc;
     }
     {
         cuuint64_t dims[2] = {(cuuint64_t)9 * C, (cuuint64_t)Cout};
@@ -322,4 +340,16 @@ extern "C" int eds_conv3x3_halo_bf16(const void* x, int N, int H, int W, int C, 
     const int grid = (int)std::min<int64_t>(total, g_num_sms);
     conv3x3_halo_kernel<<<grid, kHaloThreads, smem, as_stream(stream)>>>(p);
     return check_launch("conv3x3_halo_kernel");
+}
+
+extern "C" int eds_conv3x3_halo_bf16(const void* x, int N, int H, int W, int C, const void* w, const float* bias,
+                                     int Cout, int relu, const void* residual, void* y, void* stream) {
+    return halo_launch(x, C, nullptr, 0, N, H, W, w, bias, Cout, relu, residual, y, stream);
+}
+
+extern "C" int eds_conv3x3_halo_bf16_2src(const void* x0, int C0, const void* x1, int C1, int N, int H, int W,
+                                          const void* w, const float* bias, int Cout, int relu, const void* residual,
+                                          void* y, void* stream) {
+    EDS_REQUIRE(x1 && C1 > 0, "conv3x3_halo_2src: second input missing");
+    return halo_launch(x0, C0, x1, C1, N, H, W, w, bias, Cout, relu, residual, y, stream);
 }

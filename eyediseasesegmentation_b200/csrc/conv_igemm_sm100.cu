@@ -35,6 +35,8 @@ constexpr int kTileM = 128;
 
 struct IgemmParams {
     CUtensorMap a_map[4];
+    CUtensorMap a_map1;     // optional second input (channels C0.. of the concatenated K axis), stride 1 only
+    int k_split;            // channel chunks served by a_map (== k_chunks when there is one input)
     CUtensorMap b_map;
     const float* bias;
     const __nv_bfloat16* residual;
@@ -119,8 +121,12 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
                                           (uint32_t)(kTileM * p.block_k * 2 + p.block_n * p.block_k * 2));
                     uint8_t* sa = smem + (size_t)stage * stage_bytes;
                     uint8_t* sb = sa + p.a_stage_bytes;
-                    tma_load_4d(sa, &p.a_map[p.tap_plane[tap]], &full_bar[stage], kc * p.block_k, w0 + p.tap_dw[tap],
-                                h0 + p.tap_dh[tap], n0);
+                    if (kc < p.k_split)
+                        tma_load_4d(sa, &p.a_map[p.tap_plane[tap]], &full_bar[stage], kc * p.block_k,
+                                    w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
+                    else
+                        tma_load_4d(sa, &p.a_map1, &full_bar[stage], (kc - p.k_split) * p.block_k,
+                                    w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
                     tma_load_2d(sb, &p.b_map, &full_bar[stage], tap * p.C + kc * p.block_k, n_tile * p.block_n);
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
@@ -345,12 +351,17 @@ int tmap_encode_bf16(CUtensorMap* map, const void* base, int rank, const cuuint6
 
 using namespace eds;
 
-extern "C" int eds_conv2d_igemm_bf16(const void* x, int N, int H, int W, int C, const void* w, const float* bias,
-                                     int Cout, int R, int S, int stride, int pad, int relu, const void* residual,
-                                     void* y, void* stream) {
+// x: [N][H][W][C0]; x1 (optional): [N][H][W][C1] -- the convolution of their channel concatenation
+static int igemm_launch(const void* x, int C0, const void* x1, int C1, int N, int H, int W, const void* w,
+                        const float* bias, int Cout, int R, int S, int stride, int pad, int relu, const void* residual,
+                        void* y, void* stream) {
+    const int C = C0 + C1;
     EDS_REQUIRE(x && w && y, "conv2d_igemm: null pointer");
     EDS_REQUIRE(N > 0 && H > 0 && W > 0, "conv2d_igemm: bad shape N=%d H=%d W=%d", N, H, W);
-    EDS_REQUIRE(C >= 16 && C % 16 == 0, "conv2d_igemm: C=%d must be a multiple of 16", C);
+    EDS_REQUIRE(C0 >= 16 && C0 % 16 == 0 && C1 >= 0 && C1 % 16 == 0 && (x1 != nullptr) == (C1 > 0),
+                "conv2d_igemm: C0=%d C1=%d must be multiples of 16", C0, C1);
+    EDS_REQUIRE(!x1 || stride == 1, "conv2d_igemm: two inputs need stride 1");
+    EDS_REQUIRE((((uintptr_t)x1) & 15) == 0, "conv2d_igemm: pointers must be 16-byte aligned");
     EDS_REQUIRE(Cout >= 16 && Cout % 16 == 0, "conv2d_igemm: Cout=%d must be a multiple of 16", Cout);
     EDS_REQUIRE(R == S && (R == 1 || R == 3), "conv2d_igemm: filter %dx%d not supported (1x1, 3x3)", R, S);
     EDS_REQUIRE(stride == 1 || stride == 2, "conv2d_igemm: stride=%d not supported", stride);
@@ -369,9 +380,9 @@ extern "C" int eds_conv2d_igemm_bf16(const void* x, int N, int H, int W, int C, 
     p.y = (__nv_bfloat16*)y;
     p.taps = R * S;
     p.C = C;
-    p.block_k = (C % 64 == 0) ? 64 : (C % 32 == 0 ? 32 : 16);
+    p.block_k = ((C0 | C1) % 64 == 0) ? 64 : ((C0 | C1) % 32 == 0 ? 32 : 16);   // divides both inputs
     p.k_chunks = C / p.block_k;
-    // cout tile: the largest multiple of 16 that divides Cout and is <= 256
+    p.k_split = C0 / p.block_k;
     const int k_iters = p.taps * p.k_chunks;
     // cout tile: the largest multiple of 16 that divides Cout and is <= 256 (two accumulators of
     // block_n fp32 columns fit the 512 columns of TMEM)
@@ -445,11 +456,20 @@ extern "C" int eds_conv2d_igemm_bf16(const void* x, int N, int H, int W, int C, 
         const int ph = stride == 1 ? 0 : pl >> 1, pw = stride == 1 ? 0 : pl & 1;
         const int Wp = (W - pw + stride - 1) / stride, Hp = (H - ph + stride - 1) / stride;
         EDS_REQUIRE(Wp > 0 && Hp > 0, "conv2d_igemm: empty parity plane");
-        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)N};
-        cuuint64_t strides[3] = {(cuuint64_t)stride * C * 2, (cuuint64_t)stride * W * C * 2, (cuuint64_t)H * W * C * 2};
+        cuuint64_t dims[4] = {(cuuint64_t)C0, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)stride * C0 * 2, (cuuint64_t)stride * W * C0 * 2,
+                                 (cuuint64_t)H * W * C0 * 2};
         cuuint32_t box[4] = {(cuuint32_t)p.block_k, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TN};
-        if (int rc = tmap_encode_bf16(&p.a_map[pl], xb + ((int64_t)ph * W + pw) * C, 4, dims, strides, box, swz, "input"))
+        if (int rc = tmap_encode_bf16(&p.a_map[pl], xb + ((int64_t)ph * W + pw) * C0, 4, dims, strides, box, swz, "input"))
             return rc;
+    }
+    if (x1) {
+        cuuint64_t dims[4] = {(cuuint64_t)C1, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)C1 * 2, (cuuint64_t)W * C1 * 2, (cuuint64_t)H * W * C1 * 2};
+        cuuint32_t box[4] = {(cuuint32_t)p.block_k, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TN};
+        if (int rc = tmap_encode_bf16(&p.a_map1, x1, 4, dims, strides, box, swz, "second input")) return rc;
+    } else {
+        p.a_map1 = p.a_map[p.tap_plane[0]];
     }
     if (!plane_used[0]) p.a_map[0] = p.a_map[p.tap_plane[0]];  // keep the prefetch target valid
     {
@@ -469,4 +489,17 @@ extern "C" int eds_conv2d_igemm_bf16(const void* x, int N, int H, int W, int C, 
     }
     conv_igemm_kernel<<<grid, kIgemmThreads, smem, as_stream(stream)>>>(p);
     return check_launch("conv_igemm_kernel");
+}
+
+extern "C" int eds_conv2d_igemm_bf16(const void* x, int N, int H, int W, int C, const void* w, const float* bias,
+                                     int Cout, int R, int S, int stride, int pad, int relu, const void* residual,
+                                     void* y, void* stream) {
+    return igemm_launch(x, C, nullptr, 0, N, H, W, w, bias, Cout, R, S, stride, pad, relu, residual, y, stream);
+}
+
+extern "C" int eds_conv2d_igemm_bf16_2src(const void* x0, int C0, const void* x1, int C1, int N, int H, int W,
+                                          const void* w, const float* bias, int Cout, int R, int S, int pad, int relu,
+                                          const void* residual, void* y, void* stream) {
+    EDS_REQUIRE(x1 && C1 > 0, "conv2d_igemm_2src: second input missing");
+    return igemm_launch(x0, C0, x1, C1, N, H, W, w, bias, Cout, R, S, 1, pad, relu, residual, y, stream);
 }

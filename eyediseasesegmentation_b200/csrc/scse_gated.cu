@@ -241,7 +241,7 @@ __device__ __forceinline__ void ld_gated(const T* p, const float2 (&cg)[4], cons
 template <typename T, int PART>
 __global__ void __launch_bounds__(256, 2)
 concat_gated_kernel(CatSrcs src, int h, int w, int mode, int Ctot, const float* __restrict__ cgate1,
-                    const float* __restrict__ sgate1, T* __restrict__ y) {
+                    const float* __restrict__ sgate1, T* __restrict__ y, int y_stride, int y_coff) {
     const uint32_t C8a = (uint32_t)src.s[0].C / 8;
     const uint32_t C8 = PART == 0 ? C8a : (uint32_t)Ctot / 8 - C8a;     // vectors per pixel of this part
     const uint32_t wp = (uint32_t)(w + 1) / 2;                          // column pairs per low-res row
@@ -340,17 +340,19 @@ concat_gated_kernel(CatSrcs src, int h, int w, int mode, int Ctot, const float* 
             for (int q = 0; q < 4; ++q) o[d][q] = __fmul2_rn(o[d][q], __fadd2_rn(g1[q], s1));
         }
     }
-    T* yp = y + p00 * Ctot + c8 * 8;
-    T* yq = yp + (int64_t)W * Ctot;
+    // y_stride = channels per pixel of the destination map, y_coff = first concat channel it holds
+    // (one map of Ctot channels, or one dense map per part so that every pixel row is written whole)
+    T* yp = y + p00 * y_stride + (c8 * 8 - y_coff);
+    T* yq = yp + (int64_t)W * y_stride;
     V8<T>::st(yp, o[0]);
-    V8<T>::st(yp + Ctot, o[1]);
+    V8<T>::st(yp + y_stride, o[1]);
     V8<T>::st(yq, o[4]);
-    V8<T>::st(yq + Ctot, o[5]);
+    V8<T>::st(yq + y_stride, o[5]);
     if (second) {
-        V8<T>::st(yp + 2 * Ctot, o[2]);
-        V8<T>::st(yp + 3 * Ctot, o[3]);
-        V8<T>::st(yq + 2 * Ctot, o[6]);
-        V8<T>::st(yq + 3 * Ctot, o[7]);
+        V8<T>::st(yp + 2 * y_stride, o[2]);
+        V8<T>::st(yp + 3 * y_stride, o[3]);
+        V8<T>::st(yq + 2 * y_stride, o[6]);
+        V8<T>::st(yq + 3 * y_stride, o[7]);
     }
 }
 
@@ -440,8 +442,9 @@ extern "C" int eds_sse_finalize(const float* dot0, const float* dot1, int N, int
     return check_launch("sse_finalize_kernel");
 }
 
-extern "C" int eds_concat_gated(const eds_gated_src* srcs, int n_srcs, int N, int h, int w, int mode,
-                                const float* cgate, const float* sgate, void* y, int dtype, void* stream) {
+static int concat_gated_launch(const eds_gated_src* srcs, int n_srcs, int N, int h, int w, int mode,
+                               const float* cgate, const float* sgate, void* y, void* y_skip, int dtype,
+                               void* stream) {
     EDS_REQUIRE(srcs && y, "concat_gated: null pointer");
     EDS_REQUIRE(n_srcs >= 1 && n_srcs <= 6, "concat_gated: n_srcs=%d not in 1..6", n_srcs);
     EDS_REQUIRE(mode == EDS_UP_NEAREST || mode == EDS_UP_BILINEAR, "concat_gated: mode %d (nearest / bilinear x2 only)",
@@ -465,15 +468,33 @@ extern "C" int eds_concat_gated(const eds_gated_src* srcs, int n_srcs, int N, in
     EDS_REQUIRE((int64_t)w * (Ctot / 8) < (1ll << 24) && (int64_t)N * h < (1ll << 31), "concat_gated: map too large");
     const int c8a = cs.s[0].C / 8, c8b = Ctot / 8 - c8a;
     const int wp = (w + 1) / 2;
+    EDS_REQUIRE(!y_skip || c8b > 0, "concat_gated: y_skip given without skip sources");
+    // one destination of Ctot channels, or two dense ones (upsampled part / skip part)
+    const int stride_a = y_skip ? cs.s[0].C : Ctot;
     dim3 grid_a((unsigned)(N * h), (unsigned)ceil_div(wp * c8a, 256));
     EDS_DISPATCH_DTYPE(dtype, T, (concat_gated_kernel<T, 0><<<grid_a, 256, 0, as_stream(stream)>>>(
-                                     cs, h, w, mode, Ctot, cgate, sgate, (T*)y)));
+                                     cs, h, w, mode, Ctot, cgate, sgate, (T*)y, stride_a, 0)));
     if (c8b > 0) {
         dim3 grid_b((unsigned)(N * h), (unsigned)ceil_div(wp * c8b, 256));
+        void* yb = y_skip ? y_skip : y;
+        const int stride_b = y_skip ? Ctot - cs.s[0].C : Ctot;
+        const int coff_b = y_skip ? cs.s[0].C : 0;
         EDS_DISPATCH_DTYPE(dtype, T, (concat_gated_kernel<T, 1><<<grid_b, 256, 0, as_stream(stream)>>>(
-                                         cs, h, w, mode, Ctot, cgate, sgate, (T*)y)));
+                                         cs, h, w, mode, Ctot, cgate, sgate, (T*)yb, stride_b, coff_b)));
     }
     return check_launch("concat_gated_kernel");
+}
+
+extern "C" int eds_concat_gated(const eds_gated_src* srcs, int n_srcs, int N, int h, int w, int mode,
+                                const float* cgate, const float* sgate, void* y, int dtype, void* stream) {
+    return concat_gated_launch(srcs, n_srcs, N, h, w, mode, cgate, sgate, y, nullptr, dtype, stream);
+}
+
+extern "C" int eds_concat_gated_split(const eds_gated_src* srcs, int n_srcs, int N, int h, int w, int mode,
+                                      const float* cgate, const float* sgate, void* y_up, void* y_skip, int dtype,
+                                      void* stream) {
+    EDS_REQUIRE(y_skip, "concat_gated_split: null pointer");
+    return concat_gated_launch(srcs, n_srcs, N, h, w, mode, cgate, sgate, y_up, y_skip, dtype, stream);
 }
 
 extern "C" int eds_apply_gate(const void* x, const float* cgate, const float* sgate, int N, int HW, int C, void* y,

@@ -176,16 +176,20 @@ def conv_out_hw(H: int, W: int, R: int, stride: int, pad: int):
 
 def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], stride: int = 1, pad: int = 0,
            relu: bool = False, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-           impl: str = "auto") -> torch.Tensor:
+           impl: str = "auto", x1: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x [N,H,W,C], w [Cout,R,S,C] (same dtype as x) -> [N,Ho,Wo,Cout].
 
     impl: "tc" = tcgen05 implicit GEMM (bf16 only), "simt" = CUDA-core kernel,
     "auto" = tc for bf16 activations, simt for fp32 (the fp32 parity mode).
     """
-    _chk(x, w, bias, residual, out)
+    _chk(x, w, bias, residual, out, x1)
     N, H, W_, Cin = x.shape
     Cout, R, S, Cw = w.shape
-    assert Cw == Cin and w.dtype == x.dtype
+    C1 = 0
+    if x1 is not None:          # convolution of cat([x, x1], channel) without building it (tensor-core kernels)
+        assert x1.shape[:3] == x.shape[:3] and x1.dtype == x.dtype and stride == 1
+        C1 = x1.shape[3]
+    assert Cw == Cin + C1 and w.dtype == x.dtype
     Ho, Wo = conv_out_hw(H, W_, R, stride, pad)
     if out is None:
         out = torch.empty((N, Ho, Wo, Cout), dtype=x.dtype, device=x.device)
@@ -198,8 +202,16 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], strid
         if trace is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        if impl == "halo" or (impl == "tc" and HALO_MIN_HW and min(H, W_) >= HALO_MIN_HW and
-                              _lib.load().eds_conv3x3_halo_supported(Cin, Cout, R, S, stride, pad)):
+        halo = impl == "halo" or (impl == "tc" and HALO_MIN_HW and min(H, W_) >= HALO_MIN_HW and
+                                  _lib.load().eds_conv3x3_halo_supported(Cin + C1, Cout, R, S, stride, pad))
+        if x1 is not None:
+            if halo:
+                check(_lib.lib().eds_conv3x3_halo_bf16_2src(_p(x), Cin, _p(x1), C1, N, H, W_, _p(w), _p(bias), Cout,
+                                                            int(relu), _p(residual), _p(out), _stream()))
+            else:
+                check(_lib.lib().eds_conv2d_igemm_bf16_2src(_p(x), Cin, _p(x1), C1, N, H, W_, _p(w), _p(bias), Cout,
+                                                            R, S, pad, int(relu), _p(residual), _p(out), _stream()))
+        elif halo:
             check(_lib.lib().eds_conv3x3_halo_bf16(_p(x), N, H, W_, Cin, _p(w), _p(bias), Cout, int(relu),
                                                    _p(residual), _p(out), _stream()))
         else:
@@ -207,8 +219,11 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], strid
                                                    int(relu), _p(residual), _p(out), _stream()))
         if trace is not None:
             ev1.record()
-            trace.append((2.0 * N * Ho * Wo * Cout * R * S * Cin, ev0, ev1, (N, H, W_, Cin, Cout, R, stride)))
+            trace.append((2.0 * N * Ho * Wo * Cout * R * S * (Cin + C1), ev0, ev1,
+                          (N, H, W_, Cin + C1, Cout, R, stride)))
     elif impl == "simt":
+        if x1 is not None:
+            raise ValueError("the CUDA-core kernel takes one input: concatenate first")
         check(_lib.lib().eds_conv2d_simt(_p(x), N, H, W_, Cin, _p(w), _p(bias), Cout, R, S, stride, pad, int(relu),
                                          _p(residual), _p(out), _dt(x), _stream()))
     else:
@@ -379,6 +394,27 @@ def sse_finalize(dot0: Optional[torch.Tensor], dot1: Optional[torch.Tensor], mod
     assert out.shape == (N, up * h, up * w)
     check(_lib.lib().eds_sse_finalize(_p(dot0), _p(dot1), N, h, w, mode, float(b_sse), _p(out), _stream()))
     return out
+
+
+def concat_gated_split(srcs, mode: int, cgate: Optional[torch.Tensor] = None, sgate: Optional[torch.Tensor] = None):
+    """Like concat_gated but into TWO dense maps: (up2x(src 0) [N,2h,2w,C0], cat(src 1..) [N,2h,2w,sum Ck]),
+    each gated with its channel slice of cgate; the pair feeds conv2d(x, ..., x1=...)."""
+    x0 = srcs[0][0]
+    N, h, w, C0 = x0.shape
+    assert len(srcs) >= 2
+    c_skip = sum(t[0].shape[3] for t in srcs[1:])
+    arr = (_lib.GatedSrc * len(srcs))()
+    for k, (x, cg, sg) in enumerate(srcs):
+        _chk(x, cg, sg)
+        assert x.dtype == x0.dtype and x.shape[:3] == ((N, h, w) if k == 0 else (N, 2 * h, 2 * w))
+        arr[k].x, arr[k].cgate, arr[k].sgate, arr[k].C = _p(x), _p(cg), _p(sg), x.shape[3]
+    _chk(cgate, sgate)
+    y_up = torch.empty((N, 2 * h, 2 * w, C0), dtype=x0.dtype, device=x0.device)
+    y_skip = torch.empty((N, 2 * h, 2 * w, c_skip), dtype=x0.dtype, device=x0.device)
+    check(_lib.lib().eds_concat_gated_split(arr, len(srcs), N, h, w, mode, _p(cgate), _p(sgate), _p(y_up), _p(y_skip),
+                                            _dt(x0), _stream()))
+    LAUNCHES[0] += 1            # two kernels
+    return y_up, y_skip
 
 
 def concat_gated(srcs, mode: int, cgate: Optional[torch.Tensor] = None, sgate: Optional[torch.Tensor] = None,

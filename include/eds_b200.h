@@ -210,6 +210,16 @@ EDS_API int eds_conv3x3_halo_supported(int C, int Cout, int R, int S, int stride
 EDS_API int eds_conv3x3_halo_bf16(const void* x, int N, int H, int W, int C, const void* w, const float* bias,
                                   int Cout, int relu, const void* residual, void* y, void* stream);
 
+/* Convolution of the channel concatenation cat(x0 [N][H][W][C0], x1 [N][H][W][C1]) without building it:
+ * the K loop walks the channel chunks of x0, then of x1, through two tensor maps (stride 1; w is
+ * [Cout][R][S][C0+C1]).  Same contract otherwise as the single-input forms above. */
+EDS_API int eds_conv2d_igemm_bf16_2src(const void* x0, int C0, const void* x1, int C1, int N, int H, int W,
+                                       const void* w, const float* bias, int Cout, int R, int S, int pad, int relu,
+                                       const void* residual, void* y, void* stream);
+EDS_API int eds_conv3x3_halo_bf16_2src(const void* x0, int C0, const void* x1, int C1, int N, int H, int W,
+                                       const void* w, const float* bias, int Cout, int relu, const void* residual,
+                                       void* y, void* stream);
+
 /* ---- SCSE with deferred gates (the product path of the decoders; scse_gated.cu) ----------------
  * A "gated source" is a map whose SCSE gate has not been applied yet:
  *     value[n][p][c] = x[n][p][c] * (cgate[n][c] + sgate[n][p])     (cgate == sgate == NULL: plain map)
@@ -241,6 +251,14 @@ EDS_API int eds_sse_finalize(const float* dot0, const float* dot1, int N, int h,
  * plain concat of the (gated) sources. */
 EDS_API int eds_concat_gated(const eds_gated_src* srcs, int n_srcs, int N, int h, int w, int mode,
                              const float* cgate, const float* sgate, void* y, int dtype, void* stream);
+
+/* The same with TWO dense destinations: y_up [N][2h][2w][C0] holds the upsampled source 0, y_skip
+ * [N][2h][2w][sum C1..] the other sources, so every pixel row of either map is written whole (a single
+ * Ctot-wide map is written in two interleaved passes, which costs DRAM write efficiency).  The pair is
+ * consumed by eds_conv2d_igemm_bf16_2src / eds_conv3x3_halo_bf16_2src. */
+EDS_API int eds_concat_gated_split(const eds_gated_src* srcs, int n_srcs, int N, int h, int w, int mode,
+                                   const float* cgate, const float* sgate, void* y_up, void* y_skip, int dtype,
+                                   void* stream);
 
 /* y = x * (cgate[n][c] + sgate[n][p]) (materialise a gated map; y may alias x). */
 EDS_API int eds_apply_gate(const void* x, const float* cgate, const float* sgate, int N, int HW, int C, void* y,

@@ -578,3 +578,47 @@ def test_deferred_gate_scse(C0, skip_ch, mode, gated, dtype):
     z = K.apply_gate(x, cg2, s2)
     refz = x.float() * (cg2.view(N, 1, 1, c) + s2.unsqueeze(-1))
     assert (z.float() - refz).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("case", [
+    # N, H, W, C0, C1, Cout, R, impl
+    (2, 64, 64, 64, 192, 64, 3, "halo"), (1, 40, 24, 128, 64, 32, 3, "halo"), (1, 64, 64, 32, 32, 16, 3, "halo"),
+    (1, 32, 32, 512, 512, 256, 3, "tc"), (2, 16, 16, 256, 64, 512, 3, "tc"), (1, 24, 40, 64, 192, 128, 1, "tc"),
+    (1, 64, 64, 64, 16, 64, 3, "halo"),      # block_k falls to 16 (must divide both inputs)
+])
+def test_conv_two_inputs_equals_conv_of_concat(case):
+    """conv2d(x0, ..., x1=x1) walks the channel chunks of x0 then x1 through two tensor maps: same result as
+    the single-input kernel on torch.cat([x0, x1]) and as the fp32 reference."""
+    N, H, W, C0, C1, Cout, R, impl = case
+    x0 = rnd(N, H, W, C0, seed=21).bfloat16()
+    x1 = rnd(N, H, W, C1, seed=22).bfloat16()
+    w = rnd(Cout, R, R, C0 + C1, seed=23, scale=1.0 / math.sqrt(R * R * (C0 + C1))).bfloat16()
+    b = rnd(Cout, seed=24)
+    y2 = K.conv2d(x0, w, b, 1, R // 2, True, None, impl=impl, x1=x1)
+    cat = torch.cat([x0, x1], dim=-1).contiguous()
+    y1 = K.conv2d(cat, w, b, 1, R // 2, True, None, impl=impl)
+    ref = conv_ref(cat, w, b, 1, R // 2, True, None)
+    tol = 1e-2 * max(1.0, ref.abs().max().item())
+    assert (y2.float() - ref).abs().max().item() < tol and rel_err(y2, ref) < 4e-3
+    assert (y2.float() - y1.float()).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item()) / 4
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_concat_gated_split_equals_single_map(mode):
+    """Two dense destinations hold exactly the channel slices of the single concatenated map."""
+    N, h, w = 2, 7, 5
+    srcs = []
+    for k, c in enumerate([64, 32, 48]):
+        hh, ww = (h, w) if k == 0 else (2 * h, 2 * w)
+        x = rnd(N, hh, ww, c, seed=30 + k).bfloat16()
+        g = torch.Generator(DEV).manual_seed(40 + k)
+        srcs.append((x, torch.rand(N, c, device=DEV, generator=g), torch.rand(N, hh, ww, device=DEV, generator=g))
+                    if k != 1 else (x, None, None))
+    cg = torch.rand(N, 144, device=DEV)
+    sg = torch.rand(N, 2 * h, 2 * w, device=DEV)
+    one = K.concat_gated(srcs, mode, cg, sg)
+    up, skip = K.concat_gated_split(srcs, mode, cg, sg)
+    assert torch.equal(up, one[..., :64].contiguous()) and torch.equal(skip, one[..., 64:].contiguous())
+    up2, skip2 = K.concat_gated_split(srcs, mode)
+    one2 = K.concat_gated(srcs, mode)
+    assert torch.equal(up2, one2[..., :64].contiguous()) and torch.equal(skip2, one2[..., 64:].contiguous())
