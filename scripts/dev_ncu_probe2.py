@@ -39,7 +39,8 @@ for ax in (0, 1):
 # stem (8 views of one tile), merge, paste, preprocess
 x = torch.randn(1, 3, 1024, 1024, device=dev)
 aug, deaug = tta.view_maps(tta.aliases.d4_transform(), 1024, 1024)
-K.stem_conv(x, aug, torch.randn(7, 7, 3, 64, device=dev), torch.zeros(64, device=dev), torch.bfloat16)
+wst = torch.randn(7, 7, 3, 64, device=dev)
+K.stem_conv_mma(x, aug, K.stem_pack_weights(wst), torch.zeros(64, device=dev))
 logits = torch.randn(8, 6, 1024, 1024, device=dev)
 prob = K.tta_merge(logits, deaug, True)
 full = torch.zeros(2848, 4288, device=dev)
