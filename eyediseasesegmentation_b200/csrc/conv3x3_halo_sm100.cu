@@ -289,6 +289,7 @@ static int halo_launch(const void* x, int C0, const void* x1, int C1, int N, int
     p.y = (__nv_bfloat16*)y;
     p.C = C;
     p.block_k = ((C0 | C1) % 64 == 0) ? 64 : ((C0 | C1) % 32 == 0 ? 32 : 16);   // divides both inputs
+    if (const char* bk = getenv("EDS_HALO_BK")) { const int v = atoi(bk); if ((v == 32 || v == 16) && (C0 | C1) % v == 0) p.block_k = std::min(p.block_k, v); }
     p.k_chunks = C / p.block_k;
     p.k_split = C0 / p.block_k;
     p.bn = Cout;

@@ -220,3 +220,22 @@ def test_stat_metrics_from_counts_follow_the_reference_formulas():
                 (2 * true_p + EPS * (union == 0).astype("float")) / (true_p + actual_p + false_p + EPS))
         got = metrics_from_counts(int(true_p), int(actual_p), int(pred_p), arr_gt.size)
         assert all(str(float(a)) == str(float(b)) for a, b in zip(got, want))
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the reference's CPU path = the oracle port, on the host cores): exactly one
+    JSON line on stdout with the keys the driver reads; nothing else on stdout."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, res.stdout
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "images/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"]
