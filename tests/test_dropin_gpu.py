@@ -132,3 +132,75 @@ def test_vessel_test_tta_from_disk_to_disk(tmp_path, fp32_mode):
     stat_result_vessel.export_result("Vessel_DRIVE/vexp", config)
     rows = helpers.read_stat_csvs(out_dir / "DRIVE" / "result_assessment" / "Vessel_DRIVE" / "vexp")
     assert set(rows["sn"]) == {n for _, _, n in items} | {"Avg:"}
+
+
+def test_lesion_test_tta_whole_image_from_disk_to_disk(tmp_path, fp32_mode):
+    """tta.test_tta (tta.py:56-148), BASELINE config 1 network (smp.Unet / resnet34): LongestMaxSize(1024) +
+    centred pad on the host, batch of 2 through hflip TTA, sigmoid, centre crop + bilinear resize back to the
+    original size, PR scoring at the original size, masks written under the image name."""
+    import cv2
+    name, cfg = "Unet", dict(encoder_name="resnet34", encoder_weights=None, classes=1)
+    model = helpers.build_product_model(name, cfg)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    sd["segmentation_head.0.weight"] *= 6.0            # spread the random-init logits across the thresholds
+    sd["segmentation_head.0.bias"] -= 1.0
+    logdir = tmp_path / "models" / "IDRiD" / "EX" / "whole"
+    (logdir / "checkpoints").mkdir(parents=True)
+    torch.save({"model_state_dict": sd}, logdir / "checkpoints" / "best.pth")
+    img_dir = tmp_path / "wdata" / "images"
+    mask_root = tmp_path / "wdata" / "masks"
+    mask_dir = mask_root / "3. Hard Exudates"
+    img_dir.mkdir(parents=True)
+    mask_dir.mkdir(parents=True)
+    H0, W0 = 356, 536                                  # 1/8 of IDRiD's 2848 x 4288: same aspect, same pad geometry
+    S = 1024
+    mean, std = pipeline.DATASET_STATS["IDRiD"]
+    scale = S / max(H0, W0)
+    nh, nw = int(round(H0 * scale)), int(round(W0 * scale))
+    top, left = int((S - nh) / 2.0), int((S - nw) / 2.0)
+
+    # oracle first: its probability maps also define ground truths the random-init network "knows"
+    preds = []
+    for i in range(2):
+        Image.fromarray(_fundus(H0, W0, 60 + i)).save(img_dir / f"IDRiD_{i:02d}.jpg", quality=95)
+        image = np.asarray(Image.open(img_dir / f"IDRiD_{i:02d}.jpg").convert("RGB")).astype("uint8")
+        small = cv2.resize(image, (nw, nh), interpolation=cv2.INTER_LINEAR)
+        padded = np.zeros((S, S, 3), dtype=np.uint8)
+        padded[top:top + nh, left:left + nw] = small
+        x = torch.from_numpy(pipeline.preprocess(padded, mean, std).transpose(2, 0, 1)).float()[None]
+        with torch.no_grad():
+            logit = nets.tta_mean_logits(lambda t: nets.unet_forward(sd, t), x, "hflip")[0, 0]
+        pred = pipeline.whole_image_probability(torch.sigmoid(logit).numpy(), (nh, nw), (H0, W0))
+        preds.append(pred)
+        rng = np.random.default_rng(70 + i)
+        top30 = np.zeros(pred.size, dtype=bool)
+        top30[np.argsort(pred.ravel(), kind="stable")[-int(0.3 * pred.size):]] = True      # rank based: ties cannot empty it
+        gt = (top30.reshape(pred.shape) ^ (rng.random(pred.shape) < 0.05)).astype(np.uint8) * 255
+        Image.fromarray(gt, "L").save(mask_dir / f"IDRiD_{i:02d}_EX.tif")
+
+    out_dir = tmp_path / "woutputs"
+    config = {"dataset_name": "IDRiD", "lesion_type": "EX", "gray": False, "scale_size": S, "val_batch_size": 2,
+              "model_name": name, "model_params": dict(cfg), "test_img_path": img_dir, "test_mask_path": mask_root,
+              "out_dir": str(out_dir), "data_type": "all"}
+    eds_tta.test_tta(str(logdir), config, {"best": "true", "tta": "hflip"})
+
+    items = []
+    for i in range(2):
+        m = (np.asarray(Image.open(mask_dir / f"IDRiD_{i:02d}_EX.tif").convert("L")) > 50).astype(np.uint8)
+        ms = cv2.resize(m, (nw, nh), interpolation=cv2.INTER_NEAREST)
+        mp = np.zeros((S, S), dtype=np.uint8)
+        mp[top:top + nh, left:left + nw] = ms
+        gt = cv2.resize(mp[(S - nh) // 2:(S - nh) // 2 + nh, (S - nw) // 2:(S - nw) // 2 + nw], (W0, H0),
+                        interpolation=cv2.INTER_LINEAR)
+        items.append((preds[i], gt, f"IDRiD_{i:02d}.jpg"))
+    t3 = scoring.pr_curve(items)["thresholds"][2]
+    written = out_dir / "IDRiD" / "tta" / "EX" / "whole"
+    assert sorted(p.name for p in written.iterdir()) == [n for _, _, n in items]
+    for pred, _, n in items:
+        got = np.asarray(Image.open(written / n).convert("L")) > 127
+        assert got.shape == pred.shape
+        want = pred > t3
+        if want.all():                                 # save_output min-max rescales: a constant mask is saved black
+            want = np.zeros_like(want)
+        assert 0.02 < want.mean() < 0.98, "degenerate test image"
+        assert np.mean(got != want) < 5e-3, n
