@@ -188,10 +188,14 @@ def run_b200(args):
         barrier()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
+        pooled = torch.zeros(2 * 19 + 2, dtype=torch.int64, device=dev)
         for i in range(steps):
-            fn((warmup + i) % distinct)
+            out = fn((warmup + i) % distinct)
+            if world > 1 and out and isinstance(out[0], tuple) and len(out[0]) == 4:
+                for (_ap, _roc, counts, totals) in out:      # this rank's pooled (tp, pp) per threshold + totals
+                    pooled[:38] += counts.reshape(-1)
+                    pooled[38:] += totals.reshape(-1)
         if world > 1:                              # the path's single collective: pooled integer counts
-            pooled = torch.zeros(2 * 19 + 2, dtype=torch.int64, device=dev)
             dist.all_reduce(pooled)
         t1.record()
         barrier()
