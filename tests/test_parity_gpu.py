@@ -148,3 +148,23 @@ def test_cuda_graph_replay_equals_eager(precision, monkeypatch):
                 other = (got - want[mi][(xi + 1) % 3]).abs().max().item()
                 assert other > 10 * err + 1e-3
     assert all(any(isinstance(v, tuple) and v[3] > 100 for v in m._graphs.values()) for m in models), "no graph was captured"
+
+
+def test_full_size_tile_matches_oracle():
+    """BASELINE config 3 at its real size: the proposed network (base_dim 32) on one 1024 x 1024 tile with
+    8-view D4 TTA -- every layer shape of the benchmark (K = 9216 reductions, 512^2 x 448-channel halo
+    layers, attention over 64-long sequences) against the fp32 oracle: 1e-4 in fp32 mode, 2e-2 in bf16."""
+    name, cfg = "unetplusplusstar", star_cfg(32)
+    model = _build(name, cfg)
+    sd = model.state_dict()
+    x = _input(1, 1024, seed=5)
+    with torch.no_grad():
+        want = torch.sigmoid(nets.tta_mean_logits(lambda t: nets.forward(name, sd, t, cfg), x, "d4"))[0, 0]
+    model = model.to("cuda")
+    tfm = tta.aliases.d4_transform()
+    for precision, tol in (("fp32", 1e-4), ("bf16", 2e-2)):
+        model.precision = precision
+        got = model.forward_tta(x.cuda(), tfm, apply_sigmoid=True)[0, 0].cpu()
+        err = (got - want).abs().max().item()
+        assert err < tol, f"{precision}: max |dprob| {err}"
+        assert rel_l2(got - got.mean(), want - want.mean()) < (1e-4 if precision == "fp32" else 8e-2)
