@@ -339,11 +339,20 @@ class Engine:
         else:
             if skips and (p + ".attention1.sse") in self.w:
                 cat = self._concat_scse(p + ".attention1", x, skips)
+            elif (not skips and self.conv_impl == "tc" and K.FUSED_TAIL and
+                  _lib.load().eds_conv3x3_small_supported(x.shape[3], self.w[p + ".conv1"][0].shape[0])):
+                # last block: no skip, no attention1 -- upsampling (and the pending gate of x) is fused into
+                # conv1's tile loader, the upsampled map is never written
+                t, cg, sg = _parts(x)
+                w1, b1 = self.w[p + ".conv1"]
+                cat = None
+                y = K.conv3x3_small(t, w1, b1, True, self.up_mode, cg, sg)
             else:
                 srcs = [_parts(x)] + [_parts(t) for t in skips]
                 cat = K.concat_gated_split(srcs, self.up_mode) if self._split_ok(srcs) else \
                     K.concat_gated(srcs, self.up_mode)
-        y = self._cv(cat, p + ".conv1", pad=1, relu=True)
+        if cat is not None:
+            y = self._cv(cat, p + ".conv1", pad=1, relu=True)
         y = self._cv(y, p + ".conv2", pad=1, relu=True)
         if (p + ".down_sample") not in self.w:
             y = self._apply_scse(p + ".attention2", y)

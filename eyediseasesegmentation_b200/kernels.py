@@ -21,6 +21,12 @@ CONV_TRACE = None
 #: 3x3 s1 p1 convolutions with Cout <= 128 on maps at least this large take the halo-reuse kernel
 #: (0 disables it; EDS_HALO_MIN_HW overrides)
 HALO_MIN_HW = int(__import__("os").environ.get("EDS_HALO_MIN_HW", "64"))
+#: 3x3 s1 p1 convolutions with C and Cout in {16, 32} (the full-resolution decoder tail) take the mma.sync
+#: kernel of conv3x3_small.cu (EDS_SMALL_CONV=0 sends them to the implicit-GEMM kernels)
+SMALL_CONV = __import__("os").environ.get("EDS_SMALL_CONV", "1") != "0"
+#: fuse the x2 upsampling of the last decoder block into conv1's tile loader (conv3x3_small.cu, UP modes).
+#: Off by default: 4.8 ms vs 3.6 ms for concat + halo conv at 48 maps -- 32 input channels on mma.sync.
+FUSED_TAIL = __import__("os").environ.get("EDS_FUSED_TAIL", "0") != "0"
 
 
 def check(rc: int) -> None:
@@ -202,6 +208,12 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], strid
         if trace is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
+        # measured (48 maps): 16 -> 16 @1024^2 1.7 ms here vs 2.4 ms on the tcgen05 halo kernel; with 32 input
+        # channels the legacy mma.sync pipe (~100 TFLOP/s in these kernels) loses to tcgen05 (32 -> 32 @512^2:
+        # 2.2 ms vs 0.6 ms), so only the 16-channel layers are routed here
+        if (impl == "tc" and SMALL_CONV and Cin == 16 and x1 is None and residual is None and R == 3 and S == 3 and
+                stride == 1 and pad == 1 and _lib.load().eds_conv3x3_small_supported(Cin, Cout)):
+            return conv3x3_small(x, w, bias, relu, out=out)
         halo = impl == "halo" or (impl == "tc" and HALO_MIN_HW and min(H, W_) >= HALO_MIN_HW and
                                   _lib.load().eds_conv3x3_halo_supported(Cin + C1, Cout, R, S, stride, pad))
         if x1 is not None:
@@ -228,6 +240,32 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], strid
                                          _p(residual), _p(out), _dt(x), _stream()))
     else:
         raise ValueError(impl)
+    return out
+
+
+def conv3x3_small(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = True,
+                  up_mode: int = _lib.UP_NONE, cgate: Optional[torch.Tensor] = None,
+                  sgate: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Decoder-tail 3x3 convolution (C, Cout in {16, 32}, bf16) on mma.sync; with up_mode nearest / bilinear the
+    input is the LOW-resolution map [N,h,w,C] (optionally with its pending SCSE gate) and the x2 upsampling is
+    fused into the tile loader.  -> [N, H, W, Cout]."""
+    _chk(x, w, bias, cgate, sgate, out)
+    N, h, w_, Cin = x.shape
+    Cout = w.shape[0]
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.shape == (Cout, 3, 3, Cin)
+    up = 1 if up_mode == _lib.UP_NONE else 2
+    H, W_ = up * h, up * w_
+    if out is None:
+        out = torch.empty((N, H, W_, Cout), dtype=x.dtype, device=x.device)
+    trace = CONV_TRACE
+    if trace is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    check(_lib.lib().eds_conv3x3_small_bf16(_p(x), _p(cgate), _p(sgate), up_mode, N, H, W_, Cin, _p(w), _p(bias), Cout,
+                                            int(relu), _p(out), _stream()))
+    if trace is not None:
+        ev1.record()
+        trace.append((2.0 * N * H * W_ * Cout * 9 * Cin, ev0, ev1, (N, H, W_, Cin, Cout, 3, 1)))
     return out
 
 
