@@ -15,7 +15,9 @@
 //            Stride-2 convolutions read one of four parity planes of the input (plain strided
 //            tensor maps), so every tap is still a dense box.
 //   B tile : TMA box [block_k][block_n] of the [Cout][taps*C] weight matrix.
-//   D      : 128 TMEM lanes x block_n fp32 columns.
+//   D      : 128 TMEM lanes x block_n fp32 columns, two buffers (epilogue of tile t overlaps tile t+1).
+//   A second input map can follow the first along K (decoder concat read as two dense maps).
+// Persistent: grid = min(#tiles, #SMs), the TMA ring runs across tile boundaries.
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2-9 = epilogue (TMEM -> registers -> bias/residual/ReLU -> bf16 -> swizzled shared memory ->
 // one TMA bulk tensor store per 64-channel group).

@@ -1,4 +1,7 @@
-// Decoder concat + SCSE in two streaming passes.
+// Decoder concat + SCSE in two streaming passes -- the FIRST formulation, kept for already materialised maps
+// and as an independent cross-check in the tests.  The networks run the deferred-gate formulation of
+// scse_gated.cu (per-source statistics at native resolution + one gated write of the concat), which moves
+// 40 % fewer bytes; see DESIGN.md 3.3.
 //
 // Reference: DecoderBlock.forward (src/main/archs/unetplusplusstar.py:127-161):
 //     x_up = interpolate(x, 2, bilinear); x = cat([x_up, skip]); x = attention1(x)   # smp SCSEModule
@@ -14,7 +17,7 @@
 // ONE 8-channel vector (chunk*32 + L) of every pixel it visits, so its channel sums and sSE
 // weights live in 16 registers, every global access is a contiguous 512 B per warp instruction,
 // and the low register count keeps ~40 warps per SM in flight (the first version held 4
-// vectors per lane, ran 16 warps/SM and reached 31 % of HBM: profiles/r01_ncu_summary.md).
+// vectors per lane, ran 16 warps/SM and reached 31 % of HBM).
 #include "common.cuh"
 
 namespace eds {
