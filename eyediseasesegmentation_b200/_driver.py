@@ -172,8 +172,11 @@ def tiled_probability_map(model, transforms, image_dev: torch.Tensor, S: int, me
         for j, (x1, _, y1, _) in enumerate(group):
             K.preprocess_tile(image_dev, int(x1), int(y1), S, mean, std, out=x[j])
         prob = predict_probs(model, transforms, x)
-        for j, (x1, _, y1, _) in enumerate(group):
-            K.resize_paste(prob[j], preds, (0, 0, S, S), (int(x1), int(y1)), (2 * S, 2 * S))
+        if len(group) <= 32:
+            K.paste_tiles_x2(prob.contiguous(), preds, [(int(x1), int(y1)) for (x1, _, y1, _) in group])
+        else:
+            for j, (x1, _, y1, _) in enumerate(group):
+                K.resize_paste(prob[j], preds, (0, 0, S, S), (int(x1), int(y1)), (2 * S, 2 * S))
     return preds
 
 

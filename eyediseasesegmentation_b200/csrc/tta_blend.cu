@@ -9,6 +9,7 @@
 // All three are HBM-bound streaming kernels; the flip / rot90 views are never
 // materialised, they are index maps applied while reading.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace eds {
 
@@ -79,6 +80,103 @@ tta_merge_kernel(const float* __restrict__ logits, int V, int B, int S, ViewMaps
     }
 }
 
+// The same merge for S % 64 == 0 (every production tile size): one CTA (1024 / ROWS threads) = one 64x64 output
+// tile, a thread owns ROWS rows x 4 adjacent columns and moves 16-byte vectors only -- a quarter of the load
+// instructions of the kernel above and no per-element address arithmetic, which is what bounded it
+// (issue-bound at 0.40 of HBM peak).  Views are taken in two groups of four (4 * ROWS vector loads in flight per
+// thread, two CTAs per SM); the running sum is still formed in view order, so the result is bit-identical.
+// Transposing views are read along THEIR rows and turned through shared memory: [64][64] floats per view,
+// column index XORed with f(row) = ((row>>2)&7)<<2 | ((row>>5)&1)<<1, which makes the scalar stores of a
+// warp hit 32 distinct banks and keeps every aligned group of 4 columns inside one 16-byte word (its two
+// pairs swapped when bit 5 of the row is set) so the read-back is one LDS.128.
+constexpr int kMergeTile = 64;
+__device__ __forceinline__ int merge_swz(int row) { return (((row >> 2) & 7) << 2) | (((row >> 5) & 1) << 1); }
+
+template <int ROWS, int MINB>
+__global__ void __launch_bounds__(1024 / ROWS, MINB)
+tta_merge64_kernel(const float* __restrict__ logits, int V, int B, int S, ViewMaps maps, int apply_sigmoid,
+                   float* __restrict__ prob) {
+    extern __shared__ __align__(16) float mtile[];      // [4][64][64]
+    const int tid = threadIdx.x;
+    const int l16 = tid & 15, rg = tid >> 4;
+    const int b = blockIdx.z;
+    const int I0 = blockIdx.y * kMergeTile, J0 = blockIdx.x * kMergeTile;
+    constexpr int RSTEP = kMergeTile / ROWS;   // rows rg + RSTEP * r
+    float4 acc[ROWS];
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        if (g * 4 >= V) break;
+        float4 val[4][ROWS];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int v = g * 4 + u;
+            if (v >= V) continue;
+            const int* m = maps.m[v];
+            const float* src = logits + ((int64_t)v * B + b) * S * S;
+            if (m[1] == 0) {       // straight: output (i, j..j+3) <- source row m0*i+m2, columns m4*j+m5 (reversed if m4<0)
+                const float* p = src + (m[4] > 0 ? J0 + 4 * l16 + m[5] : m[5] - J0 - 4 * l16 - 3);
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r)
+                    val[u][r] = __ldg(reinterpret_cast<const float4*>(p + (int64_t)(m[0] * (I0 + rg + RSTEP * r) + m[2]) * S));
+            } else {               // transposing: the tile's source block, rows q = rg + 16r, columns 4*l16..+3
+                const int row0 = m[1] > 0 ? J0 + m[2] : m[2] - J0 - (kMergeTile - 1);
+                const int col0 = m[3] > 0 ? I0 + m[5] : m[5] - I0 - (kMergeTile - 1);
+                const float* p = src + (int64_t)(row0 + rg) * S + col0 + 4 * l16;
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r)
+                    val[u][r] = __ldg(reinterpret_cast<const float4*>(p + (int64_t)(RSTEP * r) * S));
+            }
+        }
+        if (g) __syncthreads();        // the previous group's tiles have been read
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int v = g * 4 + u;
+            if (v >= V || maps.m[v][1] == 0) continue;
+            const int* m = maps.m[v];
+            float* t = mtile + u * kMergeTile * kMergeTile;
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                const int q = rg + RSTEP * r;
+                const int jl = m[1] > 0 ? q : kMergeTile - 1 - q;
+                const float e[4] = {val[u][r].x, val[u][r].y, val[u][r].z, val[u][r].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int il = m[3] > 0 ? 4 * l16 + k : kMergeTile - 1 - 4 * l16 - k;
+                    t[il * kMergeTile + (jl ^ merge_swz(il))] = e[k];
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int v = g * 4 + u;
+            if (v >= V) continue;
+            const int* m = maps.m[v];
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                float4 x = val[u][r];
+                if (m[1] == 0) {
+                    if (m[4] < 0) x = make_float4(x.w, x.z, x.y, x.x);
+                } else {
+                    const int il = rg + RSTEP * r;
+                    const float4 w = *reinterpret_cast<const float4*>(mtile + u * kMergeTile * kMergeTile +
+                                                                      il * kMergeTile + ((l16 ^ ((il >> 2) & 7)) << 2));
+                    x = (il & 32) ? make_float4(w.z, w.w, w.x, w.y) : w;
+                }
+                if (v == 0) acc[r] = x;
+                else { acc[r].x += x.x; acc[r].y += x.y; acc[r].z += x.z; acc[r].w += x.w; }
+            }
+        }
+    }
+    const float fv = (float)V;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        float4 o = make_float4(acc[r].x / fv, acc[r].y / fv, acc[r].z / fv, acc[r].w / fv);
+        if (apply_sigmoid) o = make_float4(sigmoidf_acc(o.x), sigmoidf_acc(o.y), sigmoidf_acc(o.z), sigmoidf_acc(o.w));
+        *reinterpret_cast<float4*>(prob + ((int64_t)b * S + I0 + rg + RSTEP * r) * S + J0 + 4 * l16) = o;
+    }
+}
+
 // Bilinear resize + overwrite paste.  Coordinate arithmetic follows cv2's resizeLinear for CV_32F
 // (double coordinates, float weights, horizontal pass then vertical pass).  A CTA covers a 64 x 32
 // block of the output; its 64 column and 32 row coordinates are computed ONCE in double precision
@@ -127,6 +225,70 @@ resize_paste_kernel(const float* __restrict__ src, int src_w, int crop_y, int cr
         const float h0 = __fadd_rn(__fmul_rn(__ldg(r0 + sx), a0), __fmul_rn(__ldg(r0 + sx1), a1));
         const float h1 = __fadd_rn(__fmul_rn(__ldg(r1 + sx), a0), __fmul_rn(__ldg(r1 + sx1), a1));
         dst[(int64_t)gy * dst_w + gx] = __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, b1));
+    }
+}
+
+// All tiles of a batch in ONE launch: dst[ys[b] + oy][xs[b] + ox] = bilinear x2 of src[b] (S x S -> 2S x 2S),
+// tiles pasted in index order with last-writer-wins (tta.py:211-213: `preds[x1:x2, y1:y2] = tile` in make_grid
+// order).  Concurrent CTAs must not race on the overlaps, so a pixel of tile b is written only if no later
+// tile of the batch covers it -- the same final image, fewer bytes written.  Arithmetic is resize_paste's for
+// the exact scale 1/2 (fractions 0 / 0.25 / 0.75, horizontal pass then vertical pass, unfused mul + add),
+// so the two kernels agree bit for bit.
+constexpr int kPasteMaxTiles = 32;
+struct PasteTiles {
+    int y[kPasteMaxTiles], x[kPasteMaxTiles];
+    int n;
+};
+
+__global__ void __launch_bounds__(256)
+paste_tiles_x2_kernel(const float* __restrict__ src, int S, PasteTiles tiles, float* __restrict__ dst, int dst_h,
+                      int dst_w) {
+    const int b = blockIdx.z;
+    const float* sp = src + (int64_t)b * S * S;
+    const int ty0 = tiles.y[b], tx0 = tiles.x[b];
+    const int out = 2 * S;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int ox = blockIdx.x * kPasteBX + (tid & 63);
+    const int gx = tx0 + ox;
+    if (ox >= out || gx < 0 || gx >= dst_w) return;
+    // later tiles whose columns cover gx: only these can take a pixel of this thread away
+    unsigned later = 0;
+    for (int l = b + 1; l < tiles.n; ++l)
+        if (gx >= tiles.x[l] && gx < tiles.x[l] + out) later |= 1u << l;
+    // column taps
+    int sx = (ox >> 1) - ((ox & 1) ? 0 : 1);
+    float a1 = (ox & 1) ? 0.25f : 0.75f;
+    if (sx < 0) { sx = 0; a1 = 0.f; }
+    if (sx >= S - 1) { sx = S - 1; a1 = 0.f; }
+    const int sx1 = min(sx + 1, S - 1);
+    const float a0 = 1.f - a1;
+    // 8 consecutive output rows 2a .. 2a+7 need the source rows a-1 .. a+4: 6 horizontal passes, not 16
+    const int a = (blockIdx.y * kPasteBY + (tid >> 6) * 8) >> 1;
+    float h[6];
+#pragma unroll
+    for (int t = 0; t < 6; ++t) {
+        const float* row = sp + (int64_t)min(max(a - 1 + t, 0), S - 1) * S;
+        h[t] = __fadd_rn(__fmul_rn(__ldg(row + sx), a0), __fmul_rn(__ldg(row + sx1), a1));
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int oy = 2 * a + k;
+        const int gy = ty0 + oy;
+        if (oy >= out || gy < 0 || gy >= dst_h) continue;
+        bool owned = true;
+        for (unsigned mm = later; mm; mm &= mm - 1) {
+            const int l = __ffs(mm) - 1;
+            owned = owned && !(gy >= tiles.y[l] && gy < tiles.y[l] + out);
+        }
+        if (!owned) continue;
+        // row taps: even rows (f = 0.75) blend source rows a+k/2-1, a+k/2; odd rows (f = 0.25) a+k/2, a+k/2+1;
+        // the first and the last output row take one source row with weight 1 (the other tap has weight 0)
+        const int t0 = (k >> 1) + (k & 1);                       // index into h[] of source row sy
+        float b1 = (k & 1) ? 0.25f : 0.75f;
+        if (oy == 0 || oy == out - 1) b1 = 0.f;
+        const float h0 = (oy == 0) ? h[1] : h[t0];
+        const float h1 = (oy == out - 1) ? h[t0] : h[t0 + 1];
+        dst[(int64_t)gy * dst_w + gx] = __fadd_rn(__fmul_rn(h0, 1.f - b1), __fmul_rn(h1, b1));
     }
 }
 
@@ -183,6 +345,32 @@ extern "C" int eds_tta_merge(const float* logits, int V, int B, int S, const int
         }
         for (int q = 0; q < 6; ++q) maps.m[v][q] = m[q];
     }
+    // 64x64 vector kernel when the tile size and every column offset keep the 16-byte loads aligned
+    bool vec = S % kMergeTile == 0 && (((uintptr_t)logits | (uintptr_t)prob) & 15) == 0;
+    for (int v = 0; v < V && vec; ++v) {
+        const int* m = maps.m[v];
+        const int step = m[1] == 0 ? m[4] : m[3];
+        vec = step > 0 ? m[5] % 4 == 0 : (m[5] + 1) % 4 == 0;
+    }
+    static const bool force_scalar = getenv("EDS_MERGE_SCALAR") && atoi(getenv("EDS_MERGE_SCALAR")) != 0;
+    if (vec && !force_scalar) {
+        const int smem = 4 * kMergeTile * kMergeTile * (int)sizeof(float);
+        // 512 threads x 2 rows measured best on B200 (50.0 us for 48 maps of 1024^2; 256 x 4 rows: 53.2 us;
+        // 3 CTAs/SM at 80 registers spills: 59.4 us)
+        auto kern = tta_merge64_kernel<2, 2>;
+        static bool opted = false;
+        if (!opted) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) {
+                set_error("tta_merge: shared-memory opt-in failed: %s", cudaGetErrorString(e));
+                return EDS_ERR_CUDA;
+            }
+            opted = true;
+        }
+        dim3 grid(S / kMergeTile, S / kMergeTile, B);
+        kern<<<grid, 512, smem, as_stream(stream)>>>(logits, V, B, S, maps, apply_sigmoid, prob);
+        return check_launch("tta_merge64_kernel");
+    }
     dim3 block(32, 8), grid(ceil_div(S, 32), ceil_div(S, 32), B);
     tta_merge_kernel<<<grid, block, 0, as_stream(stream)>>>(logits, V, B, S, maps, apply_sigmoid, prob);
     return check_launch("tta_merge_kernel");
@@ -201,6 +389,22 @@ extern "C" int eds_resize_paste_f32(const float* src, int src_h, int src_w, int 
                                                              dst_h, dst_w, dst_y, dst_x, out_h, out_w,
                                                              (double)crop_h / out_h, (double)crop_w / out_w);
     return check_launch("resize_paste_kernel");
+}
+
+extern "C" int eds_paste_tiles_x2_f32(const float* src, int n_tiles, int S, const int* ys_host, const int* xs_host,
+                                      float* dst, int dst_h, int dst_w, void* stream) {
+    EDS_REQUIRE(src && dst && ys_host && xs_host, "paste_tiles_x2: null pointer");
+    EDS_REQUIRE(n_tiles >= 1 && n_tiles <= kPasteMaxTiles && S >= 1, "paste_tiles_x2: n_tiles=%d (1..%d), S=%d", n_tiles,
+                kPasteMaxTiles, S);
+    PasteTiles tiles;
+    tiles.n = n_tiles;
+    for (int b = 0; b < kPasteMaxTiles; ++b) {
+        tiles.y[b] = b < n_tiles ? ys_host[b] : 0;
+        tiles.x[b] = b < n_tiles ? xs_host[b] : 0;
+    }
+    dim3 block(64, 4), grid(ceil_div(2 * S, kPasteBX), ceil_div(2 * S, kPasteBY), n_tiles);
+    paste_tiles_x2_kernel<<<grid, block, 0, as_stream(stream)>>>(src, S, tiles, dst, dst_h, dst_w);
+    return check_launch("paste_tiles_x2_kernel");
 }
 
 extern "C" int eds_preprocess_tile_u8(const uint8_t* img, int img_h, int img_w, int y0, int x0, int S,

@@ -124,6 +124,18 @@ def resize_paste(src: torch.Tensor, dst: torch.Tensor, crop, dst_yx, out_hw) -> 
                                           dst.shape[1], dst_yx[0], dst_yx[1], out_hw[0], out_hw[1], _stream()))
 
 
+def paste_tiles_x2(src: torch.Tensor, dst: torch.Tensor, origins) -> None:
+    """src [B,S,S] fp32 tiles, each upsampled x2 (bilinear, cv2 arithmetic) and written over dst at
+    origins[b] = (y, x), in index order with last-writer-wins -- one launch for the whole batch."""
+    _chk(src, dst)
+    assert src.dtype == torch.float32 and dst.dtype == torch.float32 and src.dim() == 3 and dst.dim() == 2
+    B, S, S2 = src.shape
+    assert S == S2 and len(origins) == B
+    ys = _lib.int_array([int(o[0]) for o in origins])
+    xs = _lib.int_array([int(o[1]) for o in origins])
+    check(_lib.lib().eds_paste_tiles_x2_f32(_p(src), B, S, ys, xs, _p(dst), dst.shape[0], dst.shape[1], _stream()))
+
+
 def preprocess_tile(img: torch.Tensor, y0: int, x0: int, S: int, mean, std,
                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """img [H,W,3] u8 -> normalised half-resolution window [3,S,S] fp32."""

@@ -103,6 +103,12 @@ EDS_API int eds_resize_paste_f32(const float* src, int src_h, int src_w, int cro
                          int crop_h, int crop_w, float* dst, int dst_h, int dst_w, int dst_y,
                          int dst_x, int out_h, int out_w, void* stream);
 
+/* The sliding-window case of the above for a whole batch of tiles in one launch: dst[ys[b]+oy][xs[b]+ox] =
+ * bilinear x2 of src[b] ([n_tiles][S][S] -> 2S x 2S each), pasted in index order with last-writer-wins
+ * (tta.py:211-213); bit-identical to n_tiles calls of eds_resize_paste_f32.  n_tiles <= 32. */
+EDS_API int eds_paste_tiles_x2_f32(const float* src, int n_tiles, int S, const int* ys_host, const int* xs_host,
+                                   float* dst, int dst_h, int dst_w, void* stream);
+
 /* Sliding-window tile fetch (tta.py:201-204): window [y0,y0+2S) x [x0,x0+2S) of an
  * HWC u8 RGB image -> 2x2 box mean with round-half-up (== cv2.resize of uint8 by
  * exactly 1/2) -> x/255, -mean, /std (archs/__init__.py:88-97) -> out [3][S][S] fp32. */

@@ -366,11 +366,12 @@ def test_axial_attention(axis, cross, dtype, shape):
 
 
 # ----------------------------------------------------------- TTA / paste / tile
+@pytest.mark.parametrize("S", [96, 128, 192])       # 96: 32x32 scalar kernel; multiples of 64: the 64x64 vector kernel
 @pytest.mark.parametrize("alias", ["d4_transform", "flip_transform", "hflip_transform"])
-def test_tta_merge_matches_ttach_semantics(alias):
+def test_tta_merge_matches_ttach_semantics(alias, S):
     from eyediseasesegmentation_b200 import ttach_compat as tta
     tfm = getattr(tta.aliases, alias)()
-    B, S = 2, 96
+    B = 2
     V = len(tfm)
     logits = rnd(V, B, 1, S, S, seed=50)
     _, deaug = tta.view_maps(tfm, S, S)
@@ -694,3 +695,21 @@ def test_conv_outputs_fully_written_and_repeatable(case):
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
     ref = conv_ref(x, w, b, stride, R // 2, False, None)
     assert rel_err(outs[0], ref) < 4e-3
+
+
+def test_paste_tiles_x2_equals_sequential_pastes():
+    """One launch for a batch of overlapping tiles == the tiles pasted one after the other (last writer wins,
+    make_grid order), bit for bit; tiles hanging over the image edge are clipped."""
+    from eyediseasesegmentation_b200.util import make_grid
+    S = 64
+    H, W = 300, 420
+    slices = make_grid((H, W), window=2 * S, min_overlap=32)
+    origins = [(int(x1), int(y1)) for (x1, _, y1, _) in slices] + [(250, 380), (-20, -30)]
+    B = len(origins)
+    src = torch.rand(B, S, S, device=DEV)
+    want = torch.full((H, W), -1.0, device=DEV)
+    for b, (y, x) in enumerate(origins):
+        K.resize_paste(src[b], want, (0, 0, S, S), (y, x), (2 * S, 2 * S))
+    got = torch.full((H, W), -1.0, device=DEV)
+    K.paste_tiles_x2(src, got, origins)
+    assert torch.equal(got, want)
