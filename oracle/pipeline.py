@@ -5,6 +5,10 @@
   tiled_probability_map      src/main/tta.py:196-213 (window -> cv2 resize -> normalise ->
                              TTA net -> sigmoid -> cv2 bilinear x2 -> overwrite paste)
   whole_image_probability    src/main/tta.py:108-121 (center crop + cv2 resize to full size)
+  ensemble_probability       ensemble.py:86-100 (per-model sigmoid of the D4-mean logits, summed in
+                             model order, divided by the model count).  ensemble.py itself cannot be
+                             imported here (smp / ttach / catalyst / albumentations at module scope), so
+                             this function is a restatement only: parity unpinned for that driver
 
 ``net`` is any callable ``[B,3,S,S] float32 tensor -> logits [B,1,S,S]`` (the oracle nets, or
 the reference modules in the build container).  cv2 is the same library the reference calls.
@@ -67,3 +71,17 @@ def whole_image_probability(prob_SxS: np.ndarray, crop_hw, ori_hw) -> np.ndarray
     y0, x0 = (S_h - ch) // 2, (S_w - cw) // 2
     crop = prob_SxS[y0:y0 + ch, x0:x0 + cw]
     return cv2.resize(crop, (ori_hw[1], ori_hw[0]), interpolation=cv2.INTER_LINEAR)
+
+
+def ensemble_probability(nets_list, x: torch.Tensor) -> np.ndarray:
+    """x [1,3,S,S] -> float32 [S,S] as ensemble.py:86-100 forms ``mean_pred`` (D4 TTA on every model)."""
+    mean_pred = None
+    with torch.no_grad():
+        for net in nets_list:
+            pred = tta_mean_logits(net, x, "d4")
+            pred = torch.sigmoid(pred)[0].squeeze(dim=0).numpy()
+            if mean_pred is None:
+                mean_pred = pred
+            else:
+                mean_pred += pred
+    return mean_pred / len(nets_list)

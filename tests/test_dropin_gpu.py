@@ -204,3 +204,73 @@ def test_lesion_test_tta_whole_image_from_disk_to_disk(tmp_path, fp32_mode):
             want = np.zeros_like(want)
         assert 0.02 < want.mean() < 0.98, "degenerate test image"
         assert np.mean(got != want) < 5e-3, n
+
+
+def test_ensemble_predict_from_disk_to_disk(tmp_path, fp32_mode):
+    """ensemble.predict (reference ensemble.py:64-125): two different architectures, each read from its own
+    ``config.json`` + ``checkpoints/best.pth``, D4 TTA each, per-image mean of the sigmoids at S x S, PR scoring,
+    masks written under the image name.  Checker: oracle.pipeline.ensemble_probability on the same files."""
+    import json
+    import cv2
+    from eyediseasesegmentation_b200 import ensemble as eds_ensemble
+    S = 128
+    specs = [("unetplusplus_deepsup", dict(encoder_name="resnet34", encoder_weights=None, classes=1),
+              lambda sd: (lambda t: nets.unetplusplus_forward(sd, t))),
+             ("Unet", dict(encoder_name="resnet34", encoder_weights=None, classes=1),
+              lambda sd: (lambda t: nets.unet_forward(sd, t)))]
+    logdirs, oracle_nets = [], []
+    for i, (name, cfg, mk) in enumerate(specs):
+        model = helpers.build_product_model(name, cfg, seed=1999 + i)
+        sd = {k: v.clone() for k, v in model.state_dict().items()}
+        sd["segmentation_head.0.weight"] *= 4.0
+        logdir = tmp_path / "models" / "IDRiD" / "EX" / f"run{i}"
+        (logdir / "checkpoints").mkdir(parents=True)
+        torch.save({"model_state_dict": sd}, logdir / "checkpoints" / "best.pth")
+        with open(logdir / "config.json", "w") as j:
+            json.dump({"model_name": name, "model_params": cfg}, j)
+        logdirs.append(logdir)
+        oracle_nets.append(mk(sd))
+
+    img_dir = tmp_path / "edata" / "images"
+    mask_root = tmp_path / "edata" / "masks"
+    mask_dir = mask_root / "3. Hard Exudates"
+    img_dir.mkdir(parents=True)
+    mask_dir.mkdir(parents=True)
+    H0, W0 = 178, 268
+    scale = S / max(H0, W0)
+    nh, nw = int(round(H0 * scale)), int(round(W0 * scale))
+    top, left = int((S - nh) / 2.0), int((S - nw) / 2.0)
+    mean, std = pipeline.DATASET_STATS["IDRiD"]
+    rng = np.random.default_rng(5)
+    items = []
+    for i in range(3):
+        Image.fromarray(_fundus(H0, W0, 80 + i)).save(img_dir / f"IDRiD_{i:02d}.jpg", quality=95)
+        gt = (np.kron(rng.random((H0 // 8 + 1, W0 // 8 + 1)) < 0.2, np.ones((8, 8)))[:H0, :W0] * 255).astype(np.uint8)
+        Image.fromarray(gt, "L").save(mask_dir / f"IDRiD_{i:02d}_EX.tif")
+        image = np.asarray(Image.open(img_dir / f"IDRiD_{i:02d}.jpg").convert("RGB")).astype("uint8")
+        padded = np.zeros((S, S, 3), dtype=np.uint8)
+        padded[top:top + nh, left:left + nw] = cv2.resize(image, (nw, nh), interpolation=cv2.INTER_LINEAR)
+        x = torch.from_numpy(pipeline.preprocess(padded, mean, std).transpose(2, 0, 1)).float()[None]
+        pred = pipeline.ensemble_probability(oracle_nets, x)
+        m = (np.asarray(Image.open(mask_dir / f"IDRiD_{i:02d}_EX.tif").convert("L")) > 50).astype(np.uint8)
+        mp = np.zeros((S, S), dtype=np.uint8)
+        mp[top:top + nh, left:left + nw] = cv2.resize(m, (nw, nh), interpolation=cv2.INTER_NEAREST)
+        items.append((pred, mp, f"IDRiD_{i:02d}.jpg"))
+
+    out_dir = tmp_path / "eoutputs"
+    config = {"dataset_name": "IDRiD", "lesion_type": "EX", "scale_size": S, "out_dir": str(out_dir),
+              "test_img_path": img_dir, "test_mask_path": mask_root}
+    got_auc = eds_ensemble.predict(config, logdirs, "ensemble_1")
+
+    want_auc = scoring.get_auc(items)
+    assert abs(got_auc - want_auc) < 1e-3                      # BASELINE: AUC-PR within 1e-3
+    t1 = scoring.pr_curve(items)["thresholds"][0]
+    written = out_dir / "IDRiD" / "tta" / "EX" / "ensemble_1"
+    assert sorted(p.name for p in written.iterdir()) == [n for _, _, n in items]
+    for pred, _, n in items:
+        got = np.asarray(Image.open(written / n).convert("L")) > 127
+        want = pred > t1
+        if want.all():
+            want = np.zeros_like(want)
+        assert got.shape == (S, S)
+        assert np.mean(got != want) < 5e-3, n

@@ -713,3 +713,18 @@ def test_paste_tiles_x2_equals_sequential_pastes():
     got = torch.full((H, W), -1.0, device=DEV)
     K.paste_tiles_x2(src, got, origins)
     assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("M,S", [(2, 128), (3, 96), (3, 128), (5, 64), (8, 64)])
+def test_ensemble_mean_is_the_running_sum_over_models(M, S):
+    """ensemble.py:94-96: mean_pred = p0; mean_pred += p1; ...; mean_pred / M -- bit exact in fp32."""
+    from eyediseasesegmentation_b200 import ensemble
+    probs = torch.rand(M, 2, S, S, device=DEV)
+    host = probs.cpu().numpy()
+    want = host[0].copy()
+    for m in range(1, M):
+        want += host[m]
+    want = want / M              # numpy true division, as in the reference (torch's CUDA `/ scalar` multiplies by 1/M)
+    assert np.array_equal(ensemble.ensemble_mean(probs).cpu().numpy(), want)
+    with pytest.raises(ValueError):
+        ensemble.ensemble_mean(torch.rand(9, 1, 64, 64, device=DEV))
