@@ -15,9 +15,10 @@ LIB_PATH = os.path.join(_HERE, "libeds_b200.so")
 
 EDS_BF16, EDS_F32 = 0, 1
 UP_NEAREST, UP_BILINEAR, UP_NONE = 0, 1, 2
-PR_KEY_SHIFT = 13
-PR_KEY_BIAS = (103 << 10) - 1
-PR_BINS = 24 * 1024 + 2
+PR_KEY_SHIFT = 14
+PR_KEY_BIAS = (103 << 9) - 1
+PR_HALF = 23 * 512 + 2
+PR_BINS = 2 * PR_HALF
 PR_NTHRESH = 19
 STEM_PACKED_ELEMS = 64 * 184
 #: thresholds of the reference's pooled PR / ROC curves (src/main/aucpr.py:53,128)

@@ -2,8 +2,8 @@
 //
 // Replaces, for src/main/aucpr.py of the reference:
 //   - sklearn average_precision_score / roc_auc_score (aucpr.py:24,38): sort-based
-//     on the CPU -> one HBM-bound pass that bins every pixel by a monotone 17-bit key
-//     of its fp32 score, then a scan over the bins in descending score order;
+//     on the CPU -> one HBM-bound pass that bins every pixel by a monotone key of its
+//     fp32 score (symmetric about 1/2, 9 mantissa bits per binade of min(p, 1-p)), then a scan over the bins in descending score order;
 //   - the 19 numpy passes per image of aucpr.py:60-81 / 136-170: the same histogram
 //     gives every "score > threshold" count exactly, because the bin that shares a
 //     key with threshold k is split by the `straddle` counters.
@@ -12,6 +12,7 @@
 // negative rows are contiguous for the scan), straddle [n_images][19][2] u32.
 #include "common.cuh"
 #include <cmath>
+#include <cstring>
 
 namespace eds {
 
@@ -29,10 +30,24 @@ __constant__ ThreshTable c_thresh;
 static ThreshTable h_thresh;
 static bool h_thresh_ready = false;
 
-__host__ __device__ __forceinline__ int score_key(int bits) {
-    int k = (bits >> EDS_PR_KEY_SHIFT) - EDS_PR_KEY_BIAS;
+__host__ __device__ __forceinline__ int float_bits(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_int(f);
+#else
+    int b;
+    memcpy(&b, &f, 4);
+    return b;
+#endif
+}
+
+// include/eds_b200.h "PR/ROC histogram geometry": monotone in p, symmetric about 1/2.
+__host__ __device__ __forceinline__ int score_key(float p) {
+    const bool hi = p >= 0.5f;
+    const float q = hi ? 1.0f - p : p;
+    int k = (float_bits(q) >> EDS_PR_KEY_SHIFT) - EDS_PR_KEY_BIAS;
     k = k < 0 ? 0 : k;
-    return k > kBins - 1 ? kBins - 1 : k;
+    k = k > EDS_PR_HALF - 1 ? EDS_PR_HALF - 1 : k;
+    return hi ? kBins - 1 - k : k;
 }
 
 static const double kThresholds[kNT] = {0,   0.00001, 0.0001, 0.001, 0.01,  0.1,    0.2,
@@ -44,10 +59,8 @@ static int ensure_thresholds() {
     for (int k = 0; k < kNT; ++k) {
         float f = (float)kThresholds[k];
         if ((double)f > kThresholds[k]) f = nextafterf(f, -1.0f);
-        int b;
-        memcpy(&b, &f, 4);
-        h_thresh.bits[k] = b;
-        h_thresh.key[k] = score_key(b);
+        h_thresh.bits[k] = float_bits(f);
+        h_thresh.key[k] = score_key(f);
     }
     cudaError_t e = cudaMemcpyToSymbol(c_thresh, &h_thresh, sizeof(h_thresh));
     if (e != cudaSuccess) {
@@ -72,7 +85,7 @@ __device__ __forceinline__ void straddle_update(HistSmem* s, int bits, int key, 
 
 __device__ __forceinline__ void hist_one(HistSmem* s, float p, uint8_t g) {
     const int bits = __float_as_int(p);
-    const int key = score_key(bits);
+    const int key = score_key(p);
     const int cls = g != 0;
     atomicAdd(&s->hist[cls * kBins + key], 1u);
     if (s->flag[key]) straddle_update(s, bits, key, cls);
@@ -129,7 +142,7 @@ pr_hist_kernel(const float* __restrict__ prob, const uint8_t* __restrict__ gt, i
                 const bool live = q0 + u * kHistThreads + tid < nq;
                 const int b0 = __float_as_int(p[u].x), b1 = __float_as_int(p[u].y);
                 const int b2 = __float_as_int(p[u].z), b3 = __float_as_int(p[u].w);
-                const int k0 = score_key(b0), k1 = score_key(b1), k2 = score_key(b2), k3 = score_key(b3);
+                const int k0 = score_key(p[u].x), k1 = score_key(p[u].y), k2 = score_key(p[u].z), k3 = score_key(p[u].w);
                 const int a0 = k0 + (g[u].x ? kBins : 0), a1 = k1 + (g[u].y ? kBins : 0);
                 const int a2 = k2 + (g[u].z ? kBins : 0), a3 = k3 + (g[u].w ? kBins : 0);
                 const bool same4 = (a0 == a1) & (a1 == a2) & (a2 == a3);

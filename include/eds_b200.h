@@ -42,13 +42,18 @@ extern "C" {
 #define EDS_BF16 0
 #define EDS_F32 1
 
-/* PR/ROC histogram geometry (see DESIGN.md "score key").  A probability p (fp32) is
- * mapped to key = clamp((int)(bits(p) >> 13) - EDS_PR_KEY_BIAS, 0, EDS_PR_BINS-1):
- * bin 0 = p < 2^-24 (and negatives), then 10 mantissa bits per binade for
- * 2^-24 <= p < 1 (24 * 1024 bins), and a last bin for p >= 1. */
-#define EDS_PR_KEY_SHIFT 13
-#define EDS_PR_KEY_BIAS ((103 << 10) - 1)
-#define EDS_PR_BINS (24 * 1024 + 2)
+/* PR/ROC histogram geometry (see DESIGN.md "score key").  The key of a probability p (fp32) is monotone in p
+ * and SYMMETRIC about 1/2, so a confident positive (p -> 1) is resolved as finely as a confident negative
+ * (p -> 0) -- fp32 itself has 2^-24 steps just below 1, and a segmentation net's sigmoid lives there:
+ *     q    = p >= 0.5 ? 1 - p : p                     (exact in fp32 for p in [0.5, 1])
+ *     k    = clamp((int)(bits(q) >> EDS_PR_KEY_SHIFT) - EDS_PR_KEY_BIAS, 0, EDS_PR_HALF - 1)
+ *     key  = p >= 0.5 ? EDS_PR_BINS - 1 - k : k
+ * k = 0 is q < 2^-24, then 9 mantissa bits per binade for 2^-24 <= q < 1/2 (23 * 512 bins), and k =
+ * EDS_PR_HALF - 1 is q = 1/2 exactly.  Scores that share a key are treated as tied. */
+#define EDS_PR_KEY_SHIFT 14
+#define EDS_PR_KEY_BIAS ((103 << 9) - 1)
+#define EDS_PR_HALF (23 * 512 + 2)
+#define EDS_PR_BINS (2 * EDS_PR_HALF)
 /* thresholds of aucpr.py:53,128: 0,1e-5,1e-4,1e-3,1e-2,.1,...,.9,.99,.999,.9999,.99999,1 */
 #define EDS_PR_NTHRESH 19
 

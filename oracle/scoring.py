@@ -83,5 +83,19 @@ def roc_curve(items):
 def score_key(pred: np.ndarray) -> np.ndarray:
     """The product's histogram key (include/eds_b200.h, EDS_PR_*) restated in numpy, so tests
     can ask sklearn for the AP of key-quantised scores."""
-    bits = np.ascontiguousarray(pred, dtype=np.float32).view(np.int32).astype(np.int64)
-    return np.clip((bits >> 13) - ((103 << 10) - 1), 0, 24 * 1024 + 1)
+    p = np.ascontiguousarray(pred, dtype=np.float32)
+    hi = p >= np.float32(0.5)
+    q = np.where(hi, np.float32(1.0) - p, p).astype(np.float32)
+    half = 23 * 512 + 2
+    k = np.clip((q.view(np.int32).astype(np.int64) >> 14) - ((103 << 9) - 1), 0, half - 1)
+    return np.where(hi, 2 * half - 1 - k, k)
+
+
+def callback_pr_auc(y_trues, y_preds) -> float:
+    """src/main/util/aucpr_cb.py:59-65: trapezoid area under sklearn's precision_recall_curve over every
+    pixel of the loader (lists of per-sample arrays, concatenated)."""
+    from sklearn.metrics import auc, precision_recall_curve
+    y_trues = np.concatenate([np.asarray(t) for t in y_trues])
+    y_preds = np.concatenate([np.asarray(p) for p in y_preds])
+    precision, recall, _ = precision_recall_curve(y_trues.reshape(-1), y_preds.reshape(-1))
+    return float(auc(recall, precision))

@@ -174,3 +174,28 @@ def test_export_result_writes_the_reference_csvs(tmp_path):
         helpers.read_stat_csvs(tmp_path / "out" / "IDRiD" / "result_assessment" / "EX" / "exp"), golden["lesion"])
     helpers.assert_stat_csvs_equal(
         helpers.read_stat_csvs(tmp_path / "out" / "DRIVE" / "result_assessment" / "vexp"), golden["vessel"])
+
+
+def test_aucpr_callback_matches_reference_metric():
+    """util/aucpr_cb.py: batches arrive one by one (logits [B,1,H,W], float targets), the loader metric is the
+    trapezoid PR-AUC over all their pixels; restarting the loader resets the state."""
+    from types import SimpleNamespace
+    from eyediseasesegmentation_b200.aucpr_cb import AucPRMetricCallback
+    from oracle import scoring
+    g = torch.Generator().manual_seed(31)
+    cb = AucPRMetricCallback()
+    runner = SimpleNamespace(output={}, input={}, loader_metrics={})
+    for epoch in range(2):
+        cb.on_loader_start(runner)
+        y_trues, y_preds = [], []
+        for b in range(3):
+            targets = (torch.rand(2 + b, 1, 96, 80, generator=g) < 0.05).float()
+            logits = torch.randn(2 + b, 1, 96, 80, generator=g) * 2 + (targets * 2 - 1) * (1.0 + epoch)
+            runner.output = {"logits": logits.cuda()}
+            runner.input = {"targets": targets.cuda()}
+            cb.on_batch_end(runner)
+            y_trues.extend(targets.numpy())
+            y_preds.extend(torch.sigmoid(logits).numpy())
+        cb.on_loader_end(runner)
+        want = scoring.callback_pr_auc(y_trues, y_preds)
+        assert abs(runner.loader_metrics["auc_pr"] - want) < 1e-4, (epoch, runner.loader_metrics, want)

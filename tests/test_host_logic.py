@@ -239,3 +239,23 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"]
+
+
+def test_callback_pr_auc_readout_matches_sklearn():
+    """aucpr_cb mirror: the histogram read-out is sklearn's precision_recall_curve + auc on key-quantised scores
+    exactly (ties = shared bins), and within 1e-4 of the raw-score value (BASELINE budget: 1e-3)."""
+    from eyediseasesegmentation_b200 import _lib
+    from eyediseasesegmentation_b200.aucpr_cb import pr_auc_from_hist
+    from oracle import scoring
+    rng = np.random.default_rng(21)
+    for prevalence, sharp in [(0.02, 4.0), (0.3, 1.0)]:
+        gt = (rng.random(200_000) < prevalence).astype(np.float32)
+        logit = rng.normal(size=gt.size) * sharp + (gt * 2 - 1) * 1.5
+        pred = (1.0 / (1.0 + np.exp(-logit))).astype(np.float32)
+        key = scoring.score_key(pred)
+        neg = np.bincount(key[gt == 0], minlength=_lib.PR_BINS)
+        pos = np.bincount(key[gt == 1], minlength=_lib.PR_BINS)
+        got = pr_auc_from_hist(neg, pos)
+        assert abs(got - scoring.callback_pr_auc([gt], [key.astype(np.float64)])) < 1e-12
+        assert abs(got - scoring.callback_pr_auc([gt[:1000], gt[1000:]], [pred[:1000], pred[1000:]])) < 1e-4
+    assert np.isnan(pr_auc_from_hist(np.ones(_lib.PR_BINS, dtype=np.int64), np.zeros(_lib.PR_BINS, dtype=np.int64)))

@@ -422,8 +422,11 @@ def _np_counts(prob, gt):
 
 
 def _quantise(prob):
-    bits = prob.view(np.int32).astype(np.int64)
-    return np.clip((bits >> _lib.PR_KEY_SHIFT) - _lib.PR_KEY_BIAS, 0, _lib.PR_BINS - 1)
+    """include/eds_b200.h 'PR/ROC histogram geometry', from the exported constants."""
+    hi = prob >= np.float32(0.5)
+    q = np.where(hi, np.float32(1.0) - prob, prob).astype(np.float32)
+    k = np.clip((q.view(np.int32).astype(np.int64) >> _lib.PR_KEY_SHIFT) - _lib.PR_KEY_BIAS, 0, _lib.PR_HALF - 1)
+    return np.where(hi, _lib.PR_BINS - 1 - k, k)
 
 
 @pytest.mark.parametrize("n_px", [4096 * 3, 10007, 1 << 20])
@@ -461,6 +464,25 @@ def test_pr_hist_and_scan(n_px):
         assert abs(roc[i] - roc_auc_score(gt[i], keys)) < 1e-12
         assert abs(ap[i] - average_precision_score(gt[i], prob[i])) < 1e-3
         assert abs(roc[i] - roc_auc_score(gt[i], prob[i])) < 1e-3
+
+
+def test_pr_scan_resolves_confident_scores():
+    """A trained network's sigmoid saturates: most positives sit within 1e-3 of 1, where fp32 still has 2^-24
+    steps.  The key is symmetric about 1/2, so AP / ROC stay within the budget there too (a key built from the
+    bits of p alone loses 9e-2 of AP on this case)."""
+    from sklearn.metrics import average_precision_score, roc_auc_score
+    rng = np.random.default_rng(77)
+    n_px = 600_000
+    for prevalence, sharp, sep in [(0.01, 6.0, 6.0), (0.05, 8.0, 3.0), (0.02, 4.0, 1.5)]:
+        gt = (rng.random(n_px) < prevalence).astype(np.uint8)
+        logit = rng.normal(size=n_px) * sharp + (gt.astype(np.float64) * 2 - 1) * sep
+        prob = (1.0 / (1.0 + np.exp(-logit))).astype(np.float32)
+        hist, strad = K.pr_hist(torch.from_numpy(prob[None]).to(DEV), torch.from_numpy(gt[None]).to(DEV))
+        ap, roc, counts, _ = [t.cpu().numpy() for t in K.pr_scan(hist, strad)]
+        assert abs(ap[0] - average_precision_score(gt, prob)) < 1e-4
+        assert abs(roc[0] - roc_auc_score(gt, prob)) < 1e-4
+        tp, pp = _np_counts(prob, gt)
+        assert np.array_equal(counts[0, :, 0], tp) and np.array_equal(counts[0, :, 1], pp)
 
 
 def test_pr_hist_flat_regions_and_accumulate():

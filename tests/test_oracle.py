@@ -151,6 +151,28 @@ def test_histogram_key_keeps_ap_within_budget():
     assert worst < 5e-4, worst
 
 
+def test_histogram_key_resolves_saturated_scores():
+    """Confident (saturated) sigmoid outputs: the key is symmetric about 1/2, so scores within 1e-3 of 1 keep
+    their order.  AP / ROC-AUC / the callback's trapezoid PR-AUC of key-quantised scores stay within 1e-4."""
+    from sklearn.metrics import average_precision_score, roc_auc_score
+    rng = np.random.default_rng(21)
+    for prevalence, sharp, sep in [(0.02, 4.0, 1.5), (0.01, 3.0, 4.0), (0.01, 6.0, 6.0), (0.05, 8.0, 3.0)]:
+        gt = (rng.random(300_000) < prevalence).astype(np.uint8)
+        logit = rng.normal(size=gt.size) * sharp + (gt.astype(np.float64) * 2 - 1) * sep
+        pred = (1.0 / (1.0 + np.exp(-logit))).astype(np.float32)
+        key = scoring.score_key(pred)
+        order = np.argsort(pred, kind="stable")
+        assert np.all(np.diff(key[order]) >= 0)                       # monotone
+        assert abs(average_precision_score(gt, pred) - average_precision_score(gt, key)) < 1e-4
+        assert abs(roc_auc_score(gt, pred) - roc_auc_score(gt, key)) < 1e-4
+        assert abs(scoring.callback_pr_auc([gt], [pred]) - scoring.callback_pr_auc([gt], [key.astype(np.float64)])) < 1e-4
+    edge = np.array([0.0, 2.0 ** -25, 2.0 ** -24, 0.25, np.nextafter(np.float32(0.5), np.float32(0)), 0.5,
+                     np.nextafter(np.float32(0.5), np.float32(1)), 1 - 2.0 ** -24, 1.0], dtype=np.float32)
+    k = scoring.score_key(edge)
+    assert k[0] == 0 and k[1] == 0 and k[2] == 1 and k[-1] == 2 * (23 * 512 + 2) - 1 and np.all(np.diff(k) >= 0)
+    assert k[5] - k[4] == 2 and k[6] - k[5] == 1          # q = 1/2 has its own bin; the low half's top bin stays empty
+
+
 def test_stat_result_oracle_matches_reference_csvs(tmp_path):
     """oracle/stat_result.py reproduces the CSV files the reference's own export_result wrote for the
     seeded mask set (tests/golden/stat_result.json, generated by make_golden.py); in the build
