@@ -306,46 +306,53 @@ def hist_roofline(dev, peak, peak_src):
 
 def blend_roofline(dev, peak, peak_src):
     """TTA merge (de-augment + mean + sigmoid over V*B logit maps) and the x2 bilinear overwrite-paste of
-    the B tiles, at the bench shape (V=8, B=6, S=1024); algorithmic bytes = V*B*S^2*4 read + B*S^2*4 write
-    for the merge, B*(S^2*4 read + (2S)^2*4 write) for the paste."""
+    the B tiles, at the bench shape (V=8, B=6, S=1024) for the 4 lesion models of one image, back to back as
+    in a step (4 x 201 MB of logits: larger than L2, and L2 is flushed before each repetition).
+    Algorithmic bytes per launch = V*B*S^2*4 read + B*S^2*4 write for the merge; B*S^2*4 read + H*W*4 write
+    (every pixel of the image once) for the paste."""
     import torch
     from eyediseasesegmentation_b200 import kernels as K, ttach_compat as tta
     from eyediseasesegmentation_b200.util import make_grid
-    V, B = VIEWS, TILES
+    V, B, M = VIEWS, TILES, len(LESIONS)
     _, deaug = tta.view_maps(tta.aliases.d4_transform(), S, S)
-    logits = torch.randn((V, B, S, S), device=dev)
-    prob = torch.empty((B, S, S), device=dev)
-    preds = torch.zeros((H, W), device=dev)
+    logits = [torch.randn((V, B, S, S), device=dev) for _ in range(M)]
+    prob = [torch.empty((B, S, S), device=dev) for _ in range(M)]
+    preds = [torch.zeros((H, W), device=dev) for _ in range(M)]
     slices = make_grid((H, W), window=2 * S, min_overlap=32)
+    origins = [(int(x1), int(y1)) for (x1, _, y1, _) in slices]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)        # > L2
 
-    origins = [(int(x1), int(y1)) for (x1, _, y1, _) in slices]
-
-    def run():
-        K.tta_merge(logits, deaug, True, out=prob)
-        K.paste_tiles_x2(prob, preds, origins)
-
-    run()
+    for m in range(M):
+        K.tta_merge(logits[m], deaug, True, out=prob[m])
+        K.paste_tiles_x2(prob[m], preds[m], origins)
     torch.cuda.synchronize()
     t_merge, t_all = [], []
     for _ in range(5):
         flush.zero_()
-        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        K.tta_merge(logits, deaug, True, out=prob)
+        for m in range(M):
+            K.tta_merge(logits[m], deaug, True, out=prob[m])
         b.record()
-        K.paste_tiles_x2(prob, preds, origins)
-        c.record()
         torch.cuda.synchronize()
-        t_merge.append(a.elapsed_time(b))
-        t_all.append(a.elapsed_time(c))
+        t_merge.append(a.elapsed_time(b) / M)
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for m in range(M):
+            K.tta_merge(logits[m], deaug, True, out=prob[m])
+            K.paste_tiles_x2(prob[m], preds[m], origins)
+        b.record()
+        torch.cuda.synchronize()
+        t_all.append(a.elapsed_time(b) / M)
     ms_merge, ms_all = sorted(t_merge)[2], sorted(t_all)[2]
     bytes_merge = V * B * S * S * 4 + B * S * S * 4
-    bytes_paste = B * S * S * 4 + H * W * 4           # tiles read once, every pixel of the image written once
+    bytes_paste = B * S * S * 4 + H * W * 4
     gbs = bytes_merge / (ms_merge / 1e3) / 1e9
     return {"kernel": "tta_merge64_kernel", "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s",
-            "frac": gbs / peak, "traffic": None, "launch_ms": ms_merge, "peak_source": peak_src,
-            "l2": "256 MB written between repetitions (flush)",
+            "frac": gbs / peak, "traffic": 219.0e6, "traffic_source": "profiles/r01_blend_full.md (dram rd + wr per launch)",
+            "launch_ms": ms_merge, "launches_timed": M, "peak_source": peak_src,
+            "l2": "256 MB written before each repetition (flush); 4 x 201 MB of logits per repetition",
             "with_paste": {"kernels": "tta_merge64_kernel + paste_tiles_x2_kernel (6 tiles, one launch)", "ms": ms_all,
                            "achieved": (bytes_merge + bytes_paste) / (ms_all / 1e3) / 1e9, "unit": "GB/s"}}
 
