@@ -70,6 +70,9 @@ PROTOTYPES = {
     "eds_concat_gated_split": [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp],
     "eds_conv2d_igemm_bf16_2src": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "eds_conv3x3_halo_bf16_2src": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp],
+    "eds_conv3x3_wide_supported": [_i, _i, _i, _i, _i, _i],
+    "eds_conv3x3_wide_bf16": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp],
+    "eds_conv3x3_wide_bf16_2src": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp],
     "eds_apply_gate": [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
     "eds_axial_attention": [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp],
     "eds_mhca_gate": [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],

@@ -21,6 +21,12 @@ CONV_TRACE = None
 #: 3x3 s1 p1 convolutions with Cout <= 128 on maps at least this large take the halo-reuse kernel
 #: (0 disables it; EDS_HALO_MIN_HW overrides)
 HALO_MIN_HW = int(__import__("os").environ.get("EDS_HALO_MIN_HW", "64"))
+#: 3x3 layers with Cout <= 64 run on the dw-grouped wide-N kernel (conv3x3_wide_sm100.cu) when the map is at
+#: least WIDE_MIN_HW on its short side and the reduction has at least WIDE_MIN_CIN channels or Cout is 16
+#: (EDS_WIDE_CONV=0 off)
+WIDE_CONV = __import__("os").environ.get("EDS_WIDE_CONV", "1") != "0"
+WIDE_MIN_HW = int(__import__("os").environ.get("EDS_WIDE_MIN_HW", "64"))
+WIDE_MIN_CIN = int(__import__("os").environ.get("EDS_WIDE_MIN_CIN", "128"))
 #: 3x3 s1 p1 convolutions with C and Cout in {16, 32} (the full-resolution decoder tail) take the mma.sync
 #: kernel of conv3x3_small.cu (EDS_SMALL_CONV=0 sends them to the implicit-GEMM kernels)
 SMALL_CONV = __import__("os").environ.get("EDS_SMALL_CONV", "1") != "0"
@@ -213,7 +219,7 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], strid
         out = torch.empty((N, Ho, Wo, Cout), dtype=x.dtype, device=x.device)
     if impl == "auto":
         impl = "tc" if x.dtype == torch.bfloat16 else "simt"
-    if impl in ("tc", "halo"):
+    if impl in ("tc", "halo", "wide"):
         if x.dtype != torch.bfloat16:
             raise TypeError("the tcgen05 kernel takes bf16 activations")
         trace = CONV_TRACE
@@ -226,9 +232,22 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], strid
         if (impl == "tc" and SMALL_CONV and Cin == 16 and x1 is None and residual is None and R == 3 and S == 3 and
                 stride == 1 and pad == 1 and _lib.load().eds_conv3x3_small_supported(Cin, Cout)):
             return conv3x3_small(x, w, bias, relu, out=out)
-        halo = impl == "halo" or (impl == "tc" and HALO_MIN_HW and min(H, W_) >= HALO_MIN_HW and
-                                  _lib.load().eds_conv3x3_halo_supported(Cin + C1, Cout, R, S, stride, pad))
-        if x1 is not None:
+        # measured at 48 maps (scripts/dev_wide_probe.py): 320 -> 32 @512^2 2.45 ms vs 4.31 on the halo kernel,
+        # 896 -> 64 @256^2 2.57 vs 2.95, 384 -> 64 @512^2 5.37 vs 5.92, 32 -> 16 @1024^2 1.00 vs 1.21; with a single
+        # 64-channel chunk the epilogue is not hidden and the halo kernel wins (64 -> 64 @512^2: 2.07 vs 1.49)
+        wide = impl == "wide" or (impl == "tc" and WIDE_CONV and min(H, W_) >= WIDE_MIN_HW and
+                                  (Cin + C1 >= WIDE_MIN_CIN or Cout == 16) and
+                                  _lib.load().eds_conv3x3_wide_supported(Cin + C1, Cout, R, S, stride, pad))
+        halo = not wide and (impl == "halo" or (impl == "tc" and HALO_MIN_HW and min(H, W_) >= HALO_MIN_HW and
+                                                _lib.load().eds_conv3x3_halo_supported(Cin + C1, Cout, R, S, stride, pad)))
+        if wide:
+            if x1 is not None:
+                check(_lib.lib().eds_conv3x3_wide_bf16_2src(_p(x), Cin, _p(x1), C1, N, H, W_, _p(w), _p(bias), Cout,
+                                                            int(relu), _p(residual), _p(out), _stream()))
+            else:
+                check(_lib.lib().eds_conv3x3_wide_bf16(_p(x), N, H, W_, Cin, _p(w), _p(bias), Cout, int(relu),
+                                                       _p(residual), _p(out), _stream()))
+        elif x1 is not None:
             if halo:
                 check(_lib.lib().eds_conv3x3_halo_bf16_2src(_p(x), Cin, _p(x1), C1, N, H, W_, _p(w), _p(bias), Cout,
                                                             int(relu), _p(residual), _p(out), _stream()))

@@ -221,6 +221,17 @@ EDS_API int eds_conv3x3_halo_supported(int C, int Cout, int R, int S, int stride
 EDS_API int eds_conv3x3_halo_bf16(const void* x, int N, int H, int W, int C, const void* w, const float* bias,
                                   int Cout, int relu, const void* residual, void* y, void* stream);
 
+/* 3x3 / stride 1 / pad 1 convolution for very narrow outputs (Cout <= 64), same contract as
+ * eds_conv3x3_halo_bf16: the three horizontal taps of a kernel row run as ONE tcgen05.mma of N = 3 * Cout on a
+ * shared A operand and the epilogue combines the three accumulators with a one-lane warp shuffle
+ * (conv3x3_wide_sm100.cu) -- at N = Cout <= 64 a per-tap MMA is bound by shared-memory operand reads. */
+EDS_API int eds_conv3x3_wide_supported(int C, int Cout, int R, int S, int stride, int pad);
+EDS_API int eds_conv3x3_wide_bf16(const void* x, int N, int H, int W, int C, const void* w, const float* bias,
+                                  int Cout, int relu, const void* residual, void* y, void* stream);
+EDS_API int eds_conv3x3_wide_bf16_2src(const void* x0, int C0, const void* x1, int C1, int N, int H, int W,
+                                       const void* w, const float* bias, int Cout, int relu, const void* residual,
+                                       void* y, void* stream);
+
 /* 3x3 / stride 1 / pad 1 convolution for the full-resolution decoder tail (C, Cout in {16, 32}; bf16; w
  * [Cout][3][3][C], fp32 bias, optional ReLU) on mma.sync, optionally fused with the x2 upsampling of a gated
  * low-resolution input (conv3x3_small.cu): up_mode EDS_UP_NONE -> x is [N][H][W][C]; EDS_UP_NEAREST /

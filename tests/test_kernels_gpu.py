@@ -141,12 +141,12 @@ def test_conv3x3_halo_bf16(case):
     tol = 1e-2 * max(1.0, ref.abs().max().item())
     assert err < tol, f"halo conv max abs err {err} (tol {tol}), rel {rel_err(y, ref)}"
     assert rel_err(y, ref) < 4e-3
-    old = K.HALO_MIN_HW
-    K.HALO_MIN_HW = 0
+    old = K.HALO_MIN_HW, K.WIDE_CONV
+    K.HALO_MIN_HW, K.WIDE_CONV = 0, False           # impl="tc" then means the generic kernel
     try:
         y2 = K.conv2d(x, w, b, 1, 1, relu, res, impl="tc")
     finally:
-        K.HALO_MIN_HW = old
+        K.HALO_MIN_HW, K.WIDE_CONV = old
     assert (y.float() - y2.float()).abs().max().item() < tol
 
 
@@ -750,3 +750,61 @@ def test_ensemble_mean_is_the_running_sum_over_models(M, S):
     assert np.array_equal(ensemble.ensemble_mean(probs).cpu().numpy(), want)
     with pytest.raises(ValueError):
         ensemble.ensemble_mean(torch.rand(9, 1, 64, 64, device=DEV))
+
+
+WIDE_CASES = [
+    # N, H, W, C, Cout, relu, use_res
+    (2, 64, 60, 64, 64, True, False),      # exact tiles (8 rows x 30 output columns)
+    (1, 96, 72, 128, 64, True, False),     # two channel chunks, ragged in W (72 = 2 * 30 + 12)
+    (3, 40, 20, 64, 32, False, True),      # a single (clipped) tile column, residual, three images
+    (1, 70, 13, 448, 64, True, False),     # long reduction (7 chunks), map narrower than a slab
+    (2, 64, 64, 32, 16, True, False),      # 64-byte swizzle (block_k 32), narrowest N = 48
+    (1, 66, 31, 16, 16, True, False),      # 32-byte swizzle (block_k 16), one column past a tile
+    (1, 16, 16, 64, 48, True, False),      # N = 144
+    (5, 8, 30, 96, 64, False, False),      # block_k 32 with 3 chunks, one tile per image
+    (1, 128, 128, 320, 32, True, False),   # x_0_3 shape class
+]
+
+
+@pytest.mark.parametrize("case", WIDE_CASES)
+def test_conv3x3_wide_bf16(case):
+    """dw-grouped 3x3 kernel (one N = 3 * Cout MMA per kernel row, shuffle-combined accumulators) == fp32
+    convolution of the same bf16 data, and == the generic tcgen05 kernel."""
+    N, H, W, C, Cout, relu, use_res = case
+    x = rnd(N, H, W, C, seed=11).bfloat16()
+    w = rnd(Cout, 3, 3, C, seed=12, scale=1.0 / math.sqrt(9 * C)).bfloat16()
+    b = rnd(Cout, seed=13)
+    res = rnd(N, H, W, Cout, seed=14).bfloat16() if use_res else None
+    y = torch.full((N, H, W, Cout), float("nan"), device=DEV, dtype=torch.bfloat16)
+    K.conv2d(x, w, b, 1, 1, relu, res, out=y, impl="wide")
+    torch.cuda.synchronize()
+    assert not torch.isnan(y.float()).any()
+    ref = conv_ref(x, w, b, 1, 1, relu, res)
+    err = (y.float() - ref).abs().max().item()
+    tol = 1e-2 * max(1.0, ref.abs().max().item())
+    assert err < tol, f"wide conv max abs err {err} (tol {tol}), rel {rel_err(y, ref)}"
+    assert rel_err(y, ref) < 4e-3
+    y2 = K.conv2d(x, w, b, 1, 1, relu, res, impl="halo")
+    assert (y.float() - y2.float()).abs().max().item() < tol
+    y3 = K.conv2d(x, w, b, 1, 1, relu, res, impl="wide")
+    assert torch.equal(y, y3)              # repeatable: no race between the halves' barriers
+
+
+def test_conv3x3_wide_many_tiles_and_two_inputs():
+    """More tiles than SMs (every CTA walks several tiles, the per-half TMEM barriers wrap), and the two-input
+    form against the convolution of the concatenation."""
+    x = rnd(2, 256, 256, 64, seed=15).bfloat16()
+    w = rnd(64, 3, 3, 64, seed=16, scale=1.0 / 24).bfloat16()
+    y = K.conv2d(x, w, None, 1, 1, True, None, impl="wide")
+    ref = conv_ref(x, w, None, 1, 1, True, None)
+    assert rel_err(y, ref) < 4e-3
+    assert (y.float() - ref).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
+    x0 = rnd(2, 64, 64, 64, seed=21).bfloat16()
+    x1 = rnd(2, 64, 64, 192, seed=22).bfloat16()
+    w2 = rnd(64, 3, 3, 256, seed=23, scale=1.0 / 48).bfloat16()
+    b = rnd(64, seed=24)
+    y2 = K.conv2d(x0, w2, b, 1, 1, True, None, impl="wide", x1=x1)
+    cat = torch.cat([x0, x1], dim=-1).contiguous()
+    ref2 = conv_ref(cat, w2, b, 1, 1, True, None)
+    assert rel_err(y2, ref2) < 4e-3
+    assert torch.equal(y2, K.conv2d(cat, w2, b, 1, 1, True, None, impl="wide"))
