@@ -26,9 +26,14 @@
 //   warp 0      TMA producer
 //   warp 1      MMA issuer: 2 halves x 3 dh x block_k/16 tcgen05.mma (N = 3 * Cout) per stage; the vertical taps
 //               move the A start address by whole image rows of the slab (4 swizzle atoms)
-//   warps 2-5   epilogue: tcgen05.ld of the three accumulators, shuffle-combine, bias / residual / ReLU, bf16 store.
-//               Each half has its own full / empty barrier, so the MMAs of the next tile's first half run while
-//               the second half of the previous tile is still being drained.
+//   warps 2-9   epilogue (warps 2-5: half 0, warps 6-9: half 1): tcgen05.ld of the three accumulators,
+//               shuffle-combine, bias / residual / ReLU, bf16 store.  Each half has its own full / empty barrier,
+//               so the MMAs of the next tile's first half run while the previous tile is still being drained.
+//
+// Resident weights: when the whole weight tensor (9 * Cout * C bf16) fits next to three A slabs -- the conv2 layers
+// of the narrow decoder blocks (64 -> 64, 32 -> 32, 16 -> 16) and 32 -> 16 -- it is loaded ONCE per CTA and the ring
+// carries A slabs only: L2 -> SM traffic per tile drops from 114 KB to 40 KB at Cout = 64 and a tile is bounded by
+// its 24 MMAs instead of by the weight re-load.
 #include "tc_ptx.cuh"
 #include <algorithm>
 #include <cstdlib>
@@ -37,7 +42,7 @@
 
 namespace eds {
 
-constexpr int kWideThreads = 192;
+constexpr int kWideThreads = 320;
 constexpr int kWideStagesMax = 4;
 constexpr int kWideRows = 8, kWideSlabCols = 32, kWideOutCols = 30, kWideSlabRows = kWideRows + 2;
 
@@ -53,6 +58,7 @@ struct WideParams {
     int N, H, W, relu;
     int tiles_w, tiles_h, total_tiles;
     int stages, atom_bytes, a_slab_bytes, b_box_bytes, stage_bytes, tmem_cols;
+    int b_resident, b_region_bytes;   // weights loaded once per CTA in front of the A ring
     uint32_t idesc, desc_hi;
 };
 
@@ -64,11 +70,13 @@ __global__ void __launch_bounds__(kWideThreads, 1)
 conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+    uint8_t* ring = smem + p.b_region_bytes;                  // resident weights (if any) sit in front of the ring
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + (size_t)p.stages * p.stage_bytes);
     uint64_t* empty_bar = full_bar + kWideStagesMax;
     uint64_t* tmem_full_bar = empty_bar + kWideStagesMax;     // [2]: one per half
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;             // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    uint64_t* b_bar = tmem_empty_bar + 2;                     // resident weights have landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -81,8 +89,9 @@ conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
         }
         for (int m = 0; m < 2; ++m) {
             mbar_init(&tmem_full_bar[m], 1);
-            mbar_init(&tmem_empty_bar[m], 4);      // one arrival per epilogue warp
+            mbar_init(&tmem_empty_bar[m], 4);      // one arrival per epilogue warp of the half
         }
+        mbar_init(b_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -98,7 +107,15 @@ conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
             // ===== TMA producer =====
             int stage = 0;
             uint32_t phase = 0;
-            const uint32_t tx = (uint32_t)(kWideSlabRows * 4 * p.atom_bytes + 9 * p.bn * p.block_k * 2);
+            const uint32_t a_tx = (uint32_t)(kWideSlabRows * 4 * p.atom_bytes), b_tx = (uint32_t)(9 * p.bn * p.block_k * 2);
+            const uint32_t tx = p.b_resident ? a_tx : a_tx + b_tx;
+            if (p.b_resident) {
+                mbar_arrive_expect_tx(b_bar, b_tx * (uint32_t)p.k_chunks);
+                for (int kc = 0; kc < p.k_chunks; ++kc)
+                    for (int tap = 0; tap < 9; ++tap)
+                        tma_load_2d(smem + (size_t)(kc * 9 + tap) * p.b_box_bytes, &p.b_map, b_bar,
+                                    tap * p.C + kc * p.block_k, 0);
+            }
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int tw = tile % p.tiles_w;
                 const int t2 = tile / p.tiles_w;
@@ -108,14 +125,15 @@ conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
                 for (int kc = 0; kc < p.k_chunks; ++kc) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
                     mbar_arrive_expect_tx(&full_bar[stage], tx);
-                    uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
+                    uint8_t* sa = ring + (size_t)stage * p.stage_bytes;
                     uint8_t* sb = sa + p.a_slab_bytes;
                     if (kc < p.k_split)
                         tma_load_4d(sa, &p.a_map, &full_bar[stage], kc * p.block_k, w0 - 1, h0 - 1, n);
                     else
                         tma_load_4d(sa, &p.a_map1, &full_bar[stage], (kc - p.k_split) * p.block_k, w0 - 1, h0 - 1, n);
-                    for (int tap = 0; tap < 9; ++tap)
-                        tma_load_2d(sb + tap * p.b_box_bytes, &p.b_map, &full_bar[stage], tap * p.C + kc * p.block_k, 0);
+                    if (!p.b_resident)
+                        for (int tap = 0; tap < 9; ++tap)
+                            tma_load_2d(sb + tap * p.b_box_bytes, &p.b_map, &full_bar[stage], tap * p.C + kc * p.block_k, 0);
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -124,8 +142,10 @@ conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
         // ===== MMA issuer: the warp stays converged, one elected lane issues =====
         int stage = 0;
         uint32_t phase = 0;
-        const uint32_t lo0 = desc_lo(smem_u32(smem));
+        const uint32_t lo0 = desc_lo(smem_u32(ring)), blo0 = desc_lo(smem_u32(smem));
         const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4, slab16 = (uint32_t)p.a_slab_bytes >> 4;
+        const uint32_t bchunk16 = 9u * ((uint32_t)p.b_box_bytes >> 4);
+        if (p.b_resident) mbar_wait(b_bar, 0);
         const uint32_t atom16 = (uint32_t)p.atom_bytes >> 4, brow16 = 3u * ((uint32_t)p.b_box_bytes >> 4);
         const uint32_t dhi_w = p.desc_hi, idesc = p.idesc;
         const int k_steps = p.block_k / 16;
@@ -134,7 +154,8 @@ conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
             const uint32_t empty_parity = (uint32_t)((t & 1) ^ 1);
             for (int kc = 0; kc < p.k_chunks; ++kc) {
                 mbar_wait(&full_bar[stage], phase);
-                const uint32_t a_st = lo0 + (uint32_t)stage * stage16, b_st = a_st + slab16;
+                const uint32_t a_st = lo0 + (uint32_t)stage * stage16;
+                const uint32_t b_st = p.b_resident ? blo0 + (uint32_t)kc * bchunk16 : a_st + slab16;
 #pragma unroll
                 for (int m = 0; m < 2; ++m) {
                     if (kc == 0) mbar_wait(&tmem_empty_bar[m], empty_parity);   // the epilogue drained this half
@@ -162,8 +183,9 @@ conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
             }
         }
     } else {
-        // ===== epilogue: warp q owns TMEM lanes [32q, 32q+32) = image row q of each half; lane = slab column =====
+        // ===== epilogue: warp q owns TMEM lanes [32q, 32q+32) = image row q of its half; lane = slab column =====
         const int q = warp & 3;
+        const int m = (warp - 2) >> 2;                // warps 2-5 drain half 0, warps 6-9 half 1
         const int bn = p.bn;
         int t = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
@@ -173,7 +195,7 @@ conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
             const int n = t2 / p.tiles_h;
             const int ow = tw * kWideOutCols - 1 + lane;
             const bool col_ok = lane >= 1 && lane <= kWideOutCols && ow < p.W;
-            for (int m = 0; m < 2; ++m) {
+            {
                 mbar_wait(&tmem_full_bar[m], (uint32_t)(t & 1));
                 tc_fence_after();
                 const int oh = th * kWideRows + m * 4 + q;
@@ -304,14 +326,20 @@ static int wide_launch(const void* x, int C0, const void* x1, int C1, int N, int
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((3 * p.bn) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     p.a_slab_bytes = (kWideSlabRows * 4 * p.atom_bytes + 1023) & ~1023;
     p.b_box_bytes = p.bn * p.block_k * 2;                           // bn rows, contiguous: the 3 boxes of a kernel row
-    p.stage_bytes = (p.a_slab_bytes + 9 * p.b_box_bytes + 1023) & ~1023;   // stack into one [3 * bn][block_k] operand
-    const int barrier_bytes = (2 * kWideStagesMax + 4) * 8 + 16;
-    p.stages = std::min(kWideStagesMax, (227 * 1024 - 1024 - barrier_bytes) / p.stage_bytes);
+    const int barrier_bytes = (2 * kWideStagesMax + 5) * 8 + 16;
+    const int budget = 227 * 1024 - 1024 - barrier_bytes;
+    const int b_all = p.k_chunks * 9 * p.b_box_bytes;               // the whole weight tensor
+    static const bool no_resident = getenv("EDS_WIDE_RESIDENT") && atoi(getenv("EDS_WIDE_RESIDENT")) == 0;
+    p.b_resident = !no_resident && b_all + 3 * p.a_slab_bytes <= budget;
+    p.b_region_bytes = p.b_resident ? ((b_all + 1023) & ~1023) : 0;
+    // the 9 boxes of a chunk are contiguous: the 3 of a kernel row stack into one [3 * bn][block_k] operand
+    p.stage_bytes = p.b_resident ? p.a_slab_bytes : ((p.a_slab_bytes + 9 * p.b_box_bytes + 1023) & ~1023);
+    p.stages = std::min(kWideStagesMax, (budget - p.b_region_bytes) / p.stage_bytes);
     EDS_REQUIRE(p.stages >= 2, "conv3x3_wide: a stage of %d B leaves no room for double buffering", p.stage_bytes);
     int cols = 32;
     while (cols < 6 * p.bn) cols <<= 1;
     p.tmem_cols = cols;
-    const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + barrier_bytes;
+    const size_t smem = (size_t)p.b_region_bytes + (size_t)p.stages * p.stage_bytes + 1024 + barrier_bytes;
     EDS_REQUIRE(smem <= 227 * 1024 && p.tmem_cols <= 512, "conv3x3_wide: tile does not fit (smem %zu, tmem %d)", smem,
                 p.tmem_cols);
 

@@ -8,9 +8,9 @@ dev = "cuda"
 N = 48
 LAYERS = [  # H, Cin, Cout
     (256, 896, 64), (256, 64, 64), (512, 320, 32), (512, 32, 32), (512, 448, 64), (512, 384, 64), (512, 320, 64),
-    (512, 64, 64), (1024, 32, 16),
+    (512, 64, 64), (1024, 32, 16), (1024, 16, 16), (512, 128, 32),
 ]
-impls = sys.argv[1:] or ["halo", "wide"]
+impls = sys.argv[1:] or ["halo", "wide", "tc"]
 for H, C, Co in LAYERS:
     n = N if H < 1024 else 24
     x = torch.randn(n, H, H, C, device=dev).bfloat16()
