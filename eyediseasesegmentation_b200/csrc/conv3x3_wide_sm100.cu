@@ -77,6 +77,10 @@ conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;             // [2]
     uint64_t* b_bar = tmem_empty_bar + 2;                     // resident weights have landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_bar + 1);
+    // bias in shared memory: a global load per 16-column group costs the epilogue a long-scoreboard stall per group
+    // (ncu: the top stall of the single-chunk layers), a broadcast LDS does not
+    float* s_bias = reinterpret_cast<float*>(full_bar + 16);        // 128 B behind the first barrier: 16-byte aligned
+    if (threadIdx.x < (unsigned)p.bn) s_bias[threadIdx.x] = p.bias ? __ldg(p.bias + threadIdx.x) : 0.f;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -216,11 +220,11 @@ conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
                         v[i] = (l + __uint_as_float(rc[i])) + r;
                     }
                     if (valid) {
-                        if (p.bias) {
-                            const float4* b4 = reinterpret_cast<const float4*>(p.bias + c);
+                        {
+                            const float4* b4 = reinterpret_cast<const float4*>(s_bias + c);
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                const float4 b = __ldg(b4 + i);
+                                const float4 b = b4[i];
                                 v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
                             }
                         }
@@ -326,7 +330,7 @@ static int wide_launch(const void* x, int C0, const void* x1, int C1, int N, int
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((3 * p.bn) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     p.a_slab_bytes = (kWideSlabRows * 4 * p.atom_bytes + 1023) & ~1023;
     p.b_box_bytes = p.bn * p.block_k * 2;                           // bn rows, contiguous: the 3 boxes of a kernel row
-    const int barrier_bytes = (2 * kWideStagesMax + 5) * 8 + 16;
+    const int barrier_bytes = 128 + 64 * 4;   // 13 barriers + TMEM slot in the first 128 B, then the bias
     const int budget = 227 * 1024 - 1024 - barrier_bytes;
     const int b_all = p.k_chunks * 9 * p.b_box_bytes;               // the whole weight tensor
     static const bool no_resident = getenv("EDS_WIDE_RESIDENT") && atoi(getenv("EDS_WIDE_RESIDENT")) == 0;

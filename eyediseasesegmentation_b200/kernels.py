@@ -22,11 +22,10 @@ CONV_TRACE = None
 #: (0 disables it; EDS_HALO_MIN_HW overrides)
 HALO_MIN_HW = int(__import__("os").environ.get("EDS_HALO_MIN_HW", "64"))
 #: 3x3 layers with Cout <= 64 run on the dw-grouped wide-N kernel (conv3x3_wide_sm100.cu) when the map is at
-#: least WIDE_MIN_HW on its short side and the reduction has at least WIDE_MIN_CIN channels or Cout is 16
-#: (EDS_WIDE_CONV=0 off)
+#: least WIDE_MIN_HW on its short side and the reduction has at least WIDE_MIN_CIN channels (EDS_WIDE_CONV=0 off)
 WIDE_CONV = __import__("os").environ.get("EDS_WIDE_CONV", "1") != "0"
 WIDE_MIN_HW = int(__import__("os").environ.get("EDS_WIDE_MIN_HW", "64"))
-WIDE_MIN_CIN = int(__import__("os").environ.get("EDS_WIDE_MIN_CIN", "128"))
+WIDE_MIN_CIN = int(__import__("os").environ.get("EDS_WIDE_MIN_CIN", "16"))
 #: 3x3 s1 p1 convolutions with C and Cout in {16, 32} (the full-resolution decoder tail) take the mma.sync
 #: kernel of conv3x3_small.cu (EDS_SMALL_CONV=0 sends them to the implicit-GEMM kernels)
 SMALL_CONV = __import__("os").environ.get("EDS_SMALL_CONV", "1") != "0"
@@ -232,11 +231,11 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], strid
         if (impl == "tc" and SMALL_CONV and Cin == 16 and x1 is None and residual is None and R == 3 and S == 3 and
                 stride == 1 and pad == 1 and _lib.load().eds_conv3x3_small_supported(Cin, Cout)):
             return conv3x3_small(x, w, bias, relu, out=out)
-        # measured at 48 maps (scripts/dev_wide_probe.py): 320 -> 32 @512^2 2.45 ms vs 4.31 on the halo kernel,
-        # 896 -> 64 @256^2 2.57 vs 2.95, 384 -> 64 @512^2 5.37 vs 5.92, 32 -> 16 @1024^2 1.00 vs 1.21; with a single
-        # 64-channel chunk the epilogue is not hidden and the halo kernel wins (64 -> 64 @512^2: 2.07 vs 1.49)
+        # measured at 48 maps (scripts/dev_wide_probe.py, wide vs halo): 448 -> 64 @512^2 5.17 ms vs 6.02, 320 -> 32
+        # 2.38 vs 4.31, 896 -> 64 @256^2 2.47 vs 2.92, 64 -> 64 @512^2 (weights resident) 1.33 vs 1.51, 32 -> 32 0.57
+        # vs 0.67, 32 -> 16 @1024^2 1.00 vs 1.24
         wide = impl == "wide" or (impl == "tc" and WIDE_CONV and min(H, W_) >= WIDE_MIN_HW and
-                                  (Cin + C1 >= WIDE_MIN_CIN or Cout == 16) and
+                                  Cin + C1 >= WIDE_MIN_CIN and
                                   _lib.load().eds_conv3x3_wide_supported(Cin + C1, Cout, R, S, stride, pad))
         halo = not wide and (impl == "halo" or (impl == "tc" and HALO_MIN_HW and min(H, W_) >= HALO_MIN_HW and
                                                 _lib.load().eds_conv3x3_halo_supported(Cin + C1, Cout, R, S, stride, pad)))
