@@ -51,6 +51,7 @@ struct WideParams {
     CUtensorMap a_map1;     // optional second input (channels C0.. of the concatenated K axis)
     int k_split;            // channel chunks served by a_map
     CUtensorMap b_map;
+    CUtensorMap y_map;      // output rows [Cout][30 px][1][1], 128-byte swizzle (used when `staged`)
     const float* bias;
     const __nv_bfloat16* residual;
     __nv_bfloat16* y;
@@ -59,6 +60,7 @@ struct WideParams {
     int tiles_w, tiles_h, total_tiles;
     int stages, atom_bytes, a_slab_bytes, b_box_bytes, stage_bytes, tmem_cols;
     int b_resident, b_region_bytes;   // weights loaded once per CTA in front of the A ring
+    int staged, staging_off;          // epilogue through swizzled shared memory + TMA store (Cout = 64 and room)
     uint32_t idesc, desc_hi;
 };
 
@@ -191,6 +193,11 @@ conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
         const int q = warp & 3;
         const int m = (warp - 2) >> 2;                // warps 2-5 drain half 0, warps 6-9 half 1
         const int bn = p.bn;
+        // staged stores: a lane holds one pixel = one 128-byte output row; written directly, every 16-byte store of
+        // a warp touches 32 different lines.  Through a swizzled 4 KB buffer per warp the row of 30 pixels leaves as
+        // one bulk tensor store (clipped at the map edge by the tensor map).
+        uint8_t* stg = smem + p.staging_off + (size_t)(warp - 2) * 4096;
+        const int pos = lane - 1;                      // staging row of this lane's pixel
         int t = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
             const int tw = tile % p.tiles_w;
@@ -206,6 +213,10 @@ conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
                 const bool valid = col_ok && oh < p.H;
                 const int64_t off = (((int64_t)n * p.H + oh) * p.W + ow) * bn;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)m * n3;
+                if (p.staged) {                        // the previous store of this warp has finished reading `stg`
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
+                }
                 for (int c = 0; c < bn; c += 16) {
                     uint32_t rl[16], rc[16], rr[16];
                     tmem_ld16_nowait(taddr + (uint32_t)c, rl);                 // dw = -1: wanted by lane + 1
@@ -219,7 +230,7 @@ conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
                         const float r = __shfl_down_sync(0xffffffffu, __uint_as_float(rr[i]), 1);
                         v[i] = (l + __uint_as_float(rc[i])) + r;
                     }
-                    if (valid) {
+                    if (valid || (p.staged && pos >= 0 && pos < kWideOutCols)) {
                         {
                             const float4* b4 = reinterpret_cast<const float4*>(s_bias + c);
 #pragma unroll
@@ -228,7 +239,7 @@ conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
                                 v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
                             }
                         }
-                        if (p.residual) {
+                        if (p.residual && valid) {
                             float r0[8], r1[8];
                             Vec8<__nv_bfloat16>::ld(p.residual + off + c, r0);
                             Vec8<__nv_bfloat16>::ld(p.residual + off + c + 8, r1);
@@ -242,8 +253,25 @@ conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
                         float o0[8], o1[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) { o0[i] = v[i]; o1[i] = v[8 + i]; }
-                        Vec8<__nv_bfloat16>::st(p.y + off + c, o0);
-                        Vec8<__nv_bfloat16>::st(p.y + off + c + 8, o1);
+                        if (p.staged) {
+                            const uint32_t j = (uint32_t)c >> 3, sw = (uint32_t)pos & 7u;
+                            Vec8<__nv_bfloat16>::st(reinterpret_cast<__nv_bfloat16*>(stg + pos * 128 + ((j ^ sw) << 4)), o0);
+                            Vec8<__nv_bfloat16>::st(reinterpret_cast<__nv_bfloat16*>(stg + pos * 128 + (((j + 1) ^ sw) << 4)), o1);
+                        } else {
+                            Vec8<__nv_bfloat16>::st(p.y + off + c, o0);
+                            Vec8<__nv_bfloat16>::st(p.y + off + c + 8, o1);
+                        }
+                    }
+                }
+                if (p.staged) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0 && oh < p.H) {
+                        asm volatile(
+                            "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                            ::"l"(&p.y_map), "r"(smem_u32(stg)), "r"(0), "r"(tw * kWideOutCols), "r"(oh), "r"(n)
+                            : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 }
                 // this warp's TMEM reads of the half are complete (tcgen05.wait::ld above)
@@ -252,6 +280,7 @@ conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
                 if (lane == 0) wide_mbar_arrive(&tmem_empty_bar[m]);
             }
         }
+        if (p.staged && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores done before exit
     }
 
     tc_fence_before();
@@ -343,7 +372,14 @@ static int wide_launch(const void* x, int C0, const void* x1, int C1, int N, int
     int cols = 32;
     while (cols < 6 * p.bn) cols <<= 1;
     p.tmem_cols = cols;
-    const size_t smem = (size_t)p.b_region_bytes + (size_t)p.stages * p.stage_bytes + 1024 + barrier_bytes;
+    // staged epilogue when 8 x 4 KB fit behind the ring (the resident-weight 64 -> 64 layers; the multi-chunk layers
+    // hide their epilogue behind the MMAs of the next tile and need the room for the second stage).
+    // layout: [weights][ring][barriers + bias (barrier_bytes)][pad to 1024][staging]
+    static const bool no_staging = getenv("EDS_WIDE_STAGED") && atoi(getenv("EDS_WIDE_STAGED")) == 0;
+    const int after_bars = p.b_region_bytes + p.stages * p.stage_bytes + barrier_bytes;
+    p.staging_off = (after_bars + 1023) & ~1023;
+    p.staged = !no_staging && p.bn == 64 && p.block_k == 64 && p.staging_off + 8 * 4096 + 1024 <= 227 * 1024;
+    const size_t smem = (p.staged ? (size_t)p.staging_off + 8 * 4096 : (size_t)after_bars) + 1024;
     EDS_REQUIRE(smem <= 227 * 1024 && p.tmem_cols <= 512, "conv3x3_wide: tile does not fit (smem %zu, tmem %d)", smem,
                 p.tmem_cols);
 
@@ -365,6 +401,12 @@ static int wide_launch(const void* x, int C0, const void* x1, int C1, int N, int
         cuuint64_t strides[1] = {(cuuint64_t)9 * C * 2};
         cuuint32_t box[2] = {(cuuint32_t)p.block_k, (cuuint32_t)p.bn};
         if (int rc = tmap_encode_bf16(&p.b_map, w, 2, dims, strides, box, swz, "wide weights")) return rc;
+    }
+    if (p.staged) {
+        cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)W * Cout * 2, (cuuint64_t)H * W * Cout * 2};
+        cuuint32_t box[4] = {64u, (cuuint32_t)kWideOutCols, 1u, 1u};
+        if (int rc = tmap_encode_bf16(&p.y_map, y, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, "wide output")) return rc;
     }
     const int grid = (int)std::min<int64_t>(total, g_wide_sms);
     conv3x3_wide_kernel<<<grid, kWideThreads, smem, as_stream(stream)>>>(p);

@@ -214,6 +214,16 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     if (i < n16) tmem_ld16_nowait(taddr + (uint32_t)(grp * p.st_ch + i * 16), r[i]);
+                // bias of the group's channels: requested before the waits below so the global-load latency
+                // overlaps them (a load after tcgen05.wait::ld stalled every 16-column step on the long scoreboard)
+                float4 bv[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        bv[i][e] = (p.bias && i < n16)
+                                       ? __ldg(reinterpret_cast<const float4*>(p.bias + co0 + grp * p.st_ch + i * 16) + e)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
                 // the store that last read this staging buffer must have finished reading it
                 if (issuer) {
                     if (p.st_bufs == 2) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(1) : "memory");
@@ -229,13 +239,10 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
                     float v[16];
 #pragma unroll
                     for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[i][e]);
-                    if (p.bias) {
-                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + co0 + c);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float4 bb = __ldg(b4 + e);
-                            v[4 * e] += bb.x; v[4 * e + 1] += bb.y; v[4 * e + 2] += bb.z; v[4 * e + 3] += bb.w;
-                        }
+                    for (int e = 0; e < 4; ++e) {
+                        const float4 bb = bv[i][e];
+                        v[4 * e] += bb.x; v[4 * e + 1] += bb.y; v[4 * e + 2] += bb.z; v[4 * e + 3] += bb.w;
                     }
                     if (p.residual && valid) {
                         float r0[8], r1[8];
