@@ -20,15 +20,16 @@ for H, C, Co in LAYERS:
     flops = 2.0 * n * H * H * Co * 9 * C
     line = f"{H:5d} {C:4d}->{Co:3d}"
     for impl in impls:
-        for _ in range(2):
+        for _ in range(0 if os.environ.get("PROBE_ONE_LAUNCH") else 2):     # PROBE_ONE_LAUNCH=1: one launch per layer (ncu)
             K.conv2d(x, w, b, 1, 1, True, None, out=y, impl=impl)
         torch.cuda.synchronize()
         a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for _ in range(3):
+        reps = 1 if os.environ.get("PROBE_ONE_LAUNCH") else 3
+        for _ in range(reps):
             K.conv2d(x, w, b, 1, 1, True, None, out=y, impl=impl)
         e.record(); torch.cuda.synchronize()
-        ms = a.elapsed_time(e) / 3
+        ms = a.elapsed_time(e) / reps
         line += f" | {impl} {ms:7.3f} ms {flops / ms / 1e9:7.0f} TF/s"
     print(line, flush=True)
     del x, y
