@@ -202,7 +202,8 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], strid
            impl: str = "auto", x1: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x [N,H,W,C], w [Cout,R,S,C] (same dtype as x) -> [N,Ho,Wo,Cout].
 
-    impl: "tc" = tcgen05 implicit GEMM (bf16 only), "simt" = CUDA-core kernel,
+    impl: "tc" = tcgen05 implicit GEMM (bf16 only; picks the generic, halo-reuse or dw-grouped wide-N kernel by
+    layer shape), "halo" / "wide" = force that kernel, "simt" = CUDA-core kernel,
     "auto" = tc for bf16 activations, simt for fp32 (the fp32 parity mode).
     """
     _chk(x, w, bias, residual, out, x1)

@@ -608,6 +608,8 @@ def test_deferred_gate_scse(C0, skip_ch, mode, gated, dtype):
     (2, 64, 64, 64, 192, 64, 3, "halo"), (1, 40, 24, 128, 64, 32, 3, "halo"), (1, 64, 64, 32, 32, 16, 3, "halo"),
     (1, 32, 32, 512, 512, 256, 3, "tc"), (2, 16, 16, 256, 64, 512, 3, "tc"), (1, 24, 40, 64, 192, 128, 1, "tc"),
     (1, 64, 64, 64, 16, 64, 3, "halo"),      # block_k falls to 16 (must divide both inputs)
+    (2, 64, 64, 64, 192, 64, 3, "wide"), (1, 40, 24, 128, 64, 32, 3, "wide"),
+    (1, 64, 64, 32, 32, 16, 3, "wide"),      # two inputs with resident weights (block_k 32, two chunks)
 ])
 def test_conv_two_inputs_equals_conv_of_concat(case):
     """conv2d(x0, ..., x1=x1) walks the channel chunks of x0 then x1 through two tensor maps: same result as
@@ -695,6 +697,7 @@ def test_conv3x3_small_matches_implicit_gemm_at_tail_size():
     # N, H, W, C, Cout, R, stride, impl
     (2, 37, 29, 64, 256, 3, 1, "tc"), (3, 19, 19, 128, 80, 1, 1, "tc"), (2, 38, 38, 64, 128, 3, 2, "tc"),
     (2, 70, 45, 64, 64, 3, 1, "halo"), (1, 67, 33, 32, 16, 3, 1, "halo"), (2, 131, 77, 16, 16, 3, 1, "tc"),
+    (2, 70, 45, 64, 64, 3, 1, "wide"), (1, 67, 33, 448, 64, 3, 1, "wide"), (2, 131, 77, 32, 16, 3, 1, "wide"),
 ])
 def test_conv_outputs_fully_written_and_repeatable(case):
     """Every output element is written exactly by the kernel (the buffer is pre-filled with NaN: the bulk
@@ -763,6 +766,8 @@ WIDE_CASES = [
     (1, 16, 16, 64, 48, True, False),      # N = 144
     (5, 8, 30, 96, 64, False, False),      # block_k 32 with 3 chunks, one tile per image
     (1, 128, 128, 320, 32, True, False),   # x_0_3 shape class
+    (2, 24, 45, 64, 64, True, True),       # resident weights + staged TMA-store epilogue + residual, ragged W and H
+    (1, 64, 90, 128, 32, False, False),    # resident weights over two channel chunks
 ]
 
 
