@@ -42,6 +42,20 @@ def test_compute_entries_fail_loudly_without_a_gpu():
     model = helpers.build_product_model("Unet", dict(encoder_name="resnet34", encoder_weights=None, classes=1))
     with pytest.raises(RuntimeError, match="CUDA"):
         model(torch.zeros(1, 3, 64, 64))
+    # the drivers added on top of the path keep the rule: no silent CPU route
+    from types import SimpleNamespace
+    from eyediseasesegmentation_b200 import ensemble
+    from eyediseasesegmentation_b200.aucpr_cb import AucPRMetricCallback
+    cb = AucPRMetricCallback()
+    cb.on_loader_start(None)
+    runner = SimpleNamespace(output={"logits": torch.zeros(1, 1, 8, 8)}, input={"targets": torch.zeros(1, 1, 8, 8)},
+                             loader_metrics={})
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cb.on_batch_end(runner)
+    with pytest.raises(ValueError):
+        cb.on_loader_end(runner)                       # nothing was accumulated (np.concatenate([]) in the reference)
+    with pytest.raises(ValueError, match="no CPU path"):
+        ensemble.ensemble_mean(torch.zeros(2, 1, 64, 64))
 
 
 def test_product_never_imports_the_oracle():
