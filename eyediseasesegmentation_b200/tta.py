@@ -88,7 +88,9 @@ def tta_patches(logdir, config, args):
     model = drv.build_model(config, logdir, args)
     _, mean, std = archs.get_preprocessing_fn(dataset_name=config["dataset_name"], grayscale=config["gray"])
     if config["gray"]:
-        raise NotImplementedError("gray=True inputs are outside the B200 hot path (3-channel stem)")
+        # tta.py:166,196-204: this path always reads the RGB window; `gray` only swaps the per-channel statistics
+        # for their luma-weighted scalars, broadcast over the three channels
+        mean, std = [mean] * 3, [std] * 3
     transforms = drv.tta_transforms(args)
     resize_size = config["scale_size"]
     dev = drv.device()
