@@ -65,12 +65,25 @@ def build_model(config, logdir, args):
         raise NotImplementedError("TransUnet is outside the B200 hot path")
     else:
         model = archs.get_model(model_name=config["model_name"], params=config["model_params"], training=False)
-    ckpt = torch.load(f"{logdir}/checkpoints/{'best' if str_2_bool(args['best']) else 'last'}.pth",
-                      map_location="cpu")
+    ckpt = load_checkpoint(f"{logdir}/checkpoints/{'best' if str_2_bool(args['best']) else 'last'}.pth")
     model.load_state_dict(ckpt["model_state_dict"])
     model = model.to(device())
     model.eval()
     return model
+
+
+def load_checkpoint(path):
+    """``torch.load`` of a reference checkpoint (tta.py:86,168).  catalyst checkpoints also carry optimizer /
+    scheduler state and metric dicts with numpy scalars, which the ``weights_only=True`` default of torch >= 2.6
+    refuses; the reference loads them unrestricted, so a checkpoint the restricted loader rejects is re-read the
+    reference's way (checkpoints are the user's own training output)."""
+    import pickle
+    try:
+        return torch.load(path, map_location="cpu", weights_only=True)
+    except (pickle.UnpicklingError, RuntimeError, AttributeError) as e:
+        logging.info(f"checkpoint {path} needs the unrestricted unpickler ({type(e).__name__}); loading with "
+                     "weights_only=False")
+        return torch.load(path, map_location="cpu", weights_only=False)
 
 
 def tta_transforms(args):
@@ -99,21 +112,51 @@ def predict_probs(model, transforms, x: torch.Tensor) -> torch.Tensor:
 class CachedPredictions:
     """Re-iterable ``(pred, gt, name)`` source: the first iteration runs ``produce`` (inference
     + scoring) and keeps the results on the host; later iterations replay them.  This is what
-    makes the reference's ``@multigen`` pattern cost one pass instead of three."""
+    makes the reference's ``@multigen`` pattern cost one pass instead of three.
 
-    def __init__(self, produce: Callable):
+    Memory: the reference streams its three passes in O(1) memory; a cache of full-resolution fp32 maps is
+    ~61 MB per IDRiD image and tens of GB on DDR / FGADR.  Up to ``EDS_CACHE_BYTES`` (default 8 GiB) stay in
+    RAM; beyond that the arrays are spilled to ``np.memmap`` files in a temporary directory (the scores, which
+    is all the first two consumers read, always stay in memory)."""
+
+    def __init__(self, produce: Callable, budget_bytes: Optional[int] = None):
         self._produce = produce
         self._items: Optional[list] = None
+        self._budget = int(os.environ.get("EDS_CACHE_BYTES", 8 << 30)) if budget_bytes is None else budget_bytes
+        self._held = 0
+        self._spill_dir = None
 
     def __iter__(self):
         if self._items is not None:
             return iter(self._items)
         return self._first_pass()
 
+    def _spill(self, arr: np.ndarray, tag: str) -> np.ndarray:
+        import tempfile
+        if self._spill_dir is None:
+            self._spill_dir = tempfile.TemporaryDirectory(prefix="eds_cache_")
+        mm = np.lib.format.open_memmap(os.path.join(self._spill_dir.name, tag + ".npy"), mode="w+",
+                                       dtype=arr.dtype, shape=arr.shape)
+        mm[...] = arr
+        mm.flush()
+        return mm
+
+    def _keep(self, item, index: int):
+        pred, gt, name = item
+        nbytes = getattr(pred, "nbytes", 0) + getattr(gt, "nbytes", 0)
+        if self._held + nbytes <= self._budget:
+            self._held += nbytes
+            return item
+        scores = getattr(pred, "_eds_scores", None)
+        spilled = self._spill(np.asarray(pred), f"pred{index}")
+        if scores is not None:
+            spilled = ScoredArray(spilled, scores)
+        return spilled, self._spill(np.asarray(gt), f"gt{index}"), name
+
     def _first_pass(self):
         items = []
         for item in self._produce():
-            items.append(item)
+            items.append(self._keep(item, len(items)))
             yield item
         self._items = items
 

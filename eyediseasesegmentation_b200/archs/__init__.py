@@ -13,6 +13,7 @@ row 11).
 from __future__ import annotations
 
 import os
+import threading
 from typing import Dict, Optional
 
 import numpy as np
@@ -49,6 +50,11 @@ class B200SegModel(nn.Module):
     ``.eval()``, ``.to(device)``, wrapping by ``SegmentationTTAWrapper`` / ``nn.DataParallel``.
     ``precision`` is ``"bf16"`` (tcgen05 tensor cores, default) or ``"fp32"`` (parity mode;
     also selectable with EDS_PRECISION=fp32).
+
+    Devices: the prepared (BN-folded, repacked) weights and the captured CUDA graphs are kept PER DEVICE and a
+    forward runs with the input's device made current, so one process may drive several GPUs
+    (``nn.DataParallel`` replicas share this state through their copied ``__dict__`` and each picks the
+    entry of the device its input chunk lives on).  One process per GPU (torchrun) remains the fast path.
     """
 
     def __init__(self, arch: str, cfg: dict, seed: Optional[int] = None):
@@ -90,42 +96,68 @@ class B200SegModel(nn.Module):
         _spec.materialise(self, s)
         self.deep_supervision = False
         self.precision = os.environ.get("EDS_PRECISION", "bf16")
-        self._engine: Optional[Engine] = None
-        self._engine_key = None
+        # shared (by reference) with nn.DataParallel replicas: {(device, precision): Engine}, {key: graph entry},
+        # the module that owns the parameters, and a lock for concurrent replica threads
+        self._engines: Dict[tuple, Engine] = {}
         self._graphs = {}
+        self._owner = [self]
+        self._lock = threading.Lock()
 
     # ---- any change to the parameters invalidates the prepared (folded) weights and captured graphs
+    def _invalidate(self):
+        self._engines.clear()
+        self._graphs.clear()
+
     def _apply(self, fn, *a, **k):
-        self._engine = None
-        self._graphs = {}
+        self._invalidate()
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
-        self._engine = None
-        self._graphs = {}
+        self._invalidate()
         return super().load_state_dict(state_dict, strict=strict, **kw)
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k in ("_engines", "_graphs", "_owner", "_lock"):
+                continue
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        new._engines, new._graphs, new._owner, new._lock = {}, {}, [new], threading.Lock()
+        return new
 
     def train(self, mode: bool = True):
         if mode:
             raise NotImplementedError("B200SegModel is inference-only (training is outside the hot path)")
         return super().train(False)
 
-    def engine(self) -> Engine:
-        dev = next(self.parameters()).device
+    def engine(self, device: Optional[torch.device] = None) -> Engine:
+        """Prepared weights on ``device`` (default: where the parameters live), built on first use."""
+        owner = self._owner[0]
+        dev = torch.device(device) if device is not None else next(owner.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("B200SegModel runs only on a CUDA (sm_100a) device: call .to('cuda') first; "
+                               "there is no CPU fallback")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
         key = (str(dev), self.precision)
-        if self._engine is None or self._engine_key != key:
-            self._graphs = {}
-            if dev.type != "cuda":
-                raise RuntimeError("B200SegModel runs only on a CUDA (sm_100a) device: call .to('cuda') first; "
-                                   "there is no CPU fallback")
-            with torch.no_grad():
-                self._engine = Engine(self.arch, self.cfg, self.state_dict(), dev, self.precision)
-            self._engine_key = key
-        return self._engine
+        eng = self._engines.get(key)
+        if eng is None:
+            with self._lock:
+                eng = self._engines.get(key)
+                if eng is None:
+                    with torch.no_grad(), torch.cuda.device(dev):
+                        eng = Engine(self.arch, self.cfg, owner.state_dict(), dev, self.precision)
+                    self._engines[key] = eng
+        return eng
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return self.engine().run(x)
+        if not x.is_cuda:
+            raise RuntimeError("the B200 networks only run on a CUDA device (no CPU fallback); got a CPU tensor")
+        with torch.cuda.device(x.device):
+            return self.engine(x.device).run(x)
 
     @torch.no_grad()
     def forward_tta(self, x: torch.Tensor, transforms, apply_sigmoid: bool = False) -> torch.Tensor:
@@ -143,7 +175,12 @@ class B200SegModel(nn.Module):
         aug, deaug = tta.view_maps(transforms, H, W)
         if not x.is_cuda:
             raise RuntimeError("the B200 networks only run on a CUDA device (no CPU fallback); got a CPU tensor")
-        use_graph = (_graphs_enabled() and K.CONV_TRACE is None and not self.engine().keep_features)
+        with torch.cuda.device(x.device):
+            return self._forward_tta_on_device(x, aug, deaug, apply_sigmoid)
+
+    def _forward_tta_on_device(self, x, aug, deaug, apply_sigmoid):
+        from .. import kernels as K
+        use_graph = (_graphs_enabled() and K.CONV_TRACE is None and not self.engine(x.device).keep_features)
         if not use_graph:
             return self._forward_tta_eager(x, aug, deaug, apply_sigmoid)
         key = (tuple(x.shape), str(x.device), self.precision, tuple(map(tuple, aug)), bool(apply_sigmoid))
@@ -170,7 +207,7 @@ class B200SegModel(nn.Module):
     def _forward_tta_eager(self, x, aug, deaug, apply_sigmoid):
         from .. import kernels as K
         B, _, H, W = x.shape
-        logits = self.engine().run(x, aug)                    # [V*B, classes, H, W]
+        logits = self.engine(x.device).run(x, aug)            # [V*B, classes, H, W]
         if logits.shape[1] != 1 or H != W:
             raise NotImplementedError("fused TTA merge handles square single-class maps")
         merged = K.tta_merge(logits.view(len(aug), B, H, W), deaug, apply_sigmoid)

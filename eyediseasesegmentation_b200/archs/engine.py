@@ -63,10 +63,15 @@ class Engine:
         self.w: Dict[str, object] = {}
         self.features: Optional[Dict[str, torch.Tensor]] = None  # filled when keep_features is set
         self.keep_features = False
-        sd = {k: v.detach().to(device) for k, v in sd.items()}
+        # BatchNorm folding and repacking run on the HOST (IEEE fp32, same results as on the device): weight
+        # preparation then costs uploads, not ~800 small elementwise launches per model
+        sd = {k: v.detach().cpu() for k, v in sd.items()}
         self.up_mode = _lib.UP_BILINEAR if arch == "unetplusplusstar" else _lib.UP_NEAREST
         self.senet = "encoder.layer0.conv1.weight" in sd
         self._prepare(sd)
+        self.w = {k: tuple(t.to(device) if torch.is_tensor(t) else t for t in v) for k, v in self.w.items()}
+        if self.act_dtype == torch.bfloat16:      # tensor-core stem: operand packed once
+            self.w["stem.packed"] = K.stem_pack_weights(self.w["stem"][0])
 
     # ------------------------------------------------------------ weight prep
     def _conv(self, sd, name, conv_key, bn_key=None, perm=None):
@@ -111,14 +116,12 @@ class Engine:
                 torch.arange(heads, device=device).view(heads, 1)).reshape(-1)
 
     def _prepare(self, sd):
-        dev = self.device
+        dev = torch.device("cpu")
         # stem: [64,3,7,7] -> [7][7][3][64] fp32
         stem_conv, stem_bn = ("encoder.layer0.conv1", "encoder.layer0.bn1") if self.senet else ("encoder.conv1", "encoder.bn1")
         scale, shift = _bn_affine(sd, stem_bn)
         w = sd[stem_conv + ".weight"].float() * scale.view(-1, 1, 1, 1)
         self.w["stem"] = (w.permute(2, 3, 1, 0).contiguous(), shift.contiguous())
-        if self.act_dtype == torch.bfloat16:      # tensor-core stem: operand packed once
-            self.w["stem.packed"] = K.stem_pack_weights(self.w["stem"][0])
 
         if self.senet:
             n_layers = 3 if self.arch == "unetplusplusstar" else 4

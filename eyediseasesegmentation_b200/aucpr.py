@@ -112,15 +112,19 @@ def get_auc(generator: Iterable, config):
 def get_aucroc(generator: Iterable, config):
     sum_pav = 0
     i = 0
+    one_class = 0
     for pred_mask, gt_mask, _ in generator:
         s = _scores(pred_mask, gt_mask)
         if s.n_pos == 0:
             continue
         if s.n_neg == 0:
-            raise ValueError("Only one class present in y_true. ROC AUC score is not defined in that case.")
+            one_class += 1      # raised AFTER the collective: an exception on one rank must not strand the others
+            continue
         sum_pav += s.roc
         i += 1
-    sum_pav, i = _dist_sum([float(sum_pav), float(i)], torch.float64)
+    sum_pav, i, one_class = _dist_sum([float(sum_pav), float(i), float(one_class)], torch.float64)
+    if one_class:
+        raise ValueError("Only one class present in y_true. ROC AUC score is not defined in that case.")
     return sum_pav / i
 
 
@@ -168,6 +172,9 @@ def _pooled_counts(generator):
 def _figure(figure_dir, exp_name, x, y, title, labels):
     """The plot is a side effect of the reference (plotly + orca); it is written when plotly is
     importable and skipped otherwise -- the returned thresholds do not depend on it."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_rank() != 0:
+        return                  # every rank holds the same pooled curve; one writer
     try:
         import plotly.express as px
     except Exception:

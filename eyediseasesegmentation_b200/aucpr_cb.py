@@ -86,13 +86,17 @@ class AucPRMetricCallback(_Callback):
         prob = pred_probas.detach().reshape(1, -1).to(torch.float32).contiguous()
         # precision_recall_curve: positives are the entries equal to pos_label = 1
         gt = (true_labels.to(prob.device).reshape(1, -1) == 1).to(torch.uint8).contiguous()
-        self._hist, self._straddle = K.pr_hist(prob, gt, self._hist, self._straddle)
+        # the kernel's counters are u32 stored in an int32 tensor: fold every batch into an int64 accumulator
+        # (mask off the sign extension) so a bin can grow past 2^31 over a long loader
+        hist, _ = K.pr_hist(prob, gt)
+        wide = hist.to(torch.int64) & 0xFFFFFFFF
+        self._hist = wide if self._hist is None else self._hist + wide
 
     def on_loader_end(self, runner):
         import torch.distributed as dist
         if self._hist is None:
             raise ValueError("need at least one array to concatenate")     # np.concatenate([]) in the reference
-        hist = self._hist.to(torch.int64)
+        hist = self._hist.clone()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(hist)
         h = hist.cpu().numpy()[0]

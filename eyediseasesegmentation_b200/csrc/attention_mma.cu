@@ -273,16 +273,9 @@ static int launch_attn_mma(const void* qk, int qk_cstride, const void* v, int v_
                            int heads, const float* rel, const float* sim_scale, const float* out_scale,
                            const float* out_shift, int relu, void* y, cudaStream_t stream) {
     constexpr size_t smem = AttnSmem<DV, LP>::total;
-    static bool attr_set = false;
-    if (!attr_set && smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(axial_attention_mma_kernel<DV, LP>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) {
-            set_error("axial_attention_mma: shared-memory opt-in (%zu B) failed: %s", smem, cudaGetErrorString(e));
-            return EDS_ERR_CUDA;
-        }
-        attr_set = true;
-    }
+    static PerDevice once;                    // one flag per template instance and per device
+    if (smem > 48 * 1024)
+        if (int rc = smem_opt_in(once, axial_attention_mma_kernel<DV, LP>, (int)smem, "axial_attention_mma")) return rc;
     dim3 grid(n_seq, heads / kHeadsPerCta);
     axial_attention_mma_kernel<DV, LP><<<grid, kMmaAttnThreads, smem, stream>>>(
         (const __nv_bfloat16*)qk, qk_cstride, (const __nv_bfloat16*)v, v_cstride, H, W, axis, heads, rel, sim_scale,

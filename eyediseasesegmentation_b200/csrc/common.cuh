@@ -5,6 +5,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
+#include <atomic>
+#include <mutex>
 
 #include "../../include/eds_b200.h"
 
@@ -22,6 +24,42 @@ int  check_launch(const char* what);   // cudaGetLastError -> EDS_ERR_CUDA
             return EDS_ERR_INVALID;                              \
         }                                                        \
     } while (0)
+
+// ---- one-time-per-DEVICE initialisation ---------------------------------------
+// cudaFuncSetAttribute (dynamic shared memory opt-in) and __constant__ uploads belong to a device's
+// context, not to the process: a process that drives two GPUs must repeat them on the second one.
+// `PerDevice once; once.run([](int dev) { ...; return EDS_OK; })` runs the body the first time it is
+// reached with each current device (a failed body is retried on the next call).
+constexpr int kMaxDevices = 64;
+struct PerDevice {
+    std::atomic<bool> done[kMaxDevices];
+    std::mutex mu;
+    PerDevice() { for (auto& d : done) d.store(false); }
+    template <typename F> int run(F&& body) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+            set_error("cannot identify the current CUDA device (index %d)", dev);
+            return EDS_ERR_CUDA;
+        }
+        if (done[dev].load(std::memory_order_acquire)) return EDS_OK;
+        std::lock_guard<std::mutex> lock(mu);
+        if (done[dev].load(std::memory_order_relaxed)) return EDS_OK;
+        const int rc = body(dev);
+        if (rc == EDS_OK) done[dev].store(true, std::memory_order_release);
+        return rc;
+    }
+};
+// dynamic shared-memory opt-in of one kernel, once per device
+template <typename Kern> static inline int smem_opt_in(PerDevice& once, Kern kern, int bytes, const char* what) {
+    return once.run([&](int) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) {
+            set_error("%s: cannot opt in to %d B of shared memory: %s", what, bytes, cudaGetErrorString(e));
+            return (int)EDS_ERR_CUDA;
+        }
+        return (int)EDS_OK;
+    });
+}
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

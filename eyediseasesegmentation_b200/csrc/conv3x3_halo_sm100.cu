@@ -233,22 +233,21 @@ conv3x3_halo_kernel(const __grid_constant__ HaloParams p) {
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
-static std::once_flag g_halo_once;
-static int g_halo_rc = EDS_OK;
+static PerDevice g_halo_once;             // the shared-memory opt-in belongs to a device's context
 static int g_num_sms = 148;
 static int g_stage_override = 0;
 
-static void halo_init_once() {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) {
-        set_error("conv3x3_halo: cannot opt in to 227 KB shared memory: %s", cudaGetErrorString(e));
-        g_halo_rc = EDS_ERR_CUDA;
-        return;
-    }
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
-        g_num_sms = sms;
+static int halo_init() {
+    return g_halo_once.run([](int dev) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) {
+            set_error("conv3x3_halo: cannot opt in to 227 KB shared memory: %s", cudaGetErrorString(e));
+            return (int)EDS_ERR_CUDA;
+        }
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) g_num_sms = sms;
+        return (int)EDS_OK;
+    });
 }
 
 static int pow2_ceil_i(int v) {
@@ -279,8 +278,7 @@ static int halo_launch(const void* x, int C0, const void* x1, int C1, int N, int
     EDS_REQUIRE((((uintptr_t)x | (uintptr_t)w | (uintptr_t)y | (uintptr_t)residual | (uintptr_t)bias) & 15) == 0,
                 "conv3x3_halo: pointers must be 16-byte aligned");
     if (int rc = igemm_init()) return rc;            // driver entry point for the tensor maps
-    std::call_once(g_halo_once, halo_init_once);
-    if (g_halo_rc) return g_halo_rc;
+    if (int rc = halo_init()) return rc;
 
     HaloParams p;
     memset(&p, 0, sizeof(p));

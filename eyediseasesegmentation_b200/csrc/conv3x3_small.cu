@@ -190,16 +190,9 @@ static int small_launch(const void* x, const float* cgate, const float* sgate, i
     const size_t smem_mma = ((Cfg::in_bytes + 15) & ~(size_t)15) + (size_t)COUT * Cfg::KP * 2;
     const size_t smem_out = (size_t)kSmallTH * kSmallTW * (COUT + 8) * 2;      // staging reuses the same space
     const size_t smem = smem_mma > smem_out ? smem_mma : smem_out;
-    static bool attr_set = false;
-    if (!attr_set && smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_small_kernel<CIN, COUT, UP>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) {
-            set_error("conv3x3_small: shared-memory opt-in failed: %s", cudaGetErrorString(e));
-            return EDS_ERR_CUDA;
-        }
-        attr_set = true;
-    }
+    static PerDevice once;                    // one flag per template instance and per device
+    if (smem > 48 * 1024)
+        if (int rc = smem_opt_in(once, conv3x3_small_kernel<CIN, COUT, UP>, (int)smem, "conv3x3_small")) return rc;
     dim3 grid(ceil_div(W, kSmallTW), ceil_div(H, kSmallTH), N);
     conv3x3_small_kernel<CIN, COUT, UP><<<grid, 256, smem, stream>>>(
         (const __nv_bfloat16*)x, cgate, sgate, H, W, (const __nv_bfloat16*)w, bias, relu, (__nv_bfloat16*)y);

@@ -288,21 +288,20 @@ conv3x3_wide_kernel(const __grid_constant__ WideParams p) {
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
-static std::once_flag g_wide_once;
-static int g_wide_rc = EDS_OK;
+static PerDevice g_wide_once;             // the shared-memory opt-in belongs to a device's context
 static int g_wide_sms = 148;
 
-static void wide_init_once() {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) {
-        set_error("conv3x3_wide: cannot opt in to 227 KB shared memory: %s", cudaGetErrorString(e));
-        g_wide_rc = EDS_ERR_CUDA;
-        return;
-    }
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
-        g_wide_sms = sms;
+static int wide_init() {
+    return g_wide_once.run([](int dev) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) {
+            set_error("conv3x3_wide: cannot opt in to 227 KB shared memory: %s", cudaGetErrorString(e));
+            return (int)EDS_ERR_CUDA;
+        }
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) g_wide_sms = sms;
+        return (int)EDS_OK;
+    });
 }
 
 }  // namespace eds
@@ -326,8 +325,7 @@ static int wide_launch(const void* x, int C0, const void* x1, int C1, int N, int
     EDS_REQUIRE((((uintptr_t)x | (uintptr_t)x1 | (uintptr_t)w | (uintptr_t)y | (uintptr_t)residual | (uintptr_t)bias) &
                  15) == 0, "conv3x3_wide: pointers must be 16-byte aligned");
     if (int rc = igemm_init()) return rc;            // driver entry point for the tensor maps
-    std::call_once(g_wide_once, wide_init_once);
-    if (g_wide_rc) return g_wide_rc;
+    if (int rc = wide_init()) return rc;
 
     WideParams p;
     memset(&p, 0, sizeof(p));

@@ -320,20 +320,24 @@ static void igemm_init_once() {
         g_l2_promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
                      : v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     }
-    e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) {
-        set_error("conv_igemm: cannot opt in to 227 KB shared memory: %s", cudaGetErrorString(e));
-        g_igemm_init_rc = EDS_ERR_CUDA;
-    }
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
-        g_num_sms = sms;
 }
 
+static PerDevice g_igemm_attr_once;       // the shared-memory opt-in belongs to a device's context
+
+// The driver entry point is found once per process, the kernel attribute is set once per device.
 int igemm_init() {
     std::call_once(g_igemm_once, igemm_init_once);
-    return g_igemm_init_rc;
+    if (g_igemm_init_rc) return g_igemm_init_rc;
+    return g_igemm_attr_once.run([](int dev) {
+        cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) {
+            set_error("conv_igemm: cannot opt in to 227 KB shared memory: %s", cudaGetErrorString(e));
+            return (int)EDS_ERR_CUDA;
+        }
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) g_num_sms = sms;
+        return (int)EDS_OK;
+    });
 }
 
 static int ilog2(int v) {

@@ -27,9 +27,6 @@ struct ThreshTable {
     int key[kNT];
 };
 __constant__ ThreshTable c_thresh;
-static ThreshTable h_thresh;
-static bool h_thresh_ready = false;
-
 __host__ __device__ __forceinline__ int float_bits(float f) {
 #ifdef __CUDA_ARCH__
     return __float_as_int(f);
@@ -54,139 +51,219 @@ static const double kThresholds[kNT] = {0,   0.00001, 0.0001, 0.001, 0.01,  0.1,
                                         0.3, 0.4,     0.5,    0.6,   0.7,   0.8,    0.9,
                                         0.99, 0.999,  0.9999, 0.99999, 1};
 
+static PerDevice g_thresh_once;      // __constant__ memory is per device
 static int ensure_thresholds() {
-    if (h_thresh_ready) return EDS_OK;
-    for (int k = 0; k < kNT; ++k) {
-        float f = (float)kThresholds[k];
-        if ((double)f > kThresholds[k]) f = nextafterf(f, -1.0f);
-        h_thresh.bits[k] = float_bits(f);
-        h_thresh.key[k] = score_key(f);
-    }
-    cudaError_t e = cudaMemcpyToSymbol(c_thresh, &h_thresh, sizeof(h_thresh));
-    if (e != cudaSuccess) {
-        set_error("pr_hist: cudaMemcpyToSymbol failed: %s", cudaGetErrorString(e));
-        return EDS_ERR_CUDA;
-    }
-    h_thresh_ready = true;
-    return EDS_OK;
+    return g_thresh_once.run([](int) {
+        ThreshTable h;
+        for (int k = 0; k < kNT; ++k) {
+            float f = (float)kThresholds[k];
+            if ((double)f > kThresholds[k]) f = nextafterf(f, -1.0f);
+            h.bits[k] = float_bits(f);
+            h.key[k] = score_key(f);
+            if (k > 0 && h.key[k] <= h.key[k - 1]) {      // the counter tags name ONE threshold per bin
+                set_error("pr_hist: thresholds %d and %d share a histogram key", k - 1, k);
+                return (int)EDS_ERR_INVALID;
+            }
+        }
+        cudaError_t e = cudaMemcpyToSymbol(c_thresh, &h, sizeof(h));
+        if (e != cudaSuccess) {
+            set_error("pr_hist: cudaMemcpyToSymbol failed: %s", cudaGetErrorString(e));
+            return (int)EDS_ERR_CUDA;
+        }
+        return (int)EDS_OK;
+    });
 }
 
+// Shared-memory image of one CTA: interleaved counters [key][class] (class 1 = positive), the straddle
+// counters and the bit patterns of the thresholds.
+// The counters of the 19 bins that share a key with a threshold carry a TAG in their top six bits:
+// bit 31 set, bits 26-30 = index of that threshold.  The atomic's return value therefore tells a pixel
+// that it landed in such a bin and which threshold to compare with, so the common path needs no second
+// shared-memory access per pixel (round 1 paid one LDS.U8 per pixel for a flag table -- as many
+// shared-memory wavefronts as the atomics themselves -- and a 19-step search per tagged pixel).
+// The count field is 26 bits: the launcher keeps a CTA's share of one image below 2^26 pixels.
+constexpr uint32_t kTag = 0x80000000u;
+constexpr int kTagShift = 26;
+constexpr uint32_t kCountMask = (1u << kTagShift) - 1;
 struct HistSmem {
     uint32_t hist[2 * kBins];
     uint32_t straddle[kNT * 2];
-    uint8_t flag[kBins + 2];      // 1 where the bin shares its key with one of the 19 thresholds
+    int thr_bits[32];
 };
 
-__device__ __forceinline__ void straddle_update(HistSmem* s, int bits, int key, int cls) {
-#pragma unroll 1
-    for (int k = 0; k < kNT; ++k)
-        if (key == c_thresh.key[k] && bits > c_thresh.bits[k]) atomicAdd(&s->straddle[k * 2 + cls], 1u);
+// Byte offset of the counter of (score, label byte j of the 4-label word) inside HistSmem::hist.
+// q = min(p, 1-p) equals "p >= 1/2 ? 1-p : p" for every input (1-p is exact for p in [1/2, 1]); the two
+// integer clamps keep the documented behaviour for p < 2^-24, p > 1, negative values and NaN.
+__device__ __forceinline__ uint32_t counter_offset(float p, uint32_t nz, int j) {
+    const float q = fminf(p, 1.0f - p);
+    int k = (__float_as_int(q) >> EDS_PR_KEY_SHIFT) - EDS_PR_KEY_BIAS;
+    k = max(k, 0);
+    k = min(k, EDS_PR_HALF - 1);
+    const int key = p >= 0.5f ? kBins - 1 - k : k;
+    return ((uint32_t)key << 3) | ((nz >> (8 * j + 5)) & 4u);
+}
+
+// 0x80 in every byte of g that is non-zero
+__device__ __forceinline__ uint32_t nonzero_bytes(uint32_t g) {
+    return (((g & 0x7f7f7f7fu) + 0x7f7f7f7fu) | g) & 0x80808080u;
+}
+
+// A pixel whose atomic returned a tagged counter: strictly above the threshold of that bin?
+__device__ __forceinline__ void straddle_one(HistSmem* s, uint32_t old, float p, uint32_t off) {
+    if (old & kTag) {
+        const int k = (old >> kTagShift) & 31;
+        if (__float_as_int(p) > s->thr_bits[k]) atomicAdd(&s->straddle[k * 2 + ((off >> 2) & 1)], 1u);
+    }
 }
 
 __device__ __forceinline__ void hist_one(HistSmem* s, float p, uint8_t g) {
-    const int bits = __float_as_int(p);
-    const int key = score_key(p);
-    const int cls = g != 0;
-    atomicAdd(&s->hist[cls * kBins + key], 1u);
-    if (s->flag[key]) straddle_update(s, bits, key, cls);
+    const uint32_t off = counter_offset(p, g ? 0x80u : 0u, 0);
+    const uint32_t old = atomicAdd(reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(s->hist) + off), 1u);
+    straddle_one(s, old, p, off);
 }
 
-constexpr int kQuadUnroll = 2;    // float4 + uchar4 pairs in flight per thread
-
-// grid = (splits, n_images); each CTA bins a contiguous slice of one image.
-// The loop body is ~12 instructions per pixel (key: shift, subtract, clamp; class offset; one
-// shared-memory atomic; one byte load for the threshold flag), which is what lets one SM retire
-// several pixels per clock: the first version spent 60 instructions per pixel and was bound by
-// instruction issue at ~1 pixel/clk/SM (profiles/r01_probe1_full.md), not by the atomics.
-__global__ void __launch_bounds__(kHistThreads, 1)
-pr_hist_kernel(const float* __restrict__ prob, const uint8_t* __restrict__ gt, int64_t n_pixels,
-               uint32_t* __restrict__ g_hist, uint32_t* __restrict__ g_straddle, int vec_ok) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    HistSmem* s = reinterpret_cast<HistSmem*>(smem_raw);
-    const int tid = threadIdx.x;
-    const int img = blockIdx.y;
+__device__ __forceinline__ void hist_clear(HistSmem* s, int tid) {
     for (int i = tid; i < 2 * kBins; i += kHistThreads) s->hist[i] = 0;
-    for (int i = tid; i < kBins + 2; i += kHistThreads) s->flag[i] = 0;
     if (tid < kNT * 2) s->straddle[tid] = 0;
+    if (tid < 32) s->thr_bits[tid] = tid < kNT ? c_thresh.bits[tid] : 0x7fffffff;
     __syncthreads();
-    if (tid < kNT) s->flag[c_thresh.key[tid]] = 1;
-    __syncthreads();
-
-    const float* p_img = prob + (int64_t)img * n_pixels;
-    const uint8_t* g_img = gt + (int64_t)img * n_pixels;
-    // slice boundaries in units of 4 pixels so the vector path stays aligned
-    const int64_t n_quads = (n_pixels + 3) / 4;
-    const int64_t q_per = (n_quads + gridDim.x - 1) / gridDim.x;
-    const int64_t q_begin = (int64_t)blockIdx.x * q_per;
-    int64_t q_end = q_begin + q_per;
-    if (q_end > n_quads) q_end = n_quads;
-
-    if (vec_ok && q_end > q_begin) {
-        const float4* p4 = reinterpret_cast<const float4*>(p_img) + q_begin;
-        const uchar4* g4 = reinterpret_cast<const uchar4*>(g_img) + q_begin;
-        const int nq = (int)(q_end - q_begin);           // < 2^31: a CTA slice is part of one image
-        uint32_t* hist = s->hist;
-        const uint8_t* flag = s->flag;
-        for (int q0 = 0; q0 < nq; q0 += kHistThreads * kQuadUnroll) {
-            float4 p[kQuadUnroll];
-            uchar4 g[kQuadUnroll];
-            // unconditional loads (index clamped into the slice) keep both pairs in flight
-#pragma unroll
-            for (int u = 0; u < kQuadUnroll; ++u) {
-                const int q = min(q0 + u * kHistThreads + tid, nq - 1);
-                p[u] = __ldg(p4 + q);
-                g[u] = __ldg(g4 + q);
-            }
-#pragma unroll
-            for (int u = 0; u < kQuadUnroll; ++u) {
-                const bool live = q0 + u * kHistThreads + tid < nq;
-                const int b0 = __float_as_int(p[u].x), b1 = __float_as_int(p[u].y);
-                const int b2 = __float_as_int(p[u].z), b3 = __float_as_int(p[u].w);
-                const int k0 = score_key(p[u].x), k1 = score_key(p[u].y), k2 = score_key(p[u].z), k3 = score_key(p[u].w);
-                const int a0 = k0 + (g[u].x ? kBins : 0), a1 = k1 + (g[u].y ? kBins : 0);
-                const int a2 = k2 + (g[u].z ? kBins : 0), a3 = k3 + (g[u].w ? kBins : 0);
-                const bool same4 = (a0 == a1) & (a1 == a2) & (a2 == a3);
-                // flat regions (background of a fundus image): one atomic per thread, or per warp
-                // when the whole warp sees one bin -- same-address atomics would serialise otherwise
-                if (__all_sync(0xffffffffu, same4 && live)) {
-                    const int lead = __shfl_sync(0xffffffffu, a0, 0);
-                    if (__all_sync(0xffffffffu, a0 == lead)) {
-                        if ((tid & 31) == 0) atomicAdd(hist + lead, 128u);
-                    } else {
-                        atomicAdd(hist + a0, 4u);
-                    }
-                } else if (live) {
-                    atomicAdd(hist + a0, 1u);
-                    atomicAdd(hist + a1, 1u);
-                    atomicAdd(hist + a2, 1u);
-                    atomicAdd(hist + a3, 1u);
-                }
-                if (live) {
-                    const uint32_t hit = (uint32_t)flag[k0] | flag[k1] | flag[k2] | flag[k3];
-                    if (hit) {
-                        if (flag[k0]) straddle_update(s, b0, k0, g[u].x != 0);
-                        if (flag[k1]) straddle_update(s, b1, k1, g[u].y != 0);
-                        if (flag[k2]) straddle_update(s, b2, k2, g[u].z != 0);
-                        if (flag[k3]) straddle_update(s, b3, k3, g[u].w != 0);
-                    }
-                }
-            }
-        }
-    } else if (!vec_ok) {
-        int64_t i_end = q_end * 4;
-        if (i_end > n_pixels) i_end = n_pixels;
-        for (int64_t i = q_begin * 4 + tid; i < i_end; i += kHistThreads) hist_one(s, p_img[i], g_img[i]);
+    if (tid < kNT) {                       // the 19 keys are distinct (checked on the host)
+        const uint32_t tag = kTag | ((uint32_t)tid << kTagShift);
+        s->hist[2 * c_thresh.key[tid]] = tag;
+        s->hist[2 * c_thresh.key[tid] + 1] = tag;
     }
     __syncthreads();
+}
 
-    uint32_t* gh = g_hist + (int64_t)img * 2 * kBins;
+__device__ __forceinline__ void hist_flush(HistSmem* s, int tid, uint32_t* __restrict__ gh, uint32_t* __restrict__ gs) {
+    __syncthreads();
     for (int i = tid; i < 2 * kBins; i += kHistThreads) {
-        const uint32_t v = s->hist[i];
-        if (v) atomicAdd(gh + i, v);
+        const uint32_t v = s->hist[i] & kCountMask;       // i = key * 2 + class
+        if (v) atomicAdd(gh + (i & 1) * kBins + (i >> 1), v);
     }
     if (tid < kNT * 2) {
         const uint32_t v = s->straddle[tid];
-        if (v) atomicAdd(g_straddle + (int64_t)img * kNT * 2 + tid, v);
+        if (v) atomicAdd(gs + tid, v);
+    }
+    __syncthreads();
+}
+
+constexpr int kQuadUnroll = 4;    // float4 + uchar4 pairs in flight per thread (80 KB per SM)
+constexpr int kPxPerThread = 4 * kQuadUnroll;
+
+// Persistent grid of <= one CTA per SM.  The test set is ONE linear range of 4-pixel quads (image-major);
+// CTA c takes the contiguous share [c*T/G, (c+1)*T/G) and, when its share crosses an image boundary,
+// flushes and clears its shared-memory histogram there.  (Round 1 launched ceil(2*SMs/n_images) CTAs per
+// image: 297 CTAs for 27 images = two full waves plus ONE straggler CTA.)
+// Common path per pixel, ~13 instructions: key (fmin, shift, clamps, mirror), label bit, one returning
+// shared-memory atomic, one OR of the returned tag; one warp-uniform branch per 16 pixels of a thread.
+__global__ void __launch_bounds__(kHistThreads, 1)
+pr_hist_kernel(const float* __restrict__ prob, const uint8_t* __restrict__ gt, int64_t n_pixels, int n_images,
+               uint32_t* __restrict__ g_hist, uint32_t* __restrict__ g_straddle, int vec_ok, int per_image_splits) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    HistSmem* s = reinterpret_cast<HistSmem*>(smem_raw);
+    const int tid = threadIdx.x;
+    char* hbase = reinterpret_cast<char*>(s->hist);
+
+    const int64_t n_quads = (n_pixels + 3) / 4;           // per image; vec_ok implies n_pixels % 4 == 0
+    int64_t w_begin, w_end;                               // this CTA's share of [0, n_images * n_quads)
+    if (per_image_splits > 0) {                           // caller-fixed split: CTA = (image, split)
+        const int img = blockIdx.x / per_image_splits, sp = blockIdx.x % per_image_splits;
+        const int64_t q_per = (n_quads + per_image_splits - 1) / per_image_splits;
+        w_begin = (int64_t)img * n_quads + min((int64_t)sp * q_per, n_quads);
+        w_end = (int64_t)img * n_quads + min((int64_t)(sp + 1) * q_per, n_quads);
+    } else {
+        const int64_t total = (int64_t)n_images * n_quads;
+        w_begin = total / gridDim.x * blockIdx.x + min((int64_t)blockIdx.x, total % gridDim.x);
+        w_end = w_begin + total / gridDim.x + (blockIdx.x < total % gridDim.x ? 1 : 0);
+    }
+
+    while (w_begin < w_end) {
+        const int img = (int)(w_begin / n_quads);
+        const int64_t q_begin = w_begin - (int64_t)img * n_quads;
+        const int64_t q_end = min(q_begin + (w_end - w_begin), n_quads);
+        w_begin += q_end - q_begin;
+        const float* p_img = prob + (int64_t)img * n_pixels;
+        const uint8_t* g_img = gt + (int64_t)img * n_pixels;
+        hist_clear(s, tid);
+
+        if (vec_ok) {
+            const float4* p4 = reinterpret_cast<const float4*>(p_img) + q_begin;
+            const uint32_t* g4 = reinterpret_cast<const uint32_t*>(g_img) + q_begin;
+            const int nq = (int)(q_end - q_begin);           // < 2^24: the launcher bounds a share
+            constexpr int kStep = kHistThreads * kQuadUnroll;
+            const int n_full = nq / kStep * kStep;
+            for (int q0 = tid; q0 < n_full; q0 += kStep) {
+                float4 p[kQuadUnroll];
+                uint32_t g[kQuadUnroll];
+#pragma unroll
+                for (int u = 0; u < kQuadUnroll; ++u) {
+                    p[u] = __ldcs(p4 + q0 + u * kHistThreads);
+                    g[u] = __ldcs(g4 + q0 + u * kHistThreads);
+                }
+                uint32_t off[kQuadUnroll][4];
+#pragma unroll
+                for (int u = 0; u < kQuadUnroll; ++u) {
+                    const uint32_t nz = nonzero_bytes(g[u]);
+                    off[u][0] = counter_offset(p[u].x, nz, 0);
+                    off[u][1] = counter_offset(p[u].y, nz, 1);
+                    off[u][2] = counter_offset(p[u].z, nz, 2);
+                    off[u][3] = counter_offset(p[u].w, nz, 3);
+                }
+                // Flat regions (saturated background): when the first quad of every lane sits in one
+                // counter, look at the other twelve pixels too; 512 pixels of one bin are ONE atomic
+                // instead of 512 serialised same-address ones.
+                const uint32_t lead = __shfl_sync(0xffffffffu, off[0][0], 0);
+                uint32_t diff = (off[0][0] ^ lead) | (off[0][1] ^ lead) | (off[0][2] ^ lead) | (off[0][3] ^ lead);
+                bool flat = false;
+                if (__all_sync(0xffffffffu, diff == 0)) {
+#pragma unroll
+                    for (int u = 1; u < kQuadUnroll; ++u)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) diff |= off[u][j] ^ lead;
+                    flat = __all_sync(0xffffffffu, diff == 0);
+                }
+                uint32_t old[kQuadUnroll][4], tag = 0;
+                if (flat) {
+                    uint32_t o = 0;
+                    if ((tid & 31) == 0) o = atomicAdd(reinterpret_cast<uint32_t*>(hbase + lead), 32u * kPxPerThread);
+                    tag = __shfl_sync(0xffffffffu, o, 0);
+#pragma unroll
+                    for (int u = 0; u < kQuadUnroll; ++u)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) old[u][j] = tag;
+                } else {
+#pragma unroll
+                    for (int u = 0; u < kQuadUnroll; ++u)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            old[u][j] = atomicAdd(reinterpret_cast<uint32_t*>(hbase + off[u][j]), 1u);
+                            tag |= old[u][j];
+                        }
+                }
+                if (__any_sync(0xffffffffu, tag & kTag)) {   // some pixel of this warp shares a bin with a threshold
+#pragma unroll
+                    for (int u = 0; u < kQuadUnroll; ++u) {
+                        straddle_one(s, old[u][0], p[u].x, off[u][0]);
+                        straddle_one(s, old[u][1], p[u].y, off[u][1]);
+                        straddle_one(s, old[u][2], p[u].z, off[u][2]);
+                        straddle_one(s, old[u][3], p[u].w, off[u][3]);
+                    }
+                }
+            }
+            for (int q = n_full + tid; q < nq; q += kHistThreads) {      // tail: fewer than kStep quads
+                const float4 pq = __ldcs(p4 + q);
+                const uint32_t gq = __ldcs(g4 + q);
+                hist_one(s, pq.x, (uint8_t)(gq & 0xff));
+                hist_one(s, pq.y, (uint8_t)((gq >> 8) & 0xff));
+                hist_one(s, pq.z, (uint8_t)((gq >> 16) & 0xff));
+                hist_one(s, pq.w, (uint8_t)(gq >> 24));
+            }
+        } else {
+            const int64_t i_end = min(q_end * 4, n_pixels);
+            for (int64_t i = q_begin * 4 + tid; i < i_end; i += kHistThreads) hist_one(s, p_img[i], g_img[i]);
+        }
+        hist_flush(s, tid, g_hist + (int64_t)img * 2 * kBins, g_straddle + (int64_t)img * kNT * 2);
     }
 }
 
@@ -302,41 +379,47 @@ pr_scan_kernel(const uint32_t* __restrict__ g_hist, const uint32_t* __restrict__
 
 using namespace eds;
 
+static PerDevice g_hist_attr_once;
+static int hist_smem_opt_in(int) {
+    return smem_opt_in(g_hist_attr_once, pr_hist_kernel, (int)sizeof(HistSmem), "pr_hist");
+}
+
 extern "C" int eds_pr_hist_f32(const float* prob, const uint8_t* gt, int64_t n_pixels, int n_images,
                                uint32_t* hist, uint32_t* straddle, int splits, void* stream) {
     EDS_REQUIRE(prob && gt && hist && straddle, "pr_hist: null pointer");
     EDS_REQUIRE(n_pixels > 0 && n_images > 0, "pr_hist: empty input (n_pixels=%lld n_images=%d)",
                 (long long)n_pixels, n_images);
     EDS_REQUIRE(n_images <= 65535, "pr_hist: n_images %d > 65535", n_images);
+    EDS_REQUIRE(n_pixels < ((int64_t)1 << 33), "pr_hist: n_pixels %lld per image exceeds 2^33", (long long)n_pixels);
     if (int rc = ensure_thresholds()) return rc;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (splits <= 0) {
-        // enough CTAs for >= 2 waves when several images are batched, one wave for one image
-        splits = ceil_div(2 * sms, n_images);
-        if (splits > sms) splits = sms;
-        if (n_images == 1) splits = sms;
-    }
     const int64_t min_quads = 4096;  // do not split below 16 Ki pixels per CTA
     const int64_t n_quads = (n_pixels + 3) / 4;
-    if ((int64_t)splits * min_quads > n_quads) splits = (int)((n_quads + min_quads - 1) / min_quads);
-    if (splits < 1) splits = 1;
-    const int vec_ok = (n_pixels % 4 == 0) && (((uintptr_t)prob & 15) == 0) && (((uintptr_t)gt & 3) == 0);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(pr_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(HistSmem));
-        if (e != cudaSuccess) {
-            set_error("pr_hist: cannot opt in to %zu B shared memory: %s", sizeof(HistSmem),
-                      cudaGetErrorString(e));
-            return EDS_ERR_CUDA;
-        }
-        attr_set = true;
+    int grid;
+    if (splits > 0) {                // caller-fixed CTAs per image
+        if ((int64_t)splits * min_quads > n_quads) splits = (int)((n_quads + min_quads - 1) / min_quads);
+        grid = splits * n_images;
+    } else {                         // one persistent wave over the linear range of all images
+        const int64_t total = n_quads * n_images;
+        grid = (int)(total / min_quads < sms ? (total + min_quads - 1) / min_quads : sms);
+        if (grid < 1) grid = 1;
     }
-    dim3 grid(splits, n_images);
-    pr_hist_kernel<<<grid, kHistThreads, sizeof(HistSmem), as_stream(stream)>>>(prob, gt, n_pixels, hist,
-                                                                             straddle, vec_ok);
+    // the count field of a shared-memory counter is 26 bits: bound a CTA's share of one image
+    const int64_t max_quads = ((int64_t)1 << 24) - 1;
+    if (splits > 0) {
+        if ((n_quads + splits - 1) / splits > max_quads) {
+            splits = (int)((n_quads + max_quads - 1) / max_quads);
+            grid = splits * n_images;
+        }
+    } else if ((n_quads * n_images + grid - 1) / grid > max_quads) {
+        grid = (int)((n_quads * n_images + max_quads - 1) / max_quads);
+    }
+    const int vec_ok = (n_pixels % 4 == 0) && (((uintptr_t)prob & 15) == 0) && (((uintptr_t)gt & 3) == 0);
+    if (int rc = hist_smem_opt_in(dev)) return rc;
+    pr_hist_kernel<<<grid, kHistThreads, sizeof(HistSmem), as_stream(stream)>>>(prob, gt, n_pixels, n_images, hist,
+                                                                             straddle, vec_ok, splits > 0 ? splits : 0);
     return check_launch("pr_hist_kernel");
 }
 

@@ -148,16 +148,8 @@ int stem_conv_mma_launch(const float* x, int B, int H, int W, int V, const int* 
     StemViews views;
     for (int v = 0; v < V; ++v)
         for (int q = 0; q < 6; ++q) views.m[v][q] = maps[v * 6 + q];
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(stem_conv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)kSmSmemBytes);
-        if (e != cudaSuccess) {
-            set_error("stem_conv_mma: shared-memory opt-in failed: %s", cudaGetErrorString(e));
-            return EDS_ERR_CUDA;
-        }
-        attr_set = true;
-    }
+    static PerDevice once;
+    if (int rc = smem_opt_in(once, stem_conv_mma_kernel, (int)kSmSmemBytes, "stem_conv_mma")) return rc;
     dim3 grid(ceil_div(W / 2, kSmTileW), ceil_div(H / 2, kSmTileH), B * V);
     stem_conv_mma_kernel<<<grid, 256, kSmSmemBytes, stream>>>(x, B, H, W, views, (const __nv_bfloat16*)w_packed, bias,
                                                             (__nv_bfloat16*)y);

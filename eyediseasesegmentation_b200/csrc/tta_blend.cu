@@ -358,15 +358,8 @@ extern "C" int eds_tta_merge(const float* logits, int V, int B, int S, const int
         // 512 threads x 2 rows measured best on B200 (50.0 us for 48 maps of 1024^2; 256 x 4 rows: 53.2 us;
         // 3 CTAs/SM at 80 registers spills: 59.4 us)
         auto kern = tta_merge64_kernel<2, 2>;
-        static bool opted = false;
-        if (!opted) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (e != cudaSuccess) {
-                set_error("tta_merge: shared-memory opt-in failed: %s", cudaGetErrorString(e));
-                return EDS_ERR_CUDA;
-            }
-            opted = true;
-        }
+        static PerDevice once;
+        if (int rc = smem_opt_in(once, kern, smem, "tta_merge")) return rc;
         dim3 grid(S / kMergeTile, S / kMergeTile, B);
         kern<<<grid, 512, smem, as_stream(stream)>>>(logits, V, B, S, maps, apply_sigmoid, prob);
         return check_launch("tta_merge64_kernel");

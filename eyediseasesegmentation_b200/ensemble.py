@@ -46,7 +46,7 @@ def get_best_model(path):
     """ensemble.py:39-62: ``path/config.json`` names the architecture, ``path/checkpoints/best.pth`` holds the
     weights; the model comes back in eval mode on the GPU, wrapped for D4 TTA with mean merging."""
     path = Path(path)
-    checkpoint = torch.load(path / "checkpoints/best.pth", map_location="cpu")
+    checkpoint = drv.load_checkpoint(path / "checkpoints/best.pth")
     with open(path / "config.json", "r") as j:
         config = json.load(j)
     if hasattr(smp, config["model_name"]):

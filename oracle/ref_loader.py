@@ -133,6 +133,29 @@ def load():
     return types.SimpleNamespace(**_loaded)
 
 
+def load_pad_img():
+    """The reference's vessel padding script (src/data/augment_vessel/pad_img.py).  It imports scikit-image,
+    which is not installed: ``skimage.io.imread(path, as_gray=True)`` is stubbed by a PIL read that returns
+    what scikit-image returns for the single-channel 8-bit label files of DRIVE / CHASEDB1 (the 2-D uint8
+    array, unchanged; as_gray only converts multi-channel images)."""
+    if "refdata.pad_img" in sys.modules:
+        return sys.modules["refdata.pad_img"]
+    import numpy as np
+    from PIL import Image
+
+    def imread(path, as_gray=False):
+        im = Image.open(path)
+        if as_gray and im.mode not in ("L", "P", "1", "I;16"):
+            raise NotImplementedError("the skimage stub only covers single-channel label files")
+        return np.asarray(im.convert("L")) if as_gray else np.asarray(im)
+
+    io = _module("skimage.io", imread=imread)
+    tr = _module("skimage.transform")
+    _module("skimage", io=io, transform=tr)
+    _module("refdata")
+    return _load("refdata", "pad_img", os.path.join(REFERENCE_ROOT, "src", "data", "augment_vessel", "pad_img.py"))
+
+
 def get_preprocessing_fn(dataset_name, grayscale=False):
     """archs/__init__.py cannot be imported (it imports every architecture); its
     get_preprocessing_fn (lines 61-99) is executed from source text instead."""

@@ -37,7 +37,22 @@ def reference_module(ref, name, cfg):
     raise KeyError(name)
 
 
+def pad_fixture_only():
+    import tempfile
+    refpad = ref_loader.load_pad_img()
+    with tempfile.TemporaryDirectory() as tmp:
+        img_in, lab_in, size = helpers.make_pad_case(tmp, seed=0)
+        refpad.pad(str(img_in), os.path.join(tmp, "o_img"), desired_size=size)
+        refpad.pad(str(lab_in), os.path.join(tmp, "o_lab"), desired_size=size, is_mask=True)
+        arrays = {"img/" + k: v for k, v in helpers.read_pad_outputs(os.path.join(tmp, "o_img")).items()}
+        arrays.update({"lab/" + k: v for k, v in helpers.read_pad_outputs(os.path.join(tmp, "o_lab")).items()})
+    np.savez_compressed(os.path.join(HERE, "pad_img.npz"), **arrays)
+    print("pad_img.npz written:", sorted(arrays))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "pad":     # only the fixture added in round 2
+        return pad_fixture_only()
     ref = ref_loader.load()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
 
@@ -93,6 +108,8 @@ def main():
         stat = {"lesion": helpers.read_stat_csvs(os.path.join(tmp, "out", "IDRiD", "result_assessment", "EX", "exp")),
                 "vessel": helpers.read_stat_csvs(os.path.join(tmp, "out", "DRIVE", "result_assessment", "vexp"))}
     json.dump(stat, open(os.path.join(HERE, "stat_result.json"), "w"), indent=1)
+    # 6. vessel padding: the reference's own pad_img.pad, file to file, on tiny seeded images / labels
+    pad_fixture_only()
     print("golden fixtures written to", HERE)
 
 

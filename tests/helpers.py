@@ -167,3 +167,28 @@ def assert_stat_csvs_equal(got, want):
                 assert abs(float(got[name][key]) - float(val)) <= 1e-12 * max(1.0, abs(float(val))), (name, key)
             else:
                 assert got[name][key] == val, (name, key, got[name][key], val)
+
+
+def make_pad_case(root, seed=0):
+    """Tiny unpadded vessel-style files for pad_img.pad: RGB images as PNG and single-channel label PNGs with grey
+    levels on both sides of the 127 threshold; odd and even deltas (DRIVE 584x565 -> 608 has an odd width delta)."""
+    import numpy as np
+    from pathlib import Path
+    from PIL import Image
+    rng = np.random.default_rng(seed)
+    root = Path(root)
+    (root / "images").mkdir(parents=True, exist_ok=True)
+    (root / "labels").mkdir(parents=True, exist_ok=True)
+    shapes = {"a.png": (30, 27), "b.png": (29, 32), "c.png": (32, 32)}
+    for name, (h, w) in shapes.items():
+        Image.fromarray(rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)).save(root / "images" / name)
+        levels = np.array([0, 1, 126, 127, 128, 200, 255], dtype=np.uint8)
+        Image.fromarray(levels[rng.integers(0, len(levels), size=(h, w))], "L").save(root / "labels" / name)
+    return root / "images", root / "labels", 32
+
+
+def read_pad_outputs(directory):
+    """{file name: array as cv2 reads it back (BGR for images, 2-D for labels)} of a pad() output folder."""
+    import cv2
+    import os
+    return {f: cv2.imread(os.path.join(directory, f), cv2.IMREAD_UNCHANGED) for f in sorted(os.listdir(directory))}

@@ -273,3 +273,39 @@ def test_callback_pr_auc_readout_matches_sklearn():
         assert abs(got - scoring.callback_pr_auc([gt], [key.astype(np.float64)])) < 1e-12
         assert abs(got - scoring.callback_pr_auc([gt[:1000], gt[1000:]], [pred[:1000], pred[1000:]])) < 1e-4
     assert np.isnan(pr_auc_from_hist(np.ones(_lib.PR_BINS, dtype=np.int64), np.zeros(_lib.PR_BINS, dtype=np.int64)))
+
+
+def test_cached_predictions_spill_beyond_the_byte_budget():
+    """The three-consumer cache keeps at most EDS_CACHE_BYTES of maps in RAM and spills the rest to memmap files;
+    replayed items are identical and keep their device-computed scores."""
+    from eyediseasesegmentation_b200._driver import CachedPredictions
+    from eyediseasesegmentation_b200.aucpr import ScoredArray, ImageScores
+    calls = []
+
+    def produce():
+        calls.append(1)
+        for i in range(4):
+            s = ImageScores(0.1 * i, 0.5, np.zeros(19, dtype=np.int64), np.zeros(19, dtype=np.int64), 1, 2)
+            yield ScoredArray(np.full((6, 7), i, np.float32), s), np.full((6, 7), i % 2, np.uint8), f"img{i}"
+
+    cache = CachedPredictions(produce, budget_bytes=6 * 7 * 5 + 10)          # room for exactly one image
+    first, second, third = list(cache), list(cache), list(cache())
+    assert len(calls) == 1
+    for a, b, c in zip(first, second, third):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2] == c[2]
+        assert b[0]._eds_scores.ap == a[0]._eds_scores.ap and b[0].dtype == np.float32 and b[1].dtype == np.uint8
+    assert cache._spill_dir is not None and len(os.listdir(cache._spill_dir.name)) == 6
+
+
+def test_load_checkpoint_accepts_catalyst_style_dicts(tmp_path):
+    """Reference checkpoints are catalyst dicts (optimizer state, metric dicts with numpy scalars ...): the
+    restricted loader of torch >= 2.6 refuses some of them, the driver then loads them the reference's way."""
+    import collections
+    import torch
+    from eyediseasesegmentation_b200._driver import load_checkpoint
+    ckpt = {"model_state_dict": {"w": torch.arange(4.0)}, "epoch": 3,
+            "valid_metrics": collections.defaultdict(float, {"auc_pr": np.float64(0.5)}),
+            "checkpoint_data": {"best": np.array([1, 2, 3])}}
+    torch.save(ckpt, tmp_path / "best.pth")
+    got = load_checkpoint(tmp_path / "best.pth")
+    assert torch.equal(got["model_state_dict"]["w"], torch.arange(4.0)) and got["epoch"] == 3

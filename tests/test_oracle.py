@@ -195,3 +195,57 @@ def test_stat_result_oracle_matches_reference_csvs(tmp_path):
         ref.stat_result.export_result("EX/exp", lesion_cfg)
         helpers.assert_stat_csvs_equal(
             helpers.read_stat_csvs(tmp_path / "out" / "IDRiD" / "result_assessment" / "EX" / "exp"), golden["lesion"])
+
+
+# ------------------------------------------------------------------ vessel padding (pad_img.py:8-38)
+def _pad_golden():
+    return np.load(os.path.join(GOLDEN, "pad_img.npz"))
+
+
+def test_pad_img_oracle_and_product_match_reference_golden(tmp_path):
+    """The reference's own pad() wrote tests/golden/pad_img.npz (file to file).  Both the oracle restatement (array
+    level, same cv2 calls) and the product mirror (file to file, same signature) must reproduce it byte for byte:
+    centre pad with top = dh // 2 / left = dw // 2 (odd deltas put the extra line at the bottom / right) and
+    the `> 127 -> 255` label threshold."""
+    import cv2
+    from oracle import pad as opad
+    from eyediseasesegmentation_b200 import pad_img
+    golden = _pad_golden()
+    img_in, lab_in, size = helpers.make_pad_case(tmp_path, seed=0)
+    pad_img.pad(str(img_in), str(tmp_path / "o_img"), desired_size=size)
+    pad_img.pad(str(lab_in), str(tmp_path / "o_lab"), desired_size=size, is_mask=True)
+    got = {"img/" + k: v for k, v in helpers.read_pad_outputs(tmp_path / "o_img").items()}
+    got.update({"lab/" + k: v for k, v in helpers.read_pad_outputs(tmp_path / "o_lab").items()})
+    assert sorted(got) == sorted(golden.files)
+    for key in golden.files:
+        assert got[key].shape == golden[key].shape and np.array_equal(got[key], golden[key]), key
+        folder, name = key.split("/")
+        src = cv2.imread(str((img_in if folder == "img" else lab_in) / name), cv2.IMREAD_UNCHANGED)
+        assert np.array_equal(opad.pad_array(src, size, folder == "lab"), golden[key]), key
+        assert np.array_equal(pad_img.pad_array(src, size, folder == "lab"), golden[key]), key
+
+
+def test_pad_img_vessel_geometries():
+    """DRIVE 584x565 -> 608^2 pads 12/12 rows and 21/22 columns; CHASEDB1 960x999 -> 1024^2 pads
+    32/32 and 12/13."""
+    from eyediseasesegmentation_b200 import pad_img
+    assert pad_img.pad_geometry((584, 565), 608) == (12, 12, 21, 22)
+    assert pad_img.pad_geometry((960, 999), 1024) == (32, 32, 12, 13)
+    with pytest.raises(ValueError):
+        pad_img.pad_geometry((700, 565), 608)
+    already = np.arange(16, dtype=np.uint8).reshape(4, 4)
+    assert np.array_equal(pad_img.pad_array(already, 4), already)
+
+
+@pytest.mark.skipif(not HAS_REF, reason="reference tree not present")
+def test_pad_img_matches_reference_function(tmp_path):
+    from eyediseasesegmentation_b200 import pad_img
+    refpad = ref_loader.load_pad_img()
+    img_in, lab_in, size = helpers.make_pad_case(tmp_path, seed=3)
+    for folder, is_mask in ((img_in, False), (lab_in, True)):
+        refpad.pad(str(folder), str(tmp_path / "ref"), desired_size=size + 8, is_mask=is_mask)
+        pad_img.pad(str(folder), str(tmp_path / "got"), desired_size=size + 8, is_mask=is_mask)
+        want, got = helpers.read_pad_outputs(tmp_path / "ref"), helpers.read_pad_outputs(tmp_path / "got")
+        assert sorted(want) == sorted(got)
+        for k in want:
+            assert np.array_equal(want[k], got[k]), (k, is_mask)
