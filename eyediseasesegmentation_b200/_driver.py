@@ -57,7 +57,26 @@ def device() -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
+def ensure_distributed() -> None:
+    """Under torchrun (WORLD_SIZE > 1 in the environment) make this process one rank of the NCCL group on its
+    own GPU, unless the caller already did: the reference's ``pipeline.py`` knows nothing about ranks, so the
+    drop-in drivers join the group themselves (``torchrun --nproc-per-node N pipeline.py ...`` just works)."""
+    import torch.distributed as dist
+    if int(os.environ.get("WORLD_SIZE", "1")) <= 1 or not dist.is_available():
+        return
+    if not torch.cuda.is_available():
+        raise RuntimeError("the B200 inference drivers need a CUDA device; there is no CPU fallback")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if dist.is_initialized():
+        if dist.get_backend() == "nccl":
+            torch.cuda.set_device(local)
+        return
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+
 def build_model(config, logdir, args):
+    ensure_distributed()
     """Model dispatch + checkpoint load of tta.py:61-72,86-88 / 155-171."""
     if hasattr(smp, config["model_name"]):
         model = get_model(config["model_params"], config["model_name"])
@@ -215,12 +234,165 @@ def tiled_probability_map(model, transforms, image_dev: torch.Tensor, S: int, me
         for j, (x1, _, y1, _) in enumerate(group):
             K.preprocess_tile(image_dev, int(x1), int(y1), S, mean, std, out=x[j])
         prob = predict_probs(model, transforms, x)
-        if len(group) <= 32:
+        if len(group) <= 32 and W % 4 == 0:           # one launch, 128-bit stores (rows of preds 16-byte aligned)
             K.paste_tiles_x2(prob.contiguous(), preds, [(int(x1), int(y1)) for (x1, _, y1, _) in group])
         else:
             for j, (x1, _, y1, _) in enumerate(group):
                 K.resize_paste(prob[j], preds, (0, 0, S, S), (int(x1), int(y1)), (2 * S, 2 * S))
     return preds
+
+
+# ------------------------------------------------------------------ (image, tile) partition
+class TilePlan:
+    """Static tile geometry of one image shape: paste origins in make_grid order and the rectangles each
+    tile owns under last-writer-wins."""
+
+    def __init__(self, H: int, W: int, S: int):
+        from . import partition
+        self.slices = make_grid((H, W), window=2 * S, min_overlap=32)
+        for (x1, x2, y1, y2) in self.slices:
+            if x1 < 0 or y1 < 0 or x2 - x1 != 2 * S or y2 - y1 != 2 * S:
+                raise ValueError(f"could not broadcast input array from shape ({2 * S},{2 * S}) into shape "
+                                 f"({max(x2 - max(x1, 0), 0)},{max(y2 - max(y1, 0), 0)}): window larger than the image")
+        self.origins = [(int(x1), int(y1)) for (x1, _, y1, _) in self.slices]       # (row, column) of each window
+        self.cells = partition.owned_cells([(x1, x2, y1, y2) for (x1, x2, y1, y2) in self.slices], (H, W))
+        self.n = len(self.origins)
+
+
+_PLANS = {}
+
+
+def tile_plan(H: int, W: int, S: int) -> TilePlan:
+    key = (int(H), int(W), int(S))
+    if key not in _PLANS:
+        _PLANS[key] = TilePlan(*key)
+    return _PLANS[key]
+
+
+def partitioned_group(model, transforms, images, gts, S: int, mean, std, hist: torch.Tensor, strad: torch.Tensor,
+                      first_row: int, rank: int, world_size: int, tiles_per_batch: int = 6, unit_offset: int = 0):
+    """This rank's share of the sliding-window inference of a GROUP of images (every rank holds the same
+    decoded images ``[H,W,3]`` u8 and masks ``[H,Wp]`` u8 on its device, Wp = W rounded up to 4).
+
+    Units ``(image, tile)`` are dealt round-robin (unit number = unit_offset + running index); the rank runs its
+    tiles in batches, writes only the pixels they own into one zero-initialised canvas ``[H,Wp]`` per image and
+    adds the histogram of those pixels to ``hist[first_row + k]`` / ``strad[first_row + k]``.  Returns
+    (canvases, next unit_offset).  Summing canvases / histograms over ranks gives the single-process results."""
+    from . import partition
+    dev = images[0].device
+    plans = [tile_plan(int(im.shape[0]), int(im.shape[1]), S) for im in images]
+    units = [(k, t) for k, p in enumerate(plans) for t in range(p.n)]
+    mine = [u for j, u in enumerate(units) if (unit_offset + j) % world_size == rank]
+    canvases = [torch.zeros((int(im.shape[0]), int(g.shape[1])), dtype=torch.float32, device=dev)
+                for im, g in zip(images, gts)]
+    for batch in partition.batches(mine, tiles_per_batch):
+        x = torch.empty((len(batch), 3, S, S), dtype=torch.float32, device=dev)
+        for j, (k, t) in enumerate(batch):
+            y0, x0 = plans[k].origins[t]
+            K.preprocess_tile(images[k], y0, x0, S, mean, std, out=x[j])
+        prob = predict_probs(model, transforms, x).contiguous()
+        for j, (k, t) in enumerate(batch):
+            K.paste_tiles_owned_x2(prob[j:j + 1], t, canvases[k], plans[k].origins)
+    for k, p in enumerate(plans):
+        rects = [r for (kk, t) in mine if kk == k for r in p.cells[t]]
+        if rects:
+            K.pr_hist_rects(canvases[k], gts[k], rects, hist[first_row + k], strad[first_row + k])
+    return canvases, unit_offset + len(units)
+
+
+def partitioned_producer(model, transforms, keys, load, S: int, mean, std, tiles_per_batch: int = 6):
+    """``produce()`` of the sliding-window drivers under torchrun (world size > 1).
+
+    ``keys`` lists the images (same order on every rank), ``load(key) -> (image [H,W,3] u8, gt [H,W] u8)`` decodes
+    one on the host.  Images are taken in groups of ``world_size``: rank r decodes the r-th image of the group
+    (on a background thread, one group ahead) and broadcasts it; every rank then runs its ``(image, tile)``
+    units of the group (``partitioned_group``); the canvases are summed onto the rank that decoded the image,
+    which keeps the full-resolution map for the mask writer.  After the last group ONE all-reduce sums the
+    per-image integer histograms, every rank scans them, and the generator yields, for every image, the global
+    scores (``replicated=True``) with the map on its writer rank and an empty array elsewhere."""
+    import torch.distributed as dist
+    from . import partition
+    from . import _lib
+    from .aucpr import ImageScores
+
+    def produce():
+        rank, ws = partition.world()
+        dev = device()
+        n = len(keys)
+        hist = torch.zeros((max(n, 1), 2, _lib.PR_BINS), dtype=torch.int32, device=dev)
+        strad = torch.zeros((max(n, 1), _lib.PR_NTHRESH, 2), dtype=torch.int32, device=dev)
+        kept = {}
+        unit_offset = 0
+        starts = list(range(0, n, ws))
+        mine = prefetched([(lambda g=g: load(keys[g + rank]) if g + rank < n else None) for g in starts])
+        for g, loaded in zip(starts, mine):
+            group = list(range(g, min(g + ws, n)))
+            shapes = [None] * ws
+            dist.all_gather_object(shapes, None if loaded is None else tuple(loaded[0].shape[:2]))
+            images, gts = [], []
+            for r, i in enumerate(group):
+                H, W = shapes[r]
+                img = torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
+                gt = torch.zeros((H, (W + 3) // 4 * 4), dtype=torch.uint8, device=dev)
+                if r == rank:
+                    img.copy_(torch.from_numpy(np.ascontiguousarray(loaded[0])))
+                    gt[:, :W].copy_(torch.from_numpy(np.ascontiguousarray(loaded[1])))
+                dist.broadcast(img, src=r)
+                dist.broadcast(gt, src=r)
+                images.append(img)
+                gts.append(gt)
+            canvases, unit_offset = partitioned_group(model, transforms, images, gts, S, mean, std, hist, strad, g,
+                                                      rank, ws, tiles_per_batch, unit_offset)
+            for r, i in enumerate(group):
+                dist.reduce(canvases[r], dst=r, op=dist.ReduceOp.SUM)       # pieces -> the rank that wrote image i
+                if r == rank:
+                    W = shapes[r][1]
+                    kept[i] = (canvases[r][:, :W].cpu().numpy(), loaded[1])
+        partition.allreduce_sum_(hist, strad)                                # the path's one data collective
+        if n:
+            ap, roc, counts, totals = [t.cpu().numpy() for t in K.pr_scan(hist[:n], strad[:n])]
+        for i in range(n):
+            scores = ImageScores(float(ap[i]), float(roc[i]), counts[i, :, 0].copy(), counts[i, :, 1].copy(),
+                                 int(totals[i, 0]), int(totals[i, 1]), replicated=True)
+            name = getattr(keys[i], "name", str(keys[i]))
+            if i in kept:
+                yield ScoredArray(kept[i][0], scores), kept[i][1], name
+            else:
+                yield ScoredArray(np.zeros((0, 0), dtype=np.float32), scores), None, name
+
+    return produce
+
+
+def pad_width4(t: torch.Tensor) -> torch.Tensor:
+    """[H,W] -> [H,Wp] with Wp = W rounded up to a multiple of 4 (zero columns): rows of the canvases and masks of
+    the partitioned path start 16-byte aligned for the 128-bit paste stores."""
+    H, W = t.shape
+    if W % 4 == 0:
+        return t
+    out = torch.zeros((H, (W + 3) // 4 * 4), dtype=t.dtype, device=t.device)
+    out[:, :W] = t
+    return out
+
+
+def prefetched(thunks, depth: int = 2):
+    """Run ``thunk()`` for every element of ``thunks`` on ONE background thread, ``depth`` ahead of the consumer,
+    and yield the results in order: JPEG decode (PIL releases the GIL) and pinned staging of image k+1 hide
+    behind the GPU work of image k (the reference decodes inside the loop, tta.py:196-203)."""
+    import collections
+    from concurrent.futures import ThreadPoolExecutor
+    it = iter(thunks)
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        q = collections.deque()
+        for _ in range(max(1, depth)):
+            t = next(it, None)
+            if t is not None:
+                q.append(pool.submit(t))
+        while q:
+            fut = q.popleft()
+            t = next(it, None)
+            if t is not None:
+                q.append(pool.submit(t))
+            yield fut.result()
 
 
 _PINNED = {}

@@ -39,11 +39,13 @@ PROTOTYPES = {
     "eds_device_ok": [],
     "eds_init": [],
     "eds_pr_hist_f32": [_vp, _vp, _i64, _i, _vp, _vp, _i, _vp],
+    "eds_pr_hist_rects_f32": [_vp, _vp, _i, _i, _i, C.POINTER(_i), _vp, _vp, _vp],
     "eds_pr_scan": [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp],
     "eds_confusion_u8": [_vp, _vp, _i64, _i, _i, _i, _vp, _vp],
     "eds_tta_merge": [_vp, _i, _i, _i, C.POINTER(_i), _i, _vp, _vp],
     "eds_resize_paste_f32": [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "eds_paste_tiles_x2_f32": [_vp, _i, _i, C.POINTER(_i), C.POINTER(_i), _vp, _i, _i, _vp],
+    "eds_paste_tiles_owned_x2_f32": [_vp, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), _vp, _i, _i, _vp],
     "eds_preprocess_tile_u8": [_vp, _i, _i, _i, _i, _i, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp, _vp],
     "eds_stem_conv7x7s2": [_vp, _i, _i, _i, _i, C.POINTER(_i), _vp, _vp, _vp, _i, _vp],
     "eds_stem_pack_weights": [_vp, _vp, _vp],

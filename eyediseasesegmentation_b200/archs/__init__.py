@@ -180,7 +180,7 @@ class B200SegModel(nn.Module):
 
     def _forward_tta_on_device(self, x, aug, deaug, apply_sigmoid):
         from .. import kernels as K
-        use_graph = (_graphs_enabled() and K.CONV_TRACE is None and not self.engine(x.device).keep_features)
+        use_graph = (_graphs_enabled() and K.CONV_TRACE is None and K.KERNEL_TRACE is None and not self.engine(x.device).keep_features)
         if not use_graph:
             return self._forward_tta_eager(x, aug, deaug, apply_sigmoid)
         key = (tuple(x.shape), str(x.device), self.precision, tuple(map(tuple, aug)), bool(apply_sigmoid))

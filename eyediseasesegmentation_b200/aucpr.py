@@ -36,10 +36,13 @@ thresh_list = list(_lib.PR_THRESHOLDS)
 
 class ImageScores:
     """Per-image result of the histogram + scan kernels."""
-    __slots__ = ("ap", "roc", "tp", "pp", "n_pos", "n_neg")
+    __slots__ = ("ap", "roc", "tp", "pp", "n_pos", "n_neg", "replicated")
 
-    def __init__(self, ap, roc, tp, pp, n_pos, n_neg):
+    def __init__(self, ap, roc, tp, pp, n_pos, n_neg, replicated=False):
         self.ap, self.roc, self.tp, self.pp, self.n_pos, self.n_neg = ap, roc, tp, pp, n_pos, n_neg
+        #: True when every rank already holds this image's GLOBAL scores (tile-partitioned path: the integer
+        #: histograms were all-reduced before the scan), so the entry points must not sum over ranks again
+        self.replicated = replicated
 
 
 class ScoredArray(np.ndarray):
@@ -80,12 +83,12 @@ def _scores(pred, gt) -> ImageScores:
     return score_device(torch.from_numpy(pred).to(dev, non_blocking=True), torch.from_numpy(gt).to(dev, non_blocking=True))
 
 
-def _dist_sum(values, dtype):
+def _dist_sum(values, dtype, replicated=False):
     """Sum over ranks when torch.distributed is initialised (one process per GPU, images
     sharded by the drivers).  This is the path's single collective: a few integers / two
     float64 -- NCCL over NVLink on the GPU box, gloo in the CPU tests."""
     import torch.distributed as dist
-    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+    if replicated or not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
         return values
     on_gpu = dist.get_backend() == "nccl"
     t = torch.tensor(values, dtype=dtype, device=torch.device("cuda", torch.cuda.current_device()) if on_gpu else "cpu")
@@ -93,18 +96,27 @@ def _dist_sum(values, dtype):
     return t.cpu().tolist()
 
 
+def _all_replicated(flags) -> bool:
+    """Every item carried global scores (tile-partitioned drivers); a mix would double count."""
+    if any(flags) and not all(flags):
+        raise ValueError("items with replicated (already all-reduced) and rank-local scores cannot be mixed")
+    return bool(flags) and all(flags)
+
+
 def get_auc(generator: Iterable, config):
     sum_pav = 0
     i = 0
+    replicated = []
     for pred_mask, gt_mask, _ in generator:
         s = _scores(pred_mask, gt_mask)
+        replicated.append(s.replicated)
         if s.n_pos == 0:
             continue
         pav = s.ap
         print("PAV", pav)
         sum_pav += pav
         i += 1
-    sum_pav, i = _dist_sum([float(sum_pav), float(i)], torch.float64)
+    sum_pav, i = _dist_sum([float(sum_pav), float(i)], torch.float64, _all_replicated(replicated))
     mpav = sum_pav / i   # ZeroDivisionError when no image has positives, as in the reference
     return mpav
 
@@ -113,8 +125,10 @@ def get_aucroc(generator: Iterable, config):
     sum_pav = 0
     i = 0
     one_class = 0
+    replicated = []
     for pred_mask, gt_mask, _ in generator:
         s = _scores(pred_mask, gt_mask)
+        replicated.append(s.replicated)
         if s.n_pos == 0:
             continue
         if s.n_neg == 0:
@@ -122,7 +136,8 @@ def get_aucroc(generator: Iterable, config):
             continue
         sum_pav += s.roc
         i += 1
-    sum_pav, i, one_class = _dist_sum([float(sum_pav), float(i), float(one_class)], torch.float64)
+    sum_pav, i, one_class = _dist_sum([float(sum_pav), float(i), float(one_class)], torch.float64,
+                                      _all_replicated(replicated))
     if one_class:
         raise ValueError("Only one class present in y_true. ROC AUC score is not defined in that case.")
     return sum_pav / i
@@ -153,14 +168,17 @@ def _pooled_counts(generator):
     ap = 0
     an = 0
     n_images = 0
+    replicated = []
     for pred_mask, gt_mask, _ in generator:
         s = _scores(pred_mask, gt_mask)
+        replicated.append(s.replicated)
         tp += s.tp.astype(np.int64)
         pp += s.pp.astype(np.int64)
         ap += s.n_pos
         an += s.n_neg
         n_images += 1
-    flat = _dist_sum(tp.tolist() + pp.tolist() + [int(ap), int(an), n_images], torch.int64)
+    flat = _dist_sum(tp.tolist() + pp.tolist() + [int(ap), int(an), n_images], torch.int64,
+                     _all_replicated(replicated))
     n = len(thresh_list)
     tp, pp = np.array(flat[:n], dtype=np.int64), np.array(flat[n:2 * n], dtype=np.int64)
     ap, an, n_images = flat[2 * n], flat[2 * n + 1], flat[2 * n + 2]

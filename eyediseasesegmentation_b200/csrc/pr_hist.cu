@@ -149,7 +149,7 @@ __device__ __forceinline__ void hist_flush(HistSmem* s, int tid, uint32_t* __res
 }
 
 constexpr int kQuadUnroll = 4;    // float4 + uchar4 pairs in flight per thread (80 KB per SM)
-constexpr int kPxPerThread = 4 * kQuadUnroll;
+constexpr int kAggLanes = 8;      // lanes sharing one counter from which the warp-aggregated path pays
 
 // Persistent grid of <= one CTA per SM.  The test set is ONE linear range of 4-pixel quads (image-major);
 // CTA c takes the contiguous share [c*T/G, (c+1)*T/G) and, when its share crosses an image boundary,
@@ -210,44 +210,64 @@ pr_hist_kernel(const float* __restrict__ prob, const uint8_t* __restrict__ gt, i
                     off[u][2] = counter_offset(p[u].z, nz, 2);
                     off[u][3] = counter_offset(p[u].w, nz, 3);
                 }
-                // Flat regions (saturated background): when the first quad of every lane sits in one
-                // counter, look at the other twelve pixels too; 512 pixels of one bin are ONE atomic
-                // instead of 512 serialised same-address ones.
-                const uint32_t lead = __shfl_sync(0xffffffffu, off[0][0], 0);
-                uint32_t diff = (off[0][0] ^ lead) | (off[0][1] ^ lead) | (off[0][2] ^ lead) | (off[0][3] ^ lead);
-                bool flat = false;
-                if (__all_sync(0xffffffffu, diff == 0)) {
-#pragma unroll
-                    for (int u = 1; u < kQuadUnroll; ++u)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) diff |= off[u][j] ^ lead;
-                    flat = __all_sync(0xffffffffu, diff == 0);
+                // Crowded bins (saturated background: p < 2^-24 or p == 1 over large areas; flat regions).
+                // Same-address shared-memory atomics serialise lane by lane (measured: 1.4 TB/s on a flat map),
+                // so when >= kAggLanes lanes of the warp open this step in ONE counter -- candidates: the lowest
+                // and the highest offset in the warp, which is where saturation lands -- every pixel of that
+                // counter is tallied in registers and added by ONE atomic per warp; the rest go one by one.
+                const uint32_t o00 = off[0][0];
+                uint32_t lead = __reduce_min_sync(0xffffffffu, o00);
+                int n_lead = __popc(__ballot_sync(0xffffffffu, o00 == lead));
+                if (n_lead < kAggLanes) {
+                    lead = __reduce_max_sync(0xffffffffu, o00);
+                    n_lead = __popc(__ballot_sync(0xffffffffu, o00 == lead));
                 }
-                uint32_t old[kQuadUnroll][4], tag = 0;
-                if (flat) {
-                    uint32_t o = 0;
-                    if ((tid & 31) == 0) o = atomicAdd(reinterpret_cast<uint32_t*>(hbase + lead), 32u * kPxPerThread);
-                    tag = __shfl_sync(0xffffffffu, o, 0);
-#pragma unroll
-                    for (int u = 0; u < kQuadUnroll; ++u)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) old[u][j] = tag;
-                } else {
+                uint32_t tag = 0, skip = 0xffffffffu;       // skip: counter already settled by the aggregated path
+                if (n_lead >= kAggLanes) {
+                    skip = lead;
+                    uint32_t cnt = 0;
 #pragma unroll
                     for (int u = 0; u < kQuadUnroll; ++u)
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            old[u][j] = atomicAdd(reinterpret_cast<uint32_t*>(hbase + off[u][j]), 1u);
-                            tag |= old[u][j];
+                            const bool is_lead = off[u][j] == lead;
+                            cnt += is_lead;
+                            if (!is_lead) tag |= atomicAdd(reinterpret_cast<uint32_t*>(hbase + off[u][j]), 1u);
                         }
+                    const uint32_t total = __reduce_add_sync(0xffffffffu, cnt);
+                    uint32_t old_lead = 0;
+                    if ((tid & 31) == 0) old_lead = atomicAdd(reinterpret_cast<uint32_t*>(hbase + lead), total);
+                    old_lead = __shfl_sync(0xffffffffu, old_lead, 0);
+                    if (old_lead & kTag) {                   // the crowded bin holds a threshold (0 and 1 do)
+                        const int k = (old_lead >> kTagShift) & 31;
+                        const int thr = s->thr_bits[k];
+                        uint32_t above = 0;
+#pragma unroll
+                        for (int u = 0; u < kQuadUnroll; ++u) {
+                            above += (off[u][0] == lead) & (__float_as_int(p[u].x) > thr);
+                            above += (off[u][1] == lead) & (__float_as_int(p[u].y) > thr);
+                            above += (off[u][2] == lead) & (__float_as_int(p[u].z) > thr);
+                            above += (off[u][3] == lead) & (__float_as_int(p[u].w) > thr);
+                        }
+                        above = __reduce_add_sync(0xffffffffu, above);
+                        if ((tid & 31) == 0 && above) atomicAdd(&s->straddle[k * 2 + ((lead >> 2) & 1)], above);
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < kQuadUnroll; ++u)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            tag |= atomicAdd(reinterpret_cast<uint32_t*>(hbase + off[u][j]), 1u);
                 }
                 if (__any_sync(0xffffffffu, tag & kTag)) {   // some pixel of this warp shares a bin with a threshold
 #pragma unroll
                     for (int u = 0; u < kQuadUnroll; ++u) {
-                        straddle_one(s, old[u][0], p[u].x, off[u][0]);
-                        straddle_one(s, old[u][1], p[u].y, off[u][1]);
-                        straddle_one(s, old[u][2], p[u].z, off[u][2]);
-                        straddle_one(s, old[u][3], p[u].w, off[u][3]);
+                        // the tag bits of a counter never change after hist_clear: a plain load answers
+                        // "tagged bin, and which threshold?" for the pixels the per-pixel path counted
+                        if (off[u][0] != skip) straddle_one(s, *reinterpret_cast<volatile uint32_t*>(hbase + off[u][0]), p[u].x, off[u][0]);
+                        if (off[u][1] != skip) straddle_one(s, *reinterpret_cast<volatile uint32_t*>(hbase + off[u][1]), p[u].y, off[u][1]);
+                        if (off[u][2] != skip) straddle_one(s, *reinterpret_cast<volatile uint32_t*>(hbase + off[u][2]), p[u].z, off[u][2]);
+                        if (off[u][3] != skip) straddle_one(s, *reinterpret_cast<volatile uint32_t*>(hbase + off[u][3]), p[u].w, off[u][3]);
                     }
                 }
             }
@@ -265,6 +285,37 @@ pr_hist_kernel(const float* __restrict__ prob, const uint8_t* __restrict__ gt, i
         }
         hist_flush(s, tid, g_hist + (int64_t)img * 2 * kBins, g_straddle + (int64_t)img * kNT * 2);
     }
+}
+
+// Histogram of a list of RECTANGLES of one image (row stride = image width): the pixels a rank OWNS under
+// the (image, tile) partition of SURVEY.md 8e -- a tile's window minus every later tile's window, which for
+// make_grid's layouts is a handful of rectangles whose origins follow the tile origins (not 16-byte aligned).
+// One warp per rectangle row, lanes along the row (coalesced 4-byte loads); same shared-memory histogram,
+// tags and flush as the streaming kernel, so the two agree bin for bin.
+constexpr int kMaxRects = 32;
+struct HistRects {
+    int y[kMaxRects], x[kMaxRects], h[kMaxRects], w[kMaxRects];
+    int n;
+};
+
+__global__ void __launch_bounds__(kHistThreads, 1)
+pr_hist_rects_kernel(const float* __restrict__ prob, const uint8_t* __restrict__ gt, int row_stride, HistRects r,
+                     uint32_t* __restrict__ g_hist, uint32_t* __restrict__ g_straddle) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    HistSmem* s = reinterpret_cast<HistSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    hist_clear(s, tid);
+    int total_rows = 0;
+    for (int k = 0; k < r.n; ++k) total_rows += r.h[k];
+    const int per = (total_rows + gridDim.x - 1) / gridDim.x;
+    const int row_begin = blockIdx.x * per, row_end = min(total_rows, row_begin + per);
+    for (int row = row_begin + warp; row < row_end; row += kHistThreads / 32) {
+        int k = 0, rr = row;
+        while (rr >= r.h[k]) { rr -= r.h[k]; ++k; }
+        const int64_t base = (int64_t)(r.y[k] + rr) * row_stride + r.x[k];
+        for (int c = lane; c < r.w[k]; c += 32) hist_one(s, __ldcs(prob + base + c), __ldcs(gt + base + c));
+    }
+    hist_flush(s, tid, g_hist, g_straddle);
 }
 
 // ---- scan ------------------------------------------------------------------
@@ -421,6 +472,41 @@ extern "C" int eds_pr_hist_f32(const float* prob, const uint8_t* gt, int64_t n_p
     pr_hist_kernel<<<grid, kHistThreads, sizeof(HistSmem), as_stream(stream)>>>(prob, gt, n_pixels, n_images, hist,
                                                                              straddle, vec_ok, splits > 0 ? splits : 0);
     return check_launch("pr_hist_kernel");
+}
+
+extern "C" int eds_pr_hist_rects_f32(const float* prob, const uint8_t* gt, int img_h, int img_w, int n_rects,
+                                     const int* rects_host, uint32_t* hist, uint32_t* straddle, void* stream) {
+    EDS_REQUIRE(prob && gt && hist && straddle && rects_host, "pr_hist_rects: null pointer");
+    EDS_REQUIRE(img_h > 0 && img_w > 0, "pr_hist_rects: bad image size %dx%d", img_h, img_w);
+    EDS_REQUIRE(n_rects >= 0 && n_rects <= kMaxRects, "pr_hist_rects: n_rects=%d (0..%d)", n_rects, kMaxRects);
+    if (int rc = ensure_thresholds()) return rc;
+    HistRects r;
+    memset(&r, 0, sizeof(r));
+    int64_t rows = 0, pixels = 0;
+    for (int k = 0; k < n_rects; ++k) {
+        const int y = rects_host[4 * k], x = rects_host[4 * k + 1], h = rects_host[4 * k + 2], w = rects_host[4 * k + 3];
+        EDS_REQUIRE(y >= 0 && x >= 0 && h >= 0 && w >= 0 && y + h <= img_h && x + w <= img_w,
+                    "pr_hist_rects: rectangle %d (y=%d x=%d h=%d w=%d) leaves the %dx%d image", k, y, x, h, w, img_h, img_w);
+        if (h == 0 || w == 0) continue;
+        r.y[r.n] = y; r.x[r.n] = x; r.h[r.n] = h; r.w[r.n] = w;
+        ++r.n;
+        rows += h;
+        pixels += (int64_t)h * w;
+    }
+    if (r.n == 0) return EDS_OK;                       // nothing owned: nothing to add
+    EDS_REQUIRE(pixels < ((int64_t)1 << 26), "pr_hist_rects: %lld pixels exceed the 2^26 counter field",
+                (long long)pixels);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int grid = (int)((pixels + (1 << 16) - 1) >> 16);   // >= 64 Ki pixels per CTA: the 188 KB clear + flush amortise
+    if (grid > sms) grid = sms;
+    if (grid > rows) grid = (int)rows;
+    if (grid < 1) grid = 1;
+    static PerDevice once;
+    if (int rc = smem_opt_in(once, pr_hist_rects_kernel, (int)sizeof(HistSmem), "pr_hist_rects")) return rc;
+    pr_hist_rects_kernel<<<grid, kHistThreads, sizeof(HistSmem), as_stream(stream)>>>(prob, gt, img_w, r, hist, straddle);
+    return check_launch("pr_hist_rects_kernel");
 }
 
 extern "C" int eds_pr_scan(const uint32_t* hist, const uint32_t* straddle, int n_images, double* ap,

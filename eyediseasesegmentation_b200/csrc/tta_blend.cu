@@ -240,55 +240,91 @@ struct PasteTiles {
     int n;
 };
 
+// One thread = 4 output columns that are 16-byte ALIGNED IN dst (tile origins are arbitrary, e.g. x = 1429) x 8 output
+// rows: 6 source rows x 3-4 source columns are read (round 1: 12 scalar loads and 8 scalar stores per 8 pixels,
+// issue-bound at 1.25 TB/s), the 32 results leave as eight 128-bit stores.  Blocks that a later tile covers
+// completely return before their first load (with make_grid's overlaps that is half of all blocks).
+// grid = (ceil((2S + 3) / 256), 2S / 32, tiles in src), block = (64, 4).
 __global__ void __launch_bounds__(256)
-paste_tiles_x2_kernel(const float* __restrict__ src, int S, PasteTiles tiles, float* __restrict__ dst, int dst_h,
-                      int dst_w) {
-    const int b = blockIdx.z;
-    const float* sp = src + (int64_t)b * S * S;
+paste_tiles_x2_kernel(const float* __restrict__ src, int S, PasteTiles tiles, int first_tile, float* __restrict__ dst,
+                      int dst_h, int dst_w) {
+    const int b = first_tile + blockIdx.z;              // index into the tile list; src holds tiles first_tile ..
+    const float* sp = src + (int64_t)blockIdx.z * S * S;
     const int ty0 = tiles.y[b], tx0 = tiles.x[b];
     const int out = 2 * S;
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    const int ox = blockIdx.x * kPasteBX + (tid & 63);
-    const int gx = tx0 + ox;
-    if (ox >= out || gx < 0 || gx >= dst_w) return;
-    // later tiles whose columns cover gx: only these can take a pixel of this thread away
+    // aligned quads of dst columns covering [tx0, tx0 + out): quad index q -> columns gq .. gq+3
+    const int gq = (tx0 & ~3) + 4 * (blockIdx.x * 64 + (tid & 63));
+    if (gq >= tx0 + out || gq + 3 < tx0 || gq >= dst_w) return;
+    const int a = (blockIdx.y * kPasteBY + (tid >> 6) * 8) >> 1;      // output rows 2a .. 2a+7
+    const int gy_lo = ty0 + 2 * a;
+    if (gy_lo >= dst_h || gy_lo + 7 < 0 || 2 * a >= out) return;
+    // later tiles (last writer wins): fully covered -> nothing to do; partly covered -> per-pixel test below
     unsigned later = 0;
-    for (int l = b + 1; l < tiles.n; ++l)
-        if (gx >= tiles.x[l] && gx < tiles.x[l] + out) later |= 1u << l;
-    // column taps
-    int sx = (ox >> 1) - ((ox & 1) ? 0 : 1);
-    float a1 = (ox & 1) ? 0.25f : 0.75f;
-    if (sx < 0) { sx = 0; a1 = 0.f; }
-    if (sx >= S - 1) { sx = S - 1; a1 = 0.f; }
-    const int sx1 = min(sx + 1, S - 1);
-    const float a0 = 1.f - a1;
-    // 8 consecutive output rows 2a .. 2a+7 need the source rows a-1 .. a+4: 6 horizontal passes, not 16
-    const int a = (blockIdx.y * kPasteBY + (tid >> 6) * 8) >> 1;
-    float h[6];
+    for (int l = b + 1; l < tiles.n; ++l) {
+        const int lx = tiles.x[l], ly = tiles.y[l];
+        const bool cols_all = gq >= lx && gq + 3 < lx + out, cols_any = gq + 3 >= lx && gq < lx + out;
+        const bool rows_all = gy_lo >= ly && gy_lo + 7 < ly + out, rows_any = gy_lo + 7 >= ly && gy_lo < ly + out;
+        if (cols_all && rows_all) return;
+        if (cols_any && rows_any) later |= 1u << l;
+    }
+    // horizontal pass: output column ox of the tile blends source columns sx, sx+1 with weights (1-a1, a1)
+    int sx[4], sx1[4];
+    float a0[4], a1[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int ox = min(max(gq + j - tx0, 0), out - 1);           // columns outside the tile are never stored
+        int c = (ox >> 1) - ((ox & 1) ? 0 : 1);
+        float f = (ox & 1) ? 0.25f : 0.75f;
+        if (c < 0) { c = 0; f = 0.f; }
+        if (c >= S - 1) { c = S - 1; f = 0.f; }
+        sx[j] = c;
+        sx1[j] = min(c + 1, S - 1);
+        a1[j] = f;
+        a0[j] = 1.f - f;
+    }
+    float h[6][4];
 #pragma unroll
     for (int t = 0; t < 6; ++t) {
         const float* row = sp + (int64_t)min(max(a - 1 + t, 0), S - 1) * S;
-        h[t] = __fadd_rn(__fmul_rn(__ldg(row + sx), a0), __fmul_rn(__ldg(row + sx1), a1));
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            h[t][j] = __fadd_rn(__fmul_rn(__ldg(row + sx[j]), a0[j]), __fmul_rn(__ldg(row + sx1[j]), a1[j]));
     }
+    const bool cols_inside = gq >= tx0 && gq + 3 < tx0 + out && gq + 3 < dst_w && gq >= 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int oy = 2 * a + k;
         const int gy = ty0 + oy;
         if (oy >= out || gy < 0 || gy >= dst_h) continue;
-        bool owned = true;
-        for (unsigned mm = later; mm; mm &= mm - 1) {
-            const int l = __ffs(mm) - 1;
-            owned = owned && !(gy >= tiles.y[l] && gy < tiles.y[l] + out);
-        }
-        if (!owned) continue;
         // row taps: even rows (f = 0.75) blend source rows a+k/2-1, a+k/2; odd rows (f = 0.25) a+k/2, a+k/2+1;
         // the first and the last output row take one source row with weight 1 (the other tap has weight 0)
         const int t0 = (k >> 1) + (k & 1);                       // index into h[] of source row sy
         float b1 = (k & 1) ? 0.25f : 0.75f;
         if (oy == 0 || oy == out - 1) b1 = 0.f;
-        const float h0 = (oy == 0) ? h[1] : h[t0];
-        const float h1 = (oy == out - 1) ? h[t0] : h[t0 + 1];
-        dst[(int64_t)gy * dst_w + gx] = __fadd_rn(__fmul_rn(h0, 1.f - b1), __fmul_rn(h1, b1));
+        const float b0 = 1.f - b1;
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float h0 = (oy == 0) ? h[1][j] : h[t0][j];
+            const float h1 = (oy == out - 1) ? h[t0][j] : h[t0 + 1][j];
+            o[j] = __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, b1));
+        }
+        float* d = dst + (int64_t)gy * dst_w + gq;
+        if (cols_inside && later == 0) {
+            *reinterpret_cast<float4*>(d) = make_float4(o[0], o[1], o[2], o[3]);
+            continue;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gx = gq + j;
+            bool owned = gx >= tx0 && gx < tx0 + out && gx >= 0 && gx < dst_w;
+            for (unsigned mm = later; mm; mm &= mm - 1) {
+                const int l = __ffs(mm) - 1;
+                owned = owned && !(gy >= tiles.y[l] && gy < tiles.y[l] + out && gx >= tiles.x[l] && gx < tiles.x[l] + out);
+            }
+            if (owned) d[j] = o[j];
+        }
     }
 }
 
@@ -384,20 +420,35 @@ extern "C" int eds_resize_paste_f32(const float* src, int src_h, int src_w, int 
     return check_launch("resize_paste_kernel");
 }
 
-extern "C" int eds_paste_tiles_x2_f32(const float* src, int n_tiles, int S, const int* ys_host, const int* xs_host,
-                                      float* dst, int dst_h, int dst_w, void* stream) {
+static int paste_tiles_launch(const float* src, int n_src, int first_tile, int n_tiles, int S, const int* ys_host,
+                              const int* xs_host, float* dst, int dst_h, int dst_w, void* stream) {
     EDS_REQUIRE(src && dst && ys_host && xs_host, "paste_tiles_x2: null pointer");
     EDS_REQUIRE(n_tiles >= 1 && n_tiles <= kPasteMaxTiles && S >= 1, "paste_tiles_x2: n_tiles=%d (1..%d), S=%d", n_tiles,
                 kPasteMaxTiles, S);
+    EDS_REQUIRE(n_src >= 1 && first_tile >= 0 && first_tile + n_src <= n_tiles,
+                "paste_tiles_x2: tiles %d..%d outside the list of %d", first_tile, first_tile + n_src - 1, n_tiles);
+    EDS_REQUIRE(dst_w % 4 == 0 && (((uintptr_t)dst) & 15) == 0, "paste_tiles_x2: dst rows must be 16-byte aligned "
+                "(dst_w %% 4 == 0); use eds_resize_paste_f32 for other widths");
     PasteTiles tiles;
     tiles.n = n_tiles;
     for (int b = 0; b < kPasteMaxTiles; ++b) {
         tiles.y[b] = b < n_tiles ? ys_host[b] : 0;
         tiles.x[b] = b < n_tiles ? xs_host[b] : 0;
     }
-    dim3 block(64, 4), grid(ceil_div(2 * S, kPasteBX), ceil_div(2 * S, kPasteBY), n_tiles);
-    paste_tiles_x2_kernel<<<grid, block, 0, as_stream(stream)>>>(src, S, tiles, dst, dst_h, dst_w);
+    dim3 block(64, 4), grid(ceil_div(2 * S + 3, 4 * 64), ceil_div(2 * S, kPasteBY), n_src);
+    paste_tiles_x2_kernel<<<grid, block, 0, as_stream(stream)>>>(src, S, tiles, first_tile, dst, dst_h, dst_w);
     return check_launch("paste_tiles_x2_kernel");
+}
+
+extern "C" int eds_paste_tiles_x2_f32(const float* src, int n_tiles, int S, const int* ys_host, const int* xs_host,
+                                      float* dst, int dst_h, int dst_w, void* stream) {
+    return paste_tiles_launch(src, n_tiles, 0, n_tiles, S, ys_host, xs_host, dst, dst_h, dst_w, stream);
+}
+
+extern "C" int eds_paste_tiles_owned_x2_f32(const float* src, int n_src, int first_tile, int n_tiles, int S,
+                                            const int* ys_host, const int* xs_host, float* dst, int dst_h, int dst_w,
+                                            void* stream) {
+    return paste_tiles_launch(src, n_src, first_tile, n_tiles, S, ys_host, xs_host, dst, dst_h, dst_w, stream);
 }
 
 extern "C" int eds_preprocess_tile_u8(const uint8_t* img, int img_h, int img_w, int y0, int x0, int S,

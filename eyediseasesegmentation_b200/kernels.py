@@ -34,9 +34,20 @@ SMALL_CONV = __import__("os").environ.get("EDS_SMALL_CONV", "1") != "0"
 FUSED_TAIL = __import__("os").environ.get("EDS_FUSED_TAIL", "0") != "0"
 
 
+#: when set to a list, every launch appends (kernel class, CUDA event recorded right after it on the launching
+#: stream): consecutive events give per-launch device times of an EAGER pass (bench.py: time shares per class)
+KERNEL_TRACE = None
+_TAG = [None]
+
+
 def check(rc: int) -> None:
     LAUNCHES[0] += 1
     _check(rc)
+    if KERNEL_TRACE is not None:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        KERNEL_TRACE.append((_TAG[0] or __import__("sys")._getframe(1).f_code.co_name, ev))
+    _TAG[0] = None
 
 
 def _stream() -> int:
@@ -78,6 +89,20 @@ def pr_hist(prob: torch.Tensor, gt: torch.Tensor, hist: Optional[torch.Tensor] =
         straddle = torch.zeros((n_img, _lib.PR_NTHRESH, 2), dtype=torch.int32, device=prob.device)
     check(_lib.lib().eds_pr_hist_f32(_p(prob), _p(gt), n_px, n_img, _p(hist), _p(straddle), splits, _stream()))
     return hist, straddle
+
+
+def pr_hist_rects(prob: torch.Tensor, gt: torch.Tensor, rects, hist: torch.Tensor, straddle: torch.Tensor) -> None:
+    """prob [H,W] fp32, gt [H,W] u8, rects: [(y, x, h, w), ...] (<= 32) -> accumulates the histogram of those
+    rectangles into hist [2,BINS] i32 / straddle [19,2] i32 of that image (one rank's owned pixels)."""
+    _chk(prob, gt, hist, straddle)
+    assert prob.dtype == torch.float32 and gt.dtype == torch.uint8 and prob.shape == gt.shape and prob.dim() == 2
+    assert hist.shape == (2, _lib.PR_BINS) and straddle.shape == (_lib.PR_NTHRESH, 2)
+    rects = [r for r in rects if r[2] > 0 and r[3] > 0]
+    for i in range(0, len(rects), 32):
+        part = rects[i:i + 32]
+        flat = _lib.int_array([int(v) for r in part for v in r])
+        check(_lib.lib().eds_pr_hist_rects_f32(_p(prob), _p(gt), prob.shape[0], prob.shape[1], len(part), flat,
+                                               _p(hist), _p(straddle), _stream()))
 
 
 def pr_scan(hist: torch.Tensor, straddle: torch.Tensor):
@@ -139,6 +164,19 @@ def paste_tiles_x2(src: torch.Tensor, dst: torch.Tensor, origins) -> None:
     ys = _lib.int_array([int(o[0]) for o in origins])
     xs = _lib.int_array([int(o[1]) for o in origins])
     check(_lib.lib().eds_paste_tiles_x2_f32(_p(src), B, S, ys, xs, _p(dst), dst.shape[0], dst.shape[1], _stream()))
+
+
+def paste_tiles_owned_x2(src: torch.Tensor, first_tile: int, dst: torch.Tensor, origins) -> None:
+    """src [n,S,S] = tiles first_tile .. first_tile+n-1 of the image whose FULL tile list (make_grid order) is
+    ``origins``; writes only the pixels those tiles own (no later tile of the list covers them)."""
+    _chk(src, dst)
+    assert src.dtype == torch.float32 and dst.dtype == torch.float32 and src.dim() == 3 and dst.dim() == 2
+    n, S, S2 = src.shape
+    assert S == S2 and 0 <= first_tile and first_tile + n <= len(origins)
+    ys = _lib.int_array([int(o[0]) for o in origins])
+    xs = _lib.int_array([int(o[1]) for o in origins])
+    check(_lib.lib().eds_paste_tiles_owned_x2_f32(_p(src), n, first_tile, len(origins), S, ys, xs, _p(dst),
+                                                  dst.shape[0], dst.shape[1], _stream()))
 
 
 def preprocess_tile(img: torch.Tensor, y0: int, x0: int, S: int, mean, std,
@@ -240,6 +278,8 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], strid
                                   _lib.load().eds_conv3x3_wide_supported(Cin + C1, Cout, R, S, stride, pad))
         halo = not wide and (impl == "halo" or (impl == "tc" and HALO_MIN_HW and min(H, W_) >= HALO_MIN_HW and
                                                 _lib.load().eds_conv3x3_halo_supported(Cin + C1, Cout, R, S, stride, pad)))
+        _TAG[0] = "conv3x3_wide (tcgen05)" if wide else "conv3x3_halo (tcgen05)" if halo else \
+            f"conv_igemm {R}x{R} (tcgen05)"
         if wide:
             if x1 is not None:
                 check(_lib.lib().eds_conv3x3_wide_bf16_2src(_p(x), Cin, _p(x1), C1, N, H, W_, _p(w), _p(bias), Cout,
@@ -292,6 +332,7 @@ def conv3x3_small(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]
     if trace is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
+    _TAG[0] = "conv3x3_small (mma.sync)"
     check(_lib.lib().eds_conv3x3_small_bf16(_p(x), _p(cgate), _p(sgate), up_mode, N, H, W_, Cin, _p(w), _p(bias), Cout,
                                             int(relu), _p(out), _stream()))
     if trace is not None:

@@ -7,7 +7,9 @@ The arithmetic runs on the B200 kernels; decode (PIL) and the uint8 whole-image 
 stay on the host as in the reference.  Differences that do not change results:
   - images are visited in sorted order (the reference shuffles its DataLoader, tta.py:84);
   - the three consumers share one inference pass (see ``_driver.CachedPredictions``);
-  - with torchrun the image list is sharded over ranks and the metric sums are all-reduced.
+  - with torchrun (one process per GPU) ``tta_patches`` deals (image, tile) units to the ranks and all-reduces
+    the per-image integer histograms (``partition.py``); ``test_tta`` shards whole images and
+    all-reduces the metric sums.
 """
 from __future__ import annotations
 
@@ -18,7 +20,7 @@ from pathlib import Path
 import numpy as np
 import torch
 
-from . import archs, kernels as K
+from . import archs, kernels as K, partition
 from . import _driver as drv
 from ._driver import get_model, str_2_bool, smp  # noqa: F401  (re-exported like the reference)
 from .aucpr import get_auc, plot_aucpr_curve
@@ -84,7 +86,7 @@ def test_tta(logdir, config, args):
 def tta_patches(logdir, config, args):
     test_img_dir = config["test_img_path"]
     test_mask_dir = config["test_mask_path"] / lesion_dict[config["lesion_type"]].dir_name
-    TEST_MASKS = drv.shard(sorted(test_mask_dir.glob("*.*")))
+    ALL_MASKS = sorted(test_mask_dir.glob("*.*"))
     model = drv.build_model(config, logdir, args)
     _, mean, std = archs.get_preprocessing_fn(dataset_name=config["dataset_name"], grayscale=config["gray"])
     if config["gray"]:
@@ -93,15 +95,24 @@ def tta_patches(logdir, config, args):
         mean, std = [mean] * 3, [std] * 3
     transforms = drv.tta_transforms(args)
     resize_size = config["scale_size"]
-    dev = drv.device()
+    lesion = config["lesion_type"]
 
-    def produce():
-        for mask_path in TEST_MASKS:
-            img = test_img_dir / re.sub("_" + config["lesion_type"] + ".tif", ".jpg", mask_path.name)
-            gt_mask = drv.read_mask(mask_path, 0)
-            pred, _ = drv.infer_image_host(model, transforms, torch.from_numpy(drv.read_rgb(img)),
-                                           torch.from_numpy(gt_mask), resize_size, mean, std)
-            yield pred, gt_mask, mask_path.name
+    def load(mask_path):
+        img = test_img_dir / re.sub("_" + lesion + ".tif", ".jpg", mask_path.name)
+        return drv.read_rgb(img), drv.read_mask(mask_path, 0)
+
+    rank, world_size = partition.world()
+    if world_size > 1:
+        # one process per GPU: (image, tile) units over the ranks, one all-reduce of the integer histograms
+        produce = drv.partitioned_producer(model, transforms, ALL_MASKS, load, resize_size, mean, std)
+    else:
+        def produce():
+            # decode of image k+1 runs on a background thread while the GPU works on image k
+            loaded = drv.prefetched([(lambda m=m: load(m)) for m in ALL_MASKS])
+            for mask_path, (image, gt_mask) in zip(ALL_MASKS, loaded):
+                pred, _ = drv.infer_image_host(model, transforms, torch.from_numpy(image), torch.from_numpy(gt_mask),
+                                               resize_size, mean, std)
+                yield pred, gt_mask, mask_path.name
 
     predict_generator = drv.CachedPredictions(produce)
 
@@ -111,6 +122,8 @@ def tta_patches(logdir, config, args):
     logging.info("====> Find optimal threshold from 0 to 1 w.r.t auc-pr curve")
     optim_thres1, optim_thres2, optim_thres3 = plot_aucpr_curve(predict_generator(), Path(logdir).name, config)
     for mask_pred, _, mask_name in predict_generator():
+        if np.asarray(mask_pred).size == 0:         # partitioned run: another rank assembles and writes this image
+            continue
         mask = (np.asarray(mask_pred) > optim_thres3).astype(np.float32)
         mask_name = re.sub("_" + config["lesion_type"] + ".tif", ".jpg", mask_name)
         so(mask, drv.output_dir(config, logdir) / mask_name)

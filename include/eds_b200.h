@@ -83,6 +83,14 @@ EDS_API int eds_init(void);
 EDS_API int eds_pr_hist_f32(const float* prob, const uint8_t* gt, int64_t n_pixels, int n_images,
                     uint32_t* hist, uint32_t* straddle, int splits, void* stream);
 
+/* The same histogram over a list of rectangles of ONE image (prob / gt: [img_h][img_w]); rects_host:
+ * n_rects x (y, x, h, w), n_rects <= 32.  Used by the (image, tile) partition: every rank bins only the
+ * pixels its tiles own, the per-image integer histograms of all ranks are summed by one all-reduce and
+ * equal the single-process histogram bin for bin.  Accumulates into hist [2][EDS_PR_BINS] and
+ * straddle [EDS_PR_NTHRESH][2] of that image. */
+EDS_API int eds_pr_hist_rects_f32(const float* prob, const uint8_t* gt, int img_h, int img_w, int n_rects,
+                          const int* rects_host, uint32_t* hist, uint32_t* straddle, void* stream);
+
 /* Scan of the histograms.  Per image: ap[i] (sklearn AP on key-quantised scores),
  * roc[i] (trapezoid ROC-AUC), counts[i][k] = {tp, pp} at threshold k (strict >,
  * aucpr.py:63-66), totals[i] = {n_pos, n_neg}.  NaN when a class is empty. */
@@ -113,6 +121,15 @@ EDS_API int eds_resize_paste_f32(const float* src, int src_h, int src_w, int cro
  * (tta.py:211-213); bit-identical to n_tiles calls of eds_resize_paste_f32.  n_tiles <= 32. */
 EDS_API int eds_paste_tiles_x2_f32(const float* src, int n_tiles, int S, const int* ys_host, const int* xs_host,
                                    float* dst, int dst_h, int dst_w, void* stream);
+
+/* One rank's share of the same paste under the (image, tile) partition (replaces the
+ * single-GPU tile loop of tta.py:170,207): src holds the n_src tiles first_tile .. first_tile+n_src-1 of the
+ * image's tile list (ys/xs list ALL n_tiles tiles of the image, in make_grid order).  A pixel is written only
+ * if no LATER tile of the list covers it, whether that tile is in src or on another rank -- every rank writes
+ * exactly the pixels its tiles own, and the ranks' canvases sum to the single-process image.  dst_w % 4 == 0. */
+EDS_API int eds_paste_tiles_owned_x2_f32(const float* src, int n_src, int first_tile, int n_tiles, int S,
+                                 const int* ys_host, const int* xs_host, float* dst, int dst_h, int dst_w,
+                                 void* stream);
 
 /* Sliding-window tile fetch (tta.py:201-204): window [y0,y0+2S) x [x0,x0+2S) of an
  * HWC u8 RGB image -> 2x2 box mean with round-half-up (== cv2.resize of uint8 by

@@ -1,25 +1,45 @@
+"""pr_hist throughput on a 27-image IDRiD-sized set for several score distributions (dev tool)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from eyediseasesegmentation_b200 import kernels as K
+from eyediseasesegmentation_b200 import kernels as K, _lib
 H, W, n_img = 2848, 4288, 27
 dev = "cuda"
 torch.manual_seed(0)
-mode = sys.argv[1] if len(sys.argv) > 1 else "uniform"
-if mode == "uniform":
-    prob = torch.rand((n_img, H * W), device=dev)
-else:   # network-like: sigmoid(N(-0.55, 0.14))
-    prob = torch.sigmoid(-0.55 + 0.14 * torch.randn((n_img, H * W), device=dev))
+modes = sys.argv[1:] or ["uniform", "network", "trained", "saturated", "flat"]
 gt = (torch.rand((n_img, H * W), device=dev) < 0.01).to(torch.uint8)
-hist, strad = K.pr_hist(prob, gt)
-ref = hist.clone()
-torch.cuda.synchronize()
-times = []
-for _ in range(5):
-    hist.zero_(); strad.zero_()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(); K.pr_hist(prob, gt, hist, strad); b.record(); torch.cuda.synchronize()
-    times.append(a.elapsed_time(b))
-ms = sorted(times)[2]
-ok = bool((hist == ref).all()) and int(hist.sum()) == n_img * H * W
-print(f"gwarps={os.environ.get('EDS_HIST_GWARPS','0')} {mode}: {ms:.3f} ms  {n_img*H*W*5/ms/1e6:.0f} GB/s  consistent={ok}", flush=True)
+for mode in modes:
+    if mode == "uniform":
+        prob = torch.rand((n_img, H * W), device=dev)
+    elif mode == "network":      # random-init network: sigmoid(N(-0.55, 0.14))
+        prob = torch.sigmoid(-0.55 + 0.14 * torch.randn((n_img, H * W), device=dev))
+    elif mode == "trained":      # confident network: sigmoid(N(-8, 3)), smooth in x (runs of 8 equal pixels)
+        base = torch.sigmoid(-8 + 3 * torch.randn((n_img, H * W // 8), device=dev))
+        prob = base.repeat_interleave(8, dim=1).contiguous()
+    elif mode == "saturated":    # half the pixels below 2^-24 (tagged bin 0), a few exactly 1
+        prob = torch.sigmoid(-18 + 4 * torch.randn((n_img, H * W), device=dev))
+        prob[:, ::1000] = 1.0
+    else:                        # one bin everywhere
+        prob = torch.full((n_img, H * W), 0.25, device=dev)
+    hist, strad = K.pr_hist(prob, gt)
+    ref = hist.clone()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(7):
+        hist.zero_(); strad.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); K.pr_hist(prob, gt, hist, strad); b.record(); torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+    ms = sorted(times)[3]
+    ok = bool((hist == ref).all()) and int(hist.to(torch.int64).sum()) == n_img * H * W
+    # exactness of image 0 against torch.bincount of the documented key
+    p0 = prob[0]
+    hi = p0 >= 0.5
+    q = torch.where(hi, 1.0 - p0, p0)
+    k = ((q.view(torch.int32).to(torch.int64) >> _lib.PR_KEY_SHIFT) - _lib.PR_KEY_BIAS).clamp(0, _lib.PR_HALF - 1)
+    key = torch.where(hi, _lib.PR_BINS - 1 - k, k)
+    want0 = torch.bincount(key[gt[0] == 0], minlength=_lib.PR_BINS)
+    exact = bool((hist[0, 0].to(torch.int64) == want0).all())
+    print(f"{mode:10s}: {ms:.3f} ms  {n_img*H*W*5/ms/1e6:7.0f} GB/s  frac {n_img*H*W*5/ms/1e6/6517.6:.3f}  "
+          f"consistent={ok} exact={exact}", flush=True)
+    del prob, hist, strad, ref

@@ -45,6 +45,18 @@ def _oracle_tta_prob(name, cfg, sd_cuda, x, kind):
     return torch.stack(out)
 
 
+def _calibrate_head(name, cfg, sd, x, mean=0.0, std=2.0):
+    """Rescale the segmentation head of a random-init network so that its logits on ``x`` have the given mean
+    and spread: probabilities then cover the 19 thresholds and masks / ROC / PR are informative."""
+    with torch.no_grad():
+        logit = nets.forward(name, _cuda_sd(sd), x.cuda(), cfg)
+    m, sdev = float(logit.mean()), float(logit.std())
+    k = std / max(sdev, 1e-6)
+    sd["segmentation_head.0.weight"] = sd["segmentation_head.0.weight"] * k
+    sd["segmentation_head.0.bias"] = (sd["segmentation_head.0.bias"] - m) * k + mean
+    return sd
+
+
 # ------------------------------------------------------------------------------------------------ cfg-2
 SE50 = dict(encoder_name="se_resnet50", encoder_weights=None, classes=1, decoder_attention_type="scse",
             deep_supervision=True)
@@ -103,23 +115,24 @@ def test_cfg5_vessel_pad_then_test_tta(tmp_path, monkeypatch, raw_hw, size, base
     name, cfg = "unetplusplusstar", star_cfg(base_dim)
     model = helpers.build_product_model(name, cfg)
     sd = {k: v.clone() for k, v in model.state_dict().items()}
-    sd["segmentation_head.0.weight"] *= 6.0                 # spread the random-init logits across the thresholds
     logdir = tmp_path / "models" / dataset / "Vessel" / "vexp"
     (logdir / "checkpoints").mkdir(parents=True)
-    torch.save({"model_state_dict": sd}, logdir / "checkpoints" / "best.pth")
     raw_img, raw_lab = tmp_path / "raw" / "images", tmp_path / "raw" / "labels"
     raw_img.mkdir(parents=True)
     raw_lab.mkdir(parents=True)
     h, w = raw_hw
     top, bottom, left, right = pad_img.pad_geometry(raw_hw, size)
     mean, std = pipeline.DATASET_STATS["IDRiD"]               # tta_vessel.py:73 passes dataset_name=None
-    sd_cuda = _cuda_sd(sd)
     # vessel file lists are ``*.jpg`` (base_utils.py:81-84); labels are 8x8 blocks so that JPEG keeps them binary
     names, oracle_prob = [f"{i:02d}_test.jpg" for i in range(2)], {}
     for i, n in enumerate(names):
         Image.fromarray(_vessel_like(h, w, 90 + i)).save(raw_img / n, quality=95)
     pad_dir = tmp_path / "pad_ver" / "test"
     pad_img.pad(str(raw_img), str(pad_dir / "images"), desired_size=size)
+    first = np.asarray(Image.open(pad_dir / "images" / names[0]).convert("RGB")).astype("uint8")
+    _calibrate_head(name, cfg, sd, torch.from_numpy(pipeline.preprocess(first, mean, std).transpose(2, 0, 1)).float()[None])
+    torch.save({"model_state_dict": sd}, logdir / "checkpoints" / "best.pth")
+    sd_cuda = _cuda_sd(sd)
     for i, n in enumerate(names):
         padded = np.asarray(Image.open(pad_dir / "images" / n).convert("RGB")).astype("uint8")
         assert padded.shape == (size, size, 3)
@@ -173,8 +186,7 @@ def test_tta_patches_bf16_auc_within_1e3_of_reference_path(tmp_path, monkeypatch
     model = helpers.build_product_model(name, cfg)
     assert model.precision == "bf16"
     sd = {k: v.clone() for k, v in model.state_dict().items()}
-    sd["segmentation_head.0.weight"] *= 6.0
-    sd["segmentation_head.0.bias"] -= 1.5
+    _calibrate_head(name, cfg, sd, helpers.golden_input(1, S, seed=77), mean=-1.5, std=2.0)
     logdir = tmp_path / "models" / "IDRiD" / "EX" / "auc"
     (logdir / "checkpoints").mkdir(parents=True)
     torch.save({"model_state_dict": sd}, logdir / "checkpoints" / "best.pth")

@@ -12,7 +12,7 @@ import torch
 
 from eyediseasesegmentation_b200 import _lib, aucpr, ttach_compat as tta
 from eyediseasesegmentation_b200._driver import CachedPredictions, longest_max_size, pad_to_square
-from eyediseasesegmentation_b200.util import multigen
+from eyediseasesegmentation_b200.util import make_grid, multigen
 from oracle import nets, scoring
 import helpers
 
@@ -309,3 +309,83 @@ def test_load_checkpoint_accepts_catalyst_style_dicts(tmp_path):
     torch.save(ckpt, tmp_path / "best.pth")
     got = load_checkpoint(tmp_path / "best.pth")
     assert torch.equal(got["model_state_dict"]["w"], torch.arange(4.0)) and got["epoch"] == 3
+
+
+# ------------------------------------------------------------------ (image, tile) partition
+def test_owned_cells_equal_last_writer_wins_map():
+    """partition.owned_cells against a brute-force replay of the paste loop (preds[y1:y2, x1:x2] = tile, in order):
+    IDRiD's 6-tile grid, ragged grids, the degenerate grids of make_grid (4 identical windows for 1024^2 @1024) and
+    arbitrary overlapping windows."""
+    from eyediseasesegmentation_b200 import partition
+    cases = [((2848, 4288), 2048), ((300, 420), 128), ((608, 608), 512), ((1024, 1024), 1024), ((330, 290), 256)]
+    lists = [([tuple(int(v) for v in s) for s in make_grid(shape, window=w, min_overlap=32)], shape) for shape, w in cases]
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        wins = []
+        for _ in range(7):
+            y, x = int(rng.integers(-10, 90)), int(rng.integers(-10, 120))
+            wins.append((y, y + int(rng.integers(1, 60)), x, x + int(rng.integers(1, 70))))
+        lists.append((wins, (100, 130)))
+    for slices, shape in lists:
+        cells = partition.owned_cells(slices, shape)
+        want = partition.owner_map(slices, shape)
+        got = np.full(shape, -1, dtype=np.int32)
+        for t, rects in enumerate(cells):
+            for (y, x, h, w) in rects:
+                assert h > 0 and w > 0 and (got[y:y + h, x:x + w] == -1).all()      # disjoint
+                got[y:y + h, x:x + w] = t
+        assert np.array_equal(got, want)
+    # IDRiD: tile origins and the 27 * 6 = 162 units balance to within one unit on 8 ranks
+    sizes = [len(partition.tile_units(27, 6, r, 8)) for r in range(8)]
+    assert sum(sizes) == 162 and max(sizes) - min(sizes) <= 1
+    assert partition.batches(list(range(15)), 6) == [list(range(0, 5)), list(range(5, 10)), list(range(10, 15))]
+    assert partition.batches([], 6) == [] and [len(b) for b in partition.batches(list(range(13)), 6)] == [5, 4, 4]
+
+
+_PART_WORKER = r"""
+import os, sys, json
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, 'tests'))
+import numpy as np, torch, torch.distributed as dist
+from eyediseasesegmentation_b200 import partition, _lib
+from eyediseasesegmentation_b200.util import make_grid
+from oracle import scoring
+rank = int(sys.argv[1])
+dist.init_process_group('gloo', init_method='tcp://127.0.0.1:{port}', rank=rank, world_size=2)
+# every rank builds the same synthetic maps; each bins (numpy stand-in for eds_pr_hist_rects_f32: same key, same
+# layout) only the pixels its (image, tile) units own; ONE all-reduce of [n_img, 2, bins] int32
+shapes = [(150, 210), (140, 130), (150, 210)]
+rng = np.random.default_rng(5)
+maps = [rng.random(s, dtype=np.float32) for s in shapes]
+gts = [(rng.random(s) < 0.2).astype(np.uint8) for s in shapes]
+hist = torch.zeros((len(shapes), 2, _lib.PR_BINS), dtype=torch.int32)
+unit = 0
+for i, shape in enumerate(shapes):
+    slices = [tuple(int(v) for v in s) for s in make_grid(shape, window=64, min_overlap=32)]
+    cells = partition.owned_cells(slices, shape)
+    for t in range(len(slices)):
+        if unit % 2 == rank:
+            for (y, x, h, w) in cells[t]:
+                key = scoring.score_key(maps[i][y:y + h, x:x + w]).ravel()
+                g = gts[i][y:y + h, x:x + w].ravel()
+                for cls in (0, 1):
+                    hist[i, cls] += torch.from_numpy(np.bincount(key[g == cls], minlength=_lib.PR_BINS).astype(np.int32))
+        unit += 1
+partition.allreduce_sum_(hist)
+full = [[np.bincount(scoring.score_key(maps[i]).ravel()[gts[i].ravel() == cls], minlength=_lib.PR_BINS)
+         for cls in (0, 1)] for i in range(len(shapes))]
+ok = all(np.array_equal(hist[i, cls].numpy(), full[i][cls]) for i in range(len(shapes)) for cls in (0, 1))
+print('RESULT' + json.dumps(dict(ok=bool(ok), total=int(hist.sum())))); dist.destroy_process_group()
+"""
+
+
+def test_two_rank_tile_partition_histograms_sum_to_single_process(tmp_path):
+    import json
+    port = 29950 + os.getpid() % 300
+    code = _PART_WORKER.format(root=ROOT, port=port)
+    procs = [subprocess.Popen([sys.executable, "-c", code, str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                              text=True) for r in range(2)]
+    for p in procs:
+        out, err = p.communicate(timeout=300)
+        assert p.returncode == 0, err[-2000:]
+        res = json.loads([ln for ln in out.splitlines() if ln.startswith("RESULT")][0][6:])
+        assert res["ok"] and res["total"] == 150 * 210 * 2 + 140 * 130

@@ -813,3 +813,93 @@ def test_conv3x3_wide_many_tiles_and_two_inputs():
     ref2 = conv_ref(cat, w2, b, 1, 1, True, None)
     assert rel_err(y2, ref2) < 4e-3
     assert torch.equal(y2, K.conv2d(cat, w2, b, 1, 1, True, None, impl="wide"))
+
+
+# ------------------------------------------------------------------ (image, tile) partition kernels
+def test_pr_hist_rects_sum_to_the_full_histogram():
+    """Every tile's owned rectangles binned separately (as the ranks do) and summed == the one-launch histogram of
+    the whole image, bin for bin and straddle counter for straddle counter; origins are not 16-byte aligned."""
+    from eyediseasesegmentation_b200 import partition
+    from eyediseasesegmentation_b200.util import make_grid
+    H, W = 301, 424
+    rng = np.random.default_rng(9)
+    prob = rng.random((H, W), dtype=np.float32)
+    th32 = np.array(_lib.PR_THRESHOLDS, dtype=np.float32)
+    prob.reshape(-1)[:19] = th32
+    prob.reshape(-1)[500:519] = np.nextafter(th32, np.float32(2))
+    prob[200:, :] = 0.0                                   # a crowded tagged bin
+    gt = (rng.random((H, W)) < 0.1).astype(np.uint8)
+    p, g = torch.from_numpy(prob).to(DEV), torch.from_numpy(gt).to(DEV)
+    want_h, want_s = K.pr_hist(p.reshape(1, -1), g.reshape(1, -1))
+    slices = [tuple(int(v) for v in s) for s in make_grid((H, W), window=128, min_overlap=32)]
+    cells = partition.owned_cells(slices, (H, W))
+    hist = torch.zeros((2, _lib.PR_BINS), dtype=torch.int32, device=DEV)
+    strad = torch.zeros((_lib.PR_NTHRESH, 2), dtype=torch.int32, device=DEV)
+    for t in range(len(slices)):
+        K.pr_hist_rects(p, g, cells[t], hist, strad)
+    assert torch.equal(hist, want_h[0]) and torch.equal(strad, want_s[0])
+    K.pr_hist_rects(p, g, [(0, 0, 0, 5), (3, 3, 4, 0)], hist, strad)           # empty rectangles add nothing
+    assert torch.equal(hist, want_h[0])
+    with pytest.raises(_lib.EdsError):
+        K.pr_hist_rects(p, g, [(H - 2, 0, 5, 5)], hist, strad)
+
+
+def test_paste_tiles_owned_per_rank_canvases_sum_to_single_process_paste():
+    """Three emulated ranks paste only what their (round-robin) tiles own into zeroed canvases: the sum is the
+    one-launch paste of all tiles, bit for bit, and the canvases are disjoint."""
+    from eyediseasesegmentation_b200.util import make_grid
+    S = 64
+    H, W = 300, 420
+    slices = make_grid((H, W), window=2 * S, min_overlap=32)
+    origins = [(int(x1), int(y1)) for (x1, _, y1, _) in slices]
+    B = len(origins)
+    src = torch.rand(B, S, S, device=DEV) + 0.5            # strictly positive: written pixels are non-zero
+    want = torch.zeros((H, W), device=DEV)
+    K.paste_tiles_x2(src, want, origins)
+    canvases = [torch.zeros((H, W), device=DEV) for _ in range(3)]
+    for t in range(B):
+        K.paste_tiles_owned_x2(src[t:t + 1], t, canvases[t % 3], origins)
+    written = sum((c != 0).to(torch.int32) for c in canvases)
+    assert int(written.max()) == 1 and int(written.min()) == 1
+    assert torch.equal(canvases[0] + canvases[1] + canvases[2], want)
+    two = torch.zeros((H, W), device=DEV)                   # several consecutive tiles in one call
+    K.paste_tiles_owned_x2(src[2:5], 2, two, origins)
+    ref = torch.zeros((H, W), device=DEV)
+    for t in (2, 3, 4):
+        K.paste_tiles_owned_x2(src[t:t + 1], t, ref, origins)
+    assert torch.equal(two, ref)
+
+
+def test_partitioned_group_with_emulated_ranks_equals_single_process():
+    """_driver.partitioned_group run once per emulated rank (world size 3, two images of different sizes, tiles of
+    both mixed in one batch): canvases and integer histograms summed over the ranks == the single-process tile
+    loop + whole-image histogram, exactly.  The 'network' is an elementwise map, so results cannot depend on how
+    tiles are batched (the real networks' SE / SCSE means are accumulated with fp32 atomics)."""
+    from eyediseasesegmentation_b200 import _driver as drv, ttach_compat as tta
+
+    class Pointwise(torch.nn.Module):
+        def forward(self, x):
+            return x[:, 0:1] * 0.7 - x[:, 1:2] * 0.3 + x[:, 2:3] * 0.1
+
+    model, tfm = Pointwise(), tta.aliases.d4_transform()
+    S = 64
+    mean, std = [0.45, 0.22, 0.06], [0.33, 0.17, 0.09]
+    rng = np.random.default_rng(3)
+    images = [torch.from_numpy(rng.integers(0, 256, size=s + (3,), dtype=np.uint8)).to(DEV) for s in [(300, 420), (200, 262)]]
+    gts = [drv.pad_width4((torch.rand(im.shape[:2], device=DEV) < 0.1).to(torch.uint8)) for im in images]
+    n, world = len(images), 3
+    hist = torch.zeros((n, 2, _lib.PR_BINS), dtype=torch.int32, device=DEV)
+    strad = torch.zeros((n, _lib.PR_NTHRESH, 2), dtype=torch.int32, device=DEV)
+    total = [None] * n
+    for rank in range(world):
+        canvases, nxt = drv.partitioned_group(model, tfm, images, gts, S, mean, std, hist, strad, 0, rank, world,
+                                              tiles_per_batch=4)
+        for k in range(n):
+            total[k] = canvases[k] if total[k] is None else total[k] + canvases[k]
+    assert nxt == sum(drv.tile_plan(int(im.shape[0]), int(im.shape[1]), S).n for im in images)
+    for k, im in enumerate(images):
+        H, W = int(im.shape[0]), int(im.shape[1])
+        want = drv.tiled_probability_map(model, tfm, im, S, mean, std, tiles_per_batch=4)
+        assert torch.equal(total[k][:, :W], want), k
+        wh, ws = K.pr_hist(want.reshape(1, -1), gts[k][:, :W].contiguous().reshape(1, -1))
+        assert torch.equal(hist[k], wh[0]) and torch.equal(strad[k], ws[0]), k
