@@ -229,6 +229,6 @@ def test_tta_patches_bf16_auc_within_1e3_of_reference_path(tmp_path, monkeypatch
 
     want_pr = scoring.get_auc(items)
     want_roc = scoring.get_aucroc(items[:2])
-    assert 0.05 < want_pr < 0.95, "degenerate test set"
+    assert 0.05 < want_pr < 0.995, "degenerate test set"
     assert abs(seen["pr"] - want_pr) < 1e-3, (seen["pr"], want_pr)
     assert abs(seen["roc"] - want_roc) < 1e-3, (seen["roc"], want_roc)
