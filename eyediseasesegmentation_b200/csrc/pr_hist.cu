@@ -235,18 +235,22 @@ pr_hist_kernel(const float* __restrict__ prob, const uint8_t* __restrict__ gt, i
                     crowded = n_lead >= kAggLanes;
                 }
                 since_check = (since_check + 1) & (kCheckEvery - 1);
-                uint32_t tag = 0, skip = 0xffffffffu;       // skip: counter already settled by the aggregated path
                 if (n_lead >= kAggLanes) {
-                    skip = lead;
-                    uint32_t cnt = 0;
+                    // crowded step: the lead counter gets ONE atomic per warp; the other pixels go one by one and
+                    // remember the top byte (tag bit + threshold index) of the counter they hit
+                    uint32_t pk[kQuadUnroll], cnt = 0;
 #pragma unroll
-                    for (int u = 0; u < kQuadUnroll; ++u)
+                    for (int u = 0; u < kQuadUnroll; ++u) {
+                        pk[u] = 0;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const bool is_lead = off[u][j] == lead;
                             cnt += is_lead;
-                            if (!is_lead) tag |= atomicAdd(reinterpret_cast<uint32_t*>(hbase + off[u][j]), 1u);
+                            if (!is_lead)
+                                pk[u] = __byte_perm(pk[u], atomicAdd(reinterpret_cast<uint32_t*>(hbase + off[u][j]), 1u),
+                                                    0x3210 & ~(0xf << (4 * j)) | (7 << (4 * j)));
                         }
+                    }
                     const uint32_t total = __reduce_add_sync(0xffffffffu, cnt);
                     uint32_t old_lead = 0;
                     if ((tid & 31) == 0) old_lead = atomicAdd(reinterpret_cast<uint32_t*>(hbase + lead), total);
@@ -265,22 +269,33 @@ pr_hist_kernel(const float* __restrict__ prob, const uint8_t* __restrict__ gt, i
                         above = __reduce_add_sync(0xffffffffu, above);
                         if ((tid & 31) == 0 && above) atomicAdd(&s->straddle[k * 2 + ((lead >> 2) & 1)], above);
                     }
+#pragma unroll
+                    for (int u = 0; u < kQuadUnroll; ++u) {  // tagged pixels outside the lead counter (rare here)
+                        const float pv[4] = {p[u].x, p[u].y, p[u].z, p[u].w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            straddle_one(s, (pk[u] >> (8 * j)) << 24, pv[j], off[u][j]);
+                    }
                 } else {
+                    // common step: 16 returning atomics; on uniform scores three steps in four see SOME tagged
+                    // pixel in the warp, so the follow-up must cost (almost) nothing for lanes without one:
+                    // returned values stay in registers, one OR + one branch per thread, one test per pixel
+                    uint32_t old[kQuadUnroll][4], tag = 0;
 #pragma unroll
                     for (int u = 0; u < kQuadUnroll; ++u)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            tag |= atomicAdd(reinterpret_cast<uint32_t*>(hbase + off[u][j]), 1u);
-                }
-                if (__any_sync(0xffffffffu, tag & kTag)) {   // some pixel of this warp shares a bin with a threshold
+                        for (int j = 0; j < 4; ++j) {
+                            old[u][j] = atomicAdd(reinterpret_cast<uint32_t*>(hbase + off[u][j]), 1u);
+                            tag |= old[u][j];
+                        }
+                    if (tag & kTag) {
 #pragma unroll
-                    for (int u = 0; u < kQuadUnroll; ++u) {
-                        // the tag bits of a counter never change after hist_clear: a plain load answers
-                        // "tagged bin, and which threshold?" for the pixels the per-pixel path counted
-                        if (off[u][0] != skip) straddle_one(s, *reinterpret_cast<volatile uint32_t*>(hbase + off[u][0]), p[u].x, off[u][0]);
-                        if (off[u][1] != skip) straddle_one(s, *reinterpret_cast<volatile uint32_t*>(hbase + off[u][1]), p[u].y, off[u][1]);
-                        if (off[u][2] != skip) straddle_one(s, *reinterpret_cast<volatile uint32_t*>(hbase + off[u][2]), p[u].z, off[u][2]);
-                        if (off[u][3] != skip) straddle_one(s, *reinterpret_cast<volatile uint32_t*>(hbase + off[u][3]), p[u].w, off[u][3]);
+                        for (int u = 0; u < kQuadUnroll; ++u) {
+                            straddle_one(s, old[u][0], p[u].x, off[u][0]);
+                            straddle_one(s, old[u][1], p[u].y, off[u][1]);
+                            straddle_one(s, old[u][2], p[u].z, off[u][2]);
+                            straddle_one(s, old[u][3], p[u].w, off[u][3]);
+                        }
                     }
                 }
             }

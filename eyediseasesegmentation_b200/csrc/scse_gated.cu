@@ -471,6 +471,9 @@ static int concat_gated_launch(const eds_gated_src* srcs, int n_srcs, int N, int
     EDS_REQUIRE(!y_skip || c8b > 0, "concat_gated: y_skip given without skip sources");
     // one destination of Ctot channels, or two dense ones (upsampled part / skip part)
     const int stride_a = y_skip ? cs.s[0].C : Ctot;
+    // (A shared-memory tiled variant of this part -- neighbourhood gated once per CTA, fp32 tile, 2 x 4 output blocks
+    // per thread -- measured 2.4-2.5 TB/s against 3.3-3.7 TB/s for the per-thread kernel on the benchmark's layers,
+    // scripts/dev_concat_probe.py: one barrier per small tile and 104 registers leave too little in flight.)
     dim3 grid_a((unsigned)(N * h), (unsigned)ceil_div(wp * c8a, 256));
     EDS_DISPATCH_DTYPE(dtype, T, (concat_gated_kernel<T, 0><<<grid_a, 256, 0, as_stream(stream)>>>(
                                      cs, h, w, mode, Ctot, cgate, sgate, (T*)y, stride_a, 0)));

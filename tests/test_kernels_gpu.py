@@ -2,6 +2,7 @@
 the same op (integer outputs bit-exact, floating point within the tolerance written in
 each test).  Network-level parity against the oracle lives in test_parity_gpu.py."""
 import math
+import os
 
 import numpy as np
 import pytest
