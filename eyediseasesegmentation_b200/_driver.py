@@ -216,14 +216,28 @@ def pad_to_square(img: np.ndarray, size: int) -> np.ndarray:
     return out
 
 
+def tile_blend_mode(config=None) -> str:
+    """"overwrite" (the reference's paste, tta.py:213: last writer wins -- default and parity mode) or "gaussian"
+    (opt-in, no reference counterpart: Gaussian-weighted mean of the overlapping tiles); from
+    ``config["tile_blend"]`` or the EDS_TILE_BLEND environment variable."""
+    mode = (config or {}).get("tile_blend") or os.environ.get("EDS_TILE_BLEND", "overwrite")
+    if mode not in ("overwrite", "gaussian"):
+        raise ValueError(f"tile_blend must be 'overwrite' or 'gaussian', got {mode!r}")
+    return mode
+
+
 def tiled_probability_map(model, transforms, image_dev: torch.Tensor, S: int, mean, std,
-                          tiles_per_batch: int = 6) -> torch.Tensor:
+                          tiles_per_batch: int = 6, blend: str = "overwrite") -> torch.Tensor:
     """Sliding-window inference of tta.py:196-213 on one decoded image (``[H,W,3]`` u8 on the
     device): window 2S, min_overlap 32, each window box-averaged to SxS, all TTA views, sigmoid,
-    bilinear x2, overwrite-paste in ``make_grid`` order (last writer wins)."""
+    bilinear x2, overwrite-paste in ``make_grid`` order (last writer wins).  ``blend="gaussian"`` (opt-in, not
+    the reference's behaviour) replaces the overwrite by a Gaussian-weighted mean of the overlapping tiles."""
     H, W = int(image_dev.shape[0]), int(image_dev.shape[1])
     slices = make_grid((H, W), window=2 * S, min_overlap=32)
     preds = torch.zeros((H, W), dtype=torch.float32, device=image_dev.device)
+    if blend == "gaussian":
+        wsum = torch.zeros_like(preds)
+        window = K.gaussian_window(2 * S, device=image_dev.device)
     for (x1, x2, y1, y2) in slices:
         if x1 < 0 or y1 < 0 or x2 - x1 != 2 * S or y2 - y1 != 2 * S:
             raise ValueError(f"could not broadcast input array from shape ({2 * S},{2 * S}) into shape "
@@ -234,11 +248,17 @@ def tiled_probability_map(model, transforms, image_dev: torch.Tensor, S: int, me
         for j, (x1, _, y1, _) in enumerate(group):
             K.preprocess_tile(image_dev, int(x1), int(y1), S, mean, std, out=x[j])
         prob = predict_probs(model, transforms, x)
-        if len(group) <= 32 and W % 4 == 0:           # one launch, 128-bit stores (rows of preds 16-byte aligned)
+        if blend == "gaussian":
+            prob = prob.contiguous()
+            for j, (x1, _, y1, _) in enumerate(group):
+                K.blend_tile_gaussian_x2(prob[j], (int(x1), int(y1)), window, preds, wsum)
+        elif len(group) <= 32 and W % 4 == 0:         # one launch, 128-bit stores (rows of preds 16-byte aligned)
             K.paste_tiles_x2(prob.contiguous(), preds, [(int(x1), int(y1)) for (x1, _, y1, _) in group])
         else:
             for j, (x1, _, y1, _) in enumerate(group):
                 K.resize_paste(prob[j], preds, (0, 0, S, S), (int(x1), int(y1)), (2 * S, 2 * S))
+    if blend == "gaussian":
+        K.blend_finalize(preds, wsum, out=preds)
     return preds
 
 
@@ -435,14 +455,14 @@ def score_to_host(preds_dev: torch.Tensor, gt_dev: torch.Tensor, copy: bool = Tr
 
 
 def infer_image_host(model, transforms, image_host: torch.Tensor, gt_host: torch.Tensor, S: int, mean, std,
-                     tiles_per_batch: int = 6, copy: bool = True, slot: str = ""):
+                     tiles_per_batch: int = 6, copy: bool = True, slot: str = "", blend: str = "overwrite"):
     """Host-facing unit of the sliding-window path (one iteration of tta.py:190-215 plus its scoring):
     decoded image ``[H,W,3]`` u8 and mask ``[H,W]`` u8 on the HOST (pinned memory makes the uploads
     asynchronous) -> (probability map on the host, ImageScores)."""
     dev = device()
     image = image_host.to(dev, non_blocking=True)
     gt = gt_host.to(dev, non_blocking=True)
-    preds = tiled_probability_map(model, transforms, image, S, mean, std, tiles_per_batch)
+    preds = tiled_probability_map(model, transforms, image, S, mean, std, tiles_per_batch, blend=blend)
     return score_to_host(preds, gt, copy=copy, slot=slot)
 
 

@@ -46,6 +46,8 @@ PROTOTYPES = {
     "eds_resize_paste_f32": [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "eds_paste_tiles_x2_f32": [_vp, _i, _i, C.POINTER(_i), C.POINTER(_i), _vp, _i, _i, _vp],
     "eds_paste_tiles_owned_x2_f32": [_vp, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), _vp, _i, _i, _vp],
+    "eds_blend_tile_gaussian_x2_f32": [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
+    "eds_blend_finalize_f32": [_vp, _vp, _i64, _vp, _vp],
     "eds_preprocess_tile_u8": [_vp, _i, _i, _i, _i, _i, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp, _vp],
     "eds_stem_conv7x7s2": [_vp, _i, _i, _i, _i, C.POINTER(_i), _vp, _vp, _vp, _i, _vp],
     "eds_stem_pack_weights": [_vp, _vp, _vp],
@@ -62,10 +64,7 @@ PROTOTYPES = {
     "eds_channel_mean": [_vp, _i, _i, _i, _vp, _i, _vp],
     "eds_se_gate": [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "eds_se_scale_add_relu": [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
-    "eds_scse_apply": [_vp, _vp, _vp, _f, _i, _i, _i, _vp, _i, _vp],
     "eds_upsample2x_concat": [_vp, _i, _i, _i, _i, _i, C.POINTER(_vp), C.POINTER(_i), _i, _vp, _i, _vp],
-    "eds_concat_stats": [_vp, _i, _i, _i, _i, _i, C.POINTER(_vp), C.POINTER(_i), _i, _vp, _f, _vp, _vp, _vp, _i, _vp],
-    "eds_scse_scale": [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
     "eds_gated_stats": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp],
     "eds_sse_finalize": [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp],
     "eds_concat_gated": [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp],

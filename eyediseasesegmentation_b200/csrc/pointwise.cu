@@ -168,47 +168,6 @@ __global__ void se_scale_add_relu_kernel(const T* __restrict__ x, const float* _
     }
 }
 
-// --------------------------------------------------------------------- SCSE
-// smp SCSEModule.forward: x * cSE(x) + x * sSE(x), sSE = sigmoid(conv1x1(C->1)).
-// `lp` lanes (power of two <= 32) share one pixel; they stride over its C/8 vectors.
-template <typename T>
-__global__ void __launch_bounds__(256)
-scse_apply_kernel(const T* __restrict__ x, const float* __restrict__ cgate, const float* __restrict__ w_sse,
-                  float b_sse, int64_t HW, int C, int lp, int64_t n_pixels, T* __restrict__ y) {
-    const int tid = threadIdx.x;
-    const int sub = tid % lp;
-    const int ppb = 256 / lp;  // pixels per CTA per iteration
-    const int C8 = C / 8;
-    // the loop bound is CTA-uniform so every lane reaches the shuffles; tail lanes are masked by `live`
-    for (int64_t pbase = (int64_t)blockIdx.x * ppb; pbase < n_pixels; pbase += (int64_t)gridDim.x * ppb) {
-        const int64_t p = pbase + tid / lp;
-        const bool live = p < n_pixels;
-        const int64_t n = live ? p / HW : 0;
-        const T* xp = x + p * C;
-        float dot = 0.f;
-        if (live)
-            for (int v8 = sub; v8 < C8; v8 += lp) {
-                float v[8];
-                Vec8<T>::ld(xp + v8 * 8, v);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) dot += v[i] * w_sse[v8 * 8 + i];
-            }
-        for (int o = lp >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-        const float s = sigmoidf_acc(dot + b_sse);
-        if (live) {
-            const float* cg = cgate + n * C;
-            T* yp = y + p * C;
-            for (int v8 = sub; v8 < C8; v8 += lp) {
-                float v[8];
-                Vec8<T>::ld(xp + v8 * 8, v);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = v[i] * cg[v8 * 8 + i] + v[i] * s;
-                Vec8<T>::st(yp + v8 * 8, v);
-            }
-        }
-    }
-}
-
 // --------------------------------------------------- upsample x2 + concat
 // unetplusplusstar.py:128,153 (bilinear) / deep_supunetplusplus.py:49-51 (nearest) + torch.cat.
 struct ConcatSrc {
@@ -465,20 +424,6 @@ extern "C" int eds_se_scale_add_relu(const void* x, const float* gate, const voi
     EDS_DISPATCH_DTYPE(dtype, T, (se_scale_add_relu_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
                                      (const T*)x, gate, (const T*)residual, HW, C / 8, total, (T*)y)));
     return check_launch("se_scale_add_relu_kernel");
-}
-
-extern "C" int eds_scse_apply(const void* x, const float* cgate, const float* w_sse, float b_sse, int N, int HW,
-                              int C, void* y, int dtype, void* stream) {
-    EDS_REQUIRE(x && cgate && w_sse && y, "scse_apply: null pointer");
-    EDS_REQUIRE(C % 8 == 0 && C > 0, "scse_apply: C=%d must be a multiple of 8", C);
-    const int c8 = C / 8;
-    const int lp = c8 >= 32 ? 32 : pow2_floor(c8);
-    const int64_t n_pixels = (int64_t)N * HW;
-    const int ppb = 256 / lp;
-    EDS_DISPATCH_DTYPE(dtype, T, (scse_apply_kernel<T><<<grid_for(ceil_div64(n_pixels, ppb) * 256, 256), 256, 0,
-                                                       as_stream(stream)>>>((const T*)x, cgate, w_sse, b_sse, HW, C,
-                                                                            lp, n_pixels, (T*)y)));
-    return check_launch("scse_apply_kernel");
 }
 
 extern "C" int eds_upsample2x_concat(const void* x0, int N, int h, int w, int C0, int mode,

@@ -328,6 +328,59 @@ paste_tiles_x2_kernel(const float* __restrict__ src, int S, PasteTiles tiles, in
     }
 }
 
+// ---- opt-in: Gaussian overlap-tile blending (north_star "TTA views" bullet; NOT the reference's behaviour -- the
+// reference overwrites, tta.py:213, and that stays the default and the parity mode) -------------------------------
+// acc[gy][gx] += w * v, wsum[gy][gx] += w for ONE tile, v = the same bilinear x2 value the paste kernels write,
+// w = g[oy] * g[ox] (separable window table of length 2S, built on the host).  Tiles are accumulated by successive
+// launches in tile order, so the fp32 sums are deterministic; blend_finalize divides.
+__global__ void __launch_bounds__(256)
+blend_tile_gaussian_x2_kernel(const float* __restrict__ sp, int S, int ty0, int tx0, const float* __restrict__ g,
+                              float* __restrict__ acc, float* __restrict__ wsum, int dst_h, int dst_w) {
+    const int out = 2 * S;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int ox = blockIdx.x * kPasteBX + (tid & 63);
+    const int gx = tx0 + ox;
+    if (ox >= out || gx < 0 || gx >= dst_w) return;
+    int sx = (ox >> 1) - ((ox & 1) ? 0 : 1);
+    float a1 = (ox & 1) ? 0.25f : 0.75f;
+    if (sx < 0) { sx = 0; a1 = 0.f; }
+    if (sx >= S - 1) { sx = S - 1; a1 = 0.f; }
+    const int sx1 = min(sx + 1, S - 1);
+    const float a0 = 1.f - a1;
+    const float wx = __ldg(g + ox);
+    const int a = (blockIdx.y * kPasteBY + (tid >> 6) * 8) >> 1;
+    float h[6];
+#pragma unroll
+    for (int t = 0; t < 6; ++t) {
+        const float* row = sp + (int64_t)min(max(a - 1 + t, 0), S - 1) * S;
+        h[t] = __fadd_rn(__fmul_rn(__ldg(row + sx), a0), __fmul_rn(__ldg(row + sx1), a1));
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int oy = 2 * a + k;
+        const int gy = ty0 + oy;
+        if (oy >= out || gy < 0 || gy >= dst_h) continue;
+        const int t0 = (k >> 1) + (k & 1);
+        float b1 = (k & 1) ? 0.25f : 0.75f;
+        if (oy == 0 || oy == out - 1) b1 = 0.f;
+        const float h0 = (oy == 0) ? h[1] : h[t0];
+        const float h1 = (oy == out - 1) ? h[t0] : h[t0 + 1];
+        const float v = __fadd_rn(__fmul_rn(h0, 1.f - b1), __fmul_rn(h1, b1));
+        const float w = __fmul_rn(__ldg(g + oy), wx);
+        const int64_t idx = (int64_t)gy * dst_w + gx;
+        acc[idx] = __fadd_rn(acc[idx], __fmul_rn(w, v));
+        wsum[idx] = __fadd_rn(wsum[idx], w);
+    }
+}
+
+__global__ void blend_finalize_kernel(const float* __restrict__ acc, const float* __restrict__ wsum, int64_t n,
+                                      float* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float w = wsum[i];
+        out[i] = w > 0.f ? __fdiv_rn(acc[i], w) : 0.f;
+    }
+}
+
 struct PreLut {
     float v[3][256];
 };
@@ -449,6 +502,24 @@ extern "C" int eds_paste_tiles_owned_x2_f32(const float* src, int n_src, int fir
                                             const int* ys_host, const int* xs_host, float* dst, int dst_h, int dst_w,
                                             void* stream) {
     return paste_tiles_launch(src, n_src, first_tile, n_tiles, S, ys_host, xs_host, dst, dst_h, dst_w, stream);
+}
+
+extern "C" int eds_blend_tile_gaussian_x2_f32(const float* src, int S, int dst_y, int dst_x, const float* window,
+                                              float* acc, float* wsum, int dst_h, int dst_w, void* stream) {
+    EDS_REQUIRE(src && window && acc && wsum, "blend_tile_gaussian: null pointer");
+    EDS_REQUIRE(S >= 1 && dst_h > 0 && dst_w > 0, "blend_tile_gaussian: bad sizes");
+    dim3 block(64, 4), grid(ceil_div(2 * S, kPasteBX), ceil_div(2 * S, kPasteBY));
+    blend_tile_gaussian_x2_kernel<<<grid, block, 0, as_stream(stream)>>>(src, S, dst_y, dst_x, window, acc, wsum, dst_h,
+                                                                        dst_w);
+    return check_launch("blend_tile_gaussian_x2_kernel");
+}
+
+extern "C" int eds_blend_finalize_f32(const float* acc, const float* wsum, int64_t n, float* out, void* stream) {
+    EDS_REQUIRE(acc && wsum && out && n > 0, "blend_finalize: bad arguments");
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    blend_finalize_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(acc, wsum, n, out);
+    return check_launch("blend_finalize_kernel");
 }
 
 extern "C" int eds_preprocess_tile_u8(const uint8_t* img, int img_h, int img_w, int y0, int x0, int S,

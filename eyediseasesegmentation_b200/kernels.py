@@ -179,6 +179,33 @@ def paste_tiles_owned_x2(src: torch.Tensor, first_tile: int, dst: torch.Tensor, 
                                                   dst.shape[0], dst.shape[1], _stream()))
 
 
+def gaussian_window(S2: int, sigma_scale: float = 0.25, device=None) -> torch.Tensor:
+    """Separable blend window of the opt-in Gaussian mode: g[t] = exp(-(t - c)^2 / (2 sigma^2)), c = (S2 - 1) / 2,
+    sigma = sigma_scale * S2, evaluated in float64 and rounded once to float32."""
+    import numpy as np
+    t = np.arange(S2, dtype=np.float64)
+    g = np.exp(-((t - (S2 - 1) / 2.0) ** 2) / (2.0 * (sigma_scale * S2) ** 2)).astype(np.float32)
+    return torch.from_numpy(g).to(device) if device is not None else torch.from_numpy(g)
+
+
+def blend_tile_gaussian_x2(src: torch.Tensor, origin, window: torch.Tensor, acc: torch.Tensor, wsum: torch.Tensor) -> None:
+    """src [S,S] fp32: acc += w * up2x(src), wsum += w over the tile's window at origin (y, x); opt-in mode."""
+    _chk(src, window, acc, wsum)
+    S = src.shape[0]
+    assert src.shape == (S, S) and window.shape == (2 * S,) and acc.shape == wsum.shape and acc.dim() == 2
+    assert src.dtype == window.dtype == acc.dtype == wsum.dtype == torch.float32
+    check(_lib.lib().eds_blend_tile_gaussian_x2_f32(_p(src), S, int(origin[0]), int(origin[1]), _p(window), _p(acc),
+                                                    _p(wsum), acc.shape[0], acc.shape[1], _stream()))
+
+
+def blend_finalize(acc: torch.Tensor, wsum: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk(acc, wsum, out)
+    if out is None:
+        out = torch.empty_like(acc)
+    check(_lib.lib().eds_blend_finalize_f32(_p(acc), _p(wsum), acc.numel(), _p(out), _stream()))
+    return out
+
+
 def preprocess_tile(img: torch.Tensor, y0: int, x0: int, S: int, mean, std,
                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """img [H,W,3] u8 -> normalised half-resolution window [3,S,S] fp32."""
@@ -414,17 +441,6 @@ def se_scale_add_relu(x: torch.Tensor, gate: torch.Tensor, residual: torch.Tenso
     return out
 
 
-def scse_apply(x: torch.Tensor, cgate: torch.Tensor, w_sse: torch.Tensor, b_sse: float,
-               out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    _chk(x, cgate, w_sse, out)
-    N, H, W_, Cc = x.shape
-    if out is None:
-        out = torch.empty_like(x)
-    check(_lib.lib().eds_scse_apply(_p(x), _p(cgate), _p(w_sse), float(b_sse), N, H * W_, Cc, _p(out), _dt(x),
-                                    _stream()))
-    return out
-
-
 def upsample2x_concat(x0: torch.Tensor, skips: Sequence[torch.Tensor], mode: int,
                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _chk(x0, out, *skips)
@@ -442,37 +458,6 @@ def upsample2x_concat(x0: torch.Tensor, skips: Sequence[torch.Tensor], mode: int
     return out
 
 
-def concat_stats(x0: torch.Tensor, skips: Sequence[torch.Tensor], mode: int, w_sse: Optional[torch.Tensor],
-                 b_sse: float = 0.0, write: bool = True):
-    """Pass 1 of the two-pass SCSE: -> (concat or None, chan_mean [N,Ctot] f32, sse_logit [N,H,W] f32 or None)."""
-    _chk(x0, w_sse, *skips)
-    N, h, w, C0 = x0.shape
-    ctot = C0 + sum(s.shape[3] for s in skips)
-    up = 1 if mode == _lib.UP_NONE else 2
-    for s in skips:
-        assert s.shape[:3] == (N, up * h, up * w) and s.dtype == x0.dtype
-    dev = x0.device
-    y = torch.empty((N, up * h, up * w, ctot), dtype=x0.dtype, device=dev) if write else None
-    mean = torch.empty((N, ctot), dtype=torch.float32, device=dev)
-    logit = torch.empty((N, up * h, up * w), dtype=torch.float32, device=dev) if w_sse is not None else None
-    n = len(skips)
-    ptrs = (C.c_void_p * max(n, 1))(*[s.data_ptr() for s in skips])
-    chans = (C.c_int * max(n, 1))(*[s.shape[3] for s in skips])
-    check(_lib.lib().eds_concat_stats(_p(x0), N, h, w, C0, mode, ptrs, chans, n, _p(w_sse), float(b_sse), _p(y),
-                                      _p(mean), _p(logit), _dt(x0), _stream()))
-    return y, mean, logit
-
-
-def scse_scale(x: torch.Tensor, cgate: torch.Tensor, logit: torch.Tensor, out: Optional[torch.Tensor] = None):
-    _chk(x, cgate, logit, out)
-    N, H, W_, Cc = x.shape
-    if out is None:
-        out = torch.empty_like(x)
-    check(_lib.lib().eds_scse_scale(_p(x), _p(cgate), _p(logit), N, H * W_, Cc, _p(out), _dt(x), _stream()))
-    return out
-
-
-# ------------------------------------------------- SCSE with deferred gates (scse_gated.cu)
 def gated_stats(x: torch.Tensor, cgate: Optional[torch.Tensor], sgate: Optional[torch.Tensor],
                 w_sse: Optional[torch.Tensor], mean: torch.Tensor, c_off: int = 0, zero_mean: bool = False,
                 dot: Optional[torch.Tensor] = None, accumulate: bool = False) -> None:

@@ -101,17 +101,22 @@ def tta_patches(logdir, config, args):
         img = test_img_dir / re.sub("_" + lesion + ".tif", ".jpg", mask_path.name)
         return drv.read_rgb(img), drv.read_mask(mask_path, 0)
 
+    blend = drv.tile_blend_mode(config)
     rank, world_size = partition.world()
-    if world_size > 1:
+    if world_size > 1 and blend == "overwrite":
         # one process per GPU: (image, tile) units over the ranks, one all-reduce of the integer histograms
         produce = drv.partitioned_producer(model, transforms, ALL_MASKS, load, resize_size, mean, std)
     else:
+        # one GPU -- or the opt-in Gaussian blend, whose overlaps need every tile of an image in one place: whole
+        # images per rank, metric sums all-reduced by aucpr
+        MY_MASKS = drv.shard(ALL_MASKS)
+
         def produce():
             # decode of image k+1 runs on a background thread while the GPU works on image k
-            loaded = drv.prefetched([(lambda m=m: load(m)) for m in ALL_MASKS])
-            for mask_path, (image, gt_mask) in zip(ALL_MASKS, loaded):
+            loaded = drv.prefetched([(lambda m=m: load(m)) for m in MY_MASKS])
+            for mask_path, (image, gt_mask) in zip(MY_MASKS, loaded):
                 pred, _ = drv.infer_image_host(model, transforms, torch.from_numpy(image), torch.from_numpy(gt_mask),
-                                               resize_size, mean, std)
+                                               resize_size, mean, std, blend=blend)
                 yield pred, gt_mask, mask_path.name
 
     predict_generator = drv.CachedPredictions(produce)

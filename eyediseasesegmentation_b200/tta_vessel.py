@@ -12,7 +12,7 @@ from pathlib import Path
 import numpy as np
 import torch
 
-from . import archs
+from . import archs, partition
 from . import _driver as drv
 from ._driver import get_model, str_2_bool, smp  # noqa: F401
 from .aucpr import get_aucroc, plot_aucroc_curve
@@ -29,6 +29,8 @@ def _finish(predict_generator, logdir, config, as_float):
     optim_thres = plot_aucroc_curve(predict_generator(), Path(logdir).name, config)
     logging.info(f"Optimal threshold is {optim_thres}")
     for pred_mask, _, mask_name in predict_generator():
+        if np.asarray(pred_mask).size == 0:           # partitioned run: another rank assembles and writes this image
+            continue
         mask = (np.asarray(pred_mask) > optim_thres).astype(np.float32 if as_float else np.uint8)
         so(mask, drv.output_dir(config, logdir) / mask_name)
     logging.info("====> Finishing inference")
@@ -59,20 +61,29 @@ def test_tta(logdir, config, args):
 def tta_patches(logdir, config, args):
     test_img_dir = config["test_img_path"]
     test_mask_dir = config["test_mask_path"] / lesion_dict[config["lesion_type"]].dir_name
-    TEST_MASKS = drv.shard(sorted(test_mask_dir.glob("*.*")))
+    ALL_MASKS = sorted(test_mask_dir.glob("*.*"))
     model = drv.build_model(config, logdir, args)
     _, mean, std = archs.get_preprocessing_fn(dataset_name=config["dataset_name"], grayscale=config["gray"])
     if config["gray"]:
         raise NotImplementedError("gray=True inputs are outside the B200 hot path (3-channel stem)")
     transforms = drv.tta_transforms(args)
     resize_size = config["scale_size"]
-    dev = drv.device()
+    blend = drv.tile_blend_mode(config)
 
-    def produce():
-        for mask_path in TEST_MASKS:
-            gt_mask = drv.read_mask(mask_path, 50)
-            pred, _ = drv.infer_image_host(model, transforms, torch.from_numpy(drv.read_rgb(test_img_dir / mask_path.name)),
-                                           torch.from_numpy(gt_mask), resize_size, mean, std)
-            yield pred, gt_mask, mask_path.name
+    def load(mask_path):
+        return drv.read_rgb(test_img_dir / mask_path.name), drv.read_mask(mask_path, 50)
+
+    rank, world_size = partition.world()
+    if world_size > 1 and blend == "overwrite":          # (image, tile) units over the ranks, as in tta.tta_patches
+        produce = drv.partitioned_producer(model, transforms, ALL_MASKS, load, resize_size, mean, std)
+    else:
+        MY_MASKS = drv.shard(ALL_MASKS)
+
+        def produce():
+            loaded = drv.prefetched([(lambda m=m: load(m)) for m in MY_MASKS])
+            for mask_path, (image, gt_mask) in zip(MY_MASKS, loaded):
+                pred, _ = drv.infer_image_host(model, transforms, torch.from_numpy(image), torch.from_numpy(gt_mask),
+                                               resize_size, mean, std, blend=blend)
+                yield pred, gt_mask, mask_path.name
 
     _finish(drv.CachedPredictions(produce), logdir, config, as_float=True)

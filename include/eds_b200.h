@@ -131,6 +131,15 @@ EDS_API int eds_paste_tiles_owned_x2_f32(const float* src, int n_src, int first_
                                  const int* ys_host, const int* xs_host, float* dst, int dst_h, int dst_w,
                                  void* stream);
 
+/* OPT-IN blend mode, not the reference's behaviour (the reference overwrites, tta.py:213; overwrite stays the
+ * default and the parity mode): Gaussian-weighted accumulation of overlapping tiles.  For ONE tile src [S][S]:
+ * acc[y][x] += w * v and wsum[y][x] += w over its 2S x 2S window at (dst_y, dst_x), v = the bilinear x2 value
+ * the paste kernels write, w = window[oy] * window[ox] (device table of 2S floats).  Call once per tile in tile
+ * order (deterministic fp32 sums), then eds_blend_finalize_f32: out = acc / wsum (0 where no tile wrote). */
+EDS_API int eds_blend_tile_gaussian_x2_f32(const float* src, int S, int dst_y, int dst_x, const float* window,
+                                   float* acc, float* wsum, int dst_h, int dst_w, void* stream);
+EDS_API int eds_blend_finalize_f32(const float* acc, const float* wsum, int64_t n, float* out, void* stream);
+
 /* Sliding-window tile fetch (tta.py:201-204): window [y0,y0+2S) x [x0,x0+2S) of an
  * HWC u8 RGB image -> 2x2 box mean with round-half-up (== cv2.resize of uint8 by
  * exactly 1/2) -> x/255, -mean, /std (archs/__init__.py:88-97) -> out [3][S][S] fp32. */
@@ -202,10 +211,6 @@ EDS_API int eds_se_gate(const float* mean, int N, int C, int Cr, const float* w1
 EDS_API int eds_se_scale_add_relu(const void* x, const float* gate, const void* residual, int N, int HW,
                           int C, void* y, int dtype, void* stream);
 
-/* SCSE (smp SCSEModule): y = x * (cgate[n][c] + sigmoid(sum_c x*w_sse[c] + b_sse)). */
-EDS_API int eds_scse_apply(const void* x, const float* cgate, const float* w_sse, float b_sse, int N,
-                   int HW, int C, void* y, int dtype, void* stream);
-
 /* Decoder concat: y[N][2h][2w][C0 + sum Ci] = cat(up2x(x0), skip_1 .. skip_n) with
  * nearest or bilinear(align_corners=False) upsampling of x0 [N][h][w][C0]; with
  * EDS_UP_NONE the output is [N][h][w][...] (torch.cat of same-size maps,
@@ -214,20 +219,6 @@ EDS_API int eds_scse_apply(const void* x, const float* cgate, const float* w_sse
 EDS_API int eds_upsample2x_concat(const void* x0, int N, int h, int w, int C0, int mode,
                           const void* const* skips_host, const int* skip_channels_host,
                           int n_skips, void* y, int dtype, void* stream);
-
-/* SCSE in two streaming passes (the product path; eds_scse_apply is the one-pass form for an
- * already materialised tensor).  Pass 1: concatenate like eds_upsample2x_concat (y may be NULL
- * = statistics only) and, from the same read, produce chan_mean [N][Ctot] fp32 (global average
- * pool for cSE; zeroed inside) and sse_logit [N][H][W] fp32 = w_sse . x + b_sse (may be NULL).
- * Channels beyond 256 are split over gridDim.z (the logit is then accumulated atomically). */
-EDS_API int eds_concat_stats(const void* x0, int N, int h, int w, int C0, int mode,
-                             const void* const* skips_host, const int* skip_channels_host, int n_skips,
-                             const float* w_sse, float b_sse, void* y, float* chan_mean, float* sse_logit,
-                             int dtype, void* stream);
-
-/* Pass 2: y = x * (cgate[n][c] + sigmoid(sse_logit[n][p])); y may alias x. */
-EDS_API int eds_scse_scale(const void* x, const float* cgate, const float* sse_logit, int N, int HW, int C,
-                           void* y, int dtype, void* stream);
 
 /* 3x3 / stride 1 / pad 1 convolution for narrow outputs (Cout <= 128), same contract as
  * eds_conv2d_igemm_bf16 (bf16 NHWC in/out, w [Cout][3][3][C] with BN folded, fp32 bias, optional

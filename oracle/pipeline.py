@@ -48,10 +48,22 @@ def preprocess(img_u8: np.ndarray, mean, std) -> np.ndarray:
     return x
 
 
-def tiled_probability_map(image_u8: np.ndarray, net, S: int, mean, std, tta_kind: str) -> np.ndarray:
-    """image_u8 [H,W,3] -> float32 [H,W] exactly as tta.py:196-213 builds ``preds``."""
+def gaussian_window(S2: int, sigma_scale: float = 0.25) -> np.ndarray:
+    """Blend window of the product's OPT-IN Gaussian mode (no reference counterpart: the reference overwrites,
+    tta.py:213): g[t] = exp(-(t - c)^2 / (2 sigma^2)), c = (S2 - 1) / 2, sigma = sigma_scale * S2."""
+    t = np.arange(S2, dtype=np.float64)
+    return np.exp(-((t - (S2 - 1) / 2.0) ** 2) / (2.0 * (sigma_scale * S2) ** 2)).astype(np.float32)
+
+
+def tiled_probability_map(image_u8: np.ndarray, net, S: int, mean, std, tta_kind: str, blend: str = "overwrite") -> np.ndarray:
+    """image_u8 [H,W,3] -> float32 [H,W] exactly as tta.py:196-213 builds ``preds``.
+    ``blend="gaussian"`` restates the product's opt-in mode instead (numpy restatement only -- parity unpinned,
+    there is no reference behaviour): preds = sum_t w_t * tile_t / sum_t w_t in float32, tiles in make_grid order."""
     H, W = image_u8.shape[:2]
     preds = np.zeros((H, W), dtype=np.float32)
+    wsum = np.zeros((H, W), dtype=np.float32)
+    g = gaussian_window(2 * S)
+    w2d = (g[:, None] * g[None, :]).astype(np.float32)
     for (x1, x2, y1, y2) in make_grid((H, W), window=2 * S, min_overlap=32):
         tile = image_u8[x1:x2, y1:y2]
         tile = cv2.resize(tile, (S, S), interpolation=cv2.INTER_LINEAR)          # A.Resize(S, S)
@@ -60,7 +72,13 @@ def tiled_probability_map(image_u8: np.ndarray, net, S: int, mean, std, tta_kind
             logit = tta_mean_logits(net, t, tta_kind)[0][0]
             score = logit.sigmoid().cpu().numpy()
         score = cv2.resize(score, (2 * S, 2 * S), interpolation=cv2.INTER_LINEAR)
-        preds[x1:x2, y1:y2] = score
+        if blend == "gaussian":
+            preds[x1:x2, y1:y2] = preds[x1:x2, y1:y2] + w2d * score
+            wsum[x1:x2, y1:y2] = wsum[x1:x2, y1:y2] + w2d
+        else:
+            preds[x1:x2, y1:y2] = score
+    if blend == "gaussian":
+        preds = np.where(wsum > 0, preds / np.where(wsum > 0, wsum, 1), 0).astype(np.float32)
     return preds
 
 

@@ -199,3 +199,30 @@ def test_aucpr_callback_matches_reference_metric():
         cb.on_loader_end(runner)
         want = scoring.callback_pr_auc(y_trues, y_preds)
         assert abs(runner.loader_metrics["auc_pr"] - want) < 1e-4, (epoch, runner.loader_metrics, want)
+
+
+def test_gaussian_tile_blend_driver_matches_oracle_restatement(monkeypatch):
+    """_driver.tiled_probability_map(blend="gaussian") (opt-in; config["tile_blend"] / EDS_TILE_BLEND) against
+    oracle/pipeline.py's numpy restatement with the same network, fp32 mode: 1e-4.  Overwrite stays the default."""
+    from eyediseasesegmentation_b200 import _driver as drv
+    assert drv.tile_blend_mode({}) == "overwrite" and drv.tile_blend_mode({"tile_blend": "gaussian"}) == "gaussian"
+    with pytest.raises(ValueError):
+        drv.tile_blend_mode({"tile_blend": "pyramid"})
+    name, cfg = "unetplusplus_deepsup", dict(encoder_name="resnet34", encoder_weights=None, classes=1)
+    model = helpers.build_product_model(name, cfg)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    sd["segmentation_head.0.weight"] *= 6.0
+    model.load_state_dict(sd)
+    S = 64
+    rng = np.random.default_rng(4)
+    image = rng.integers(0, 256, size=(200, 262, 3), dtype=np.uint8)
+    mean, std = pipeline.DATASET_STATS["IDRiD"]
+    want = pipeline.tiled_probability_map(image, lambda t: nets.unetplusplus_forward(sd, t), S, mean, std, "d4",
+                                          blend="gaussian")
+    plain = pipeline.tiled_probability_map(image, lambda t: nets.unetplusplus_forward(sd, t), S, mean, std, "d4")
+    model = model.to("cuda")
+    model.precision = "fp32"
+    got = drv.tiled_probability_map(model, tta.aliases.d4_transform(), torch.from_numpy(image).cuda(), S, mean, std,
+                                    blend="gaussian").cpu().numpy()
+    assert np.abs(got - want).max() < 1e-4
+    assert np.abs(want - plain).max() > 1e-3                 # the mode does something

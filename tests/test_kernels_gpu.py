@@ -257,20 +257,6 @@ def test_se_scale_add_relu(dtype):
     assert (y.float() - ref).abs().max().item() < (1e-6 if dtype == torch.float32 else 3e-2)
 
 
-@pytest.mark.parametrize("C", [16, 32, 320, 896])
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_scse_apply(C, dtype):
-    x = rnd(2, 9, 7, C, seed=23).to(dtype)
-    cg = torch.rand(2, C, device=DEV)
-    w = rnd(C, seed=24, scale=0.1)
-    b = 0.3
-    y = K.scse_apply(x, cg, w, b)
-    xf = x.float()
-    s = torch.sigmoid((xf * w).sum(-1, keepdim=True) + b)
-    ref = xf * cg.view(2, 1, 1, C) + xf * s
-    assert (y.float() - ref).abs().max().item() < (2e-5 if dtype == torch.float32 else 4e-2)
-
-
 @pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_upsample2x_concat(mode, dtype):
@@ -500,41 +486,6 @@ def test_pr_hist_flat_regions_and_accumulate():
     tp, pp = _np_counts(prob[0], gt[0])
     assert np.array_equal(counts[0, :, 0], 2 * tp) and np.array_equal(counts[0, :, 1], 2 * pp)
     assert totals[0, 0] == 2000
-
-
-@pytest.mark.parametrize("C0,skip_ch,mode", [(32, [16, 64], 1), (128, [256, 512], 1), (64, [64], 0), (16, [], 2),
-                                             (32, [], 2), (320, [], 2), (256, [256, 256, 256], 1), (2048, [1024], 0), (64, [256], 1), (512, [512], 1)])
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_concat_stats_and_scse_scale(C0, skip_ch, mode, dtype):
-    """Two-pass SCSE == smp SCSEModule on the concatenated map."""
-    N, h, w = 2, 6, 5
-    up = 1 if mode == 2 else 2
-    x0 = rnd(N, h, w, C0, seed=60).to(dtype)
-    skips = [rnd(N, up * h, up * w, c, seed=61 + i).to(dtype) for i, c in enumerate(skip_ch)]
-    Ct = C0 + sum(skip_ch)
-    w_sse, b_sse = rnd(Ct, seed=70, scale=0.1), -0.2
-    cat, mean, logit = K.concat_stats(x0, skips, mode, w_sse, b_sse, write=True)
-    x0f = nchw(x0.float())
-    if mode == 1:
-        x0f = F.interpolate(x0f, scale_factor=2, mode="bilinear", align_corners=False)
-    elif mode == 0:
-        x0f = F.interpolate(x0f, scale_factor=2, mode="nearest")
-    ref_cat = torch.cat([nhwc(x0f)] + [s.float() for s in skips], dim=-1)
-    tol = 1e-5 if dtype == torch.float32 else 2e-2
-    assert cat.shape == ref_cat.shape and (cat.float() - ref_cat).abs().max().item() < tol
-    assert (mean - ref_cat.mean(dim=(1, 2))).abs().max().item() < 1e-4
-    assert (logit - ((ref_cat * w_sse).sum(-1) + b_sse)).abs().max().item() < 1e-3
-    # statistics-only mode on the materialised map gives the same numbers
-    _, mean2, logit2 = K.concat_stats(cat, [], 2, w_sse, b_sse, write=False)
-    assert (mean2 - cat.float().mean(dim=(1, 2))).abs().max().item() < 1e-4
-    assert (logit2 - ((cat.float() * w_sse).sum(-1) + b_sse)).abs().max().item() < 1e-3
-    cg = torch.rand(N, Ct, device=DEV)
-    y = K.scse_scale(cat, cg, logit2)
-    cf = cat.float()
-    ref = cf * cg.view(N, 1, 1, Ct) + cf * torch.sigmoid(logit2).unsqueeze(-1)
-    assert (y.float() - ref).abs().max().item() < (2e-5 if dtype == torch.float32 else 4e-2)
-    y2 = K.scse_scale(cat, cg, logit2, out=cat)   # in place
-    assert torch.equal(y2, y)
 
 
 @pytest.mark.parametrize("C0,skip_ch,mode,gated", [
@@ -904,3 +855,41 @@ def test_partitioned_group_with_emulated_ranks_equals_single_process():
         assert torch.equal(total[k][:, :W], want), k
         wh, ws = K.pr_hist(want.reshape(1, -1), gts[k][:, :W].contiguous().reshape(1, -1))
         assert torch.equal(hist[k], wh[0]) and torch.equal(strad[k], ws[0]), k
+
+
+def test_gaussian_blend_mode_matches_numpy_restatement():
+    """Opt-in Gaussian overlap-tile blending (no reference counterpart; the overwrite paste stays the default): tiles
+    accumulated in order with w = g[oy] * g[ox], then acc / wsum -- against the numpy restatement built on cv2's x2
+    resize, 1e-6 (the x2 bilinear itself agrees with cv2 to 2e-7); pixels no tile covers stay 0."""
+    import cv2
+    from eyediseasesegmentation_b200.util import make_grid
+    from oracle import pipeline
+    S = 48
+    H, W = 230, 301                                          # width not a multiple of 4
+    slices = [tuple(int(v) for v in s) for s in make_grid((H, W), window=2 * S, min_overlap=32)][:-1]   # last tile dropped
+    src = torch.rand(len(slices), S, S, device=DEV)
+    acc = torch.zeros((H, W), device=DEV)
+    wsum = torch.zeros((H, W), device=DEV)
+    window = K.gaussian_window(2 * S, device=DEV)
+    for t, (y1, _, x1, _) in enumerate(slices):
+        K.blend_tile_gaussian_x2(src[t], (y1, x1), window, acc, wsum)
+    got = K.blend_finalize(acc, wsum).cpu().numpy()
+    g = pipeline.gaussian_window(2 * S)
+    assert np.array_equal(g, window.cpu().numpy())
+    w2d = (g[:, None] * g[None, :]).astype(np.float32)
+    pa, pw = np.zeros((H, W), np.float32), np.zeros((H, W), np.float32)
+    for t, (y1, y2, x1, x2) in enumerate(slices):
+        up = cv2.resize(src[t].cpu().numpy(), (2 * S, 2 * S), interpolation=cv2.INTER_LINEAR)
+        pa[y1:y2, x1:x2] += w2d * up
+        pw[y1:y2, x1:x2] += w2d
+    want = np.where(pw > 0, pa / np.where(pw > 0, pw, 1), 0)
+    assert (pw == 0).any() and np.array_equal(got == 0, want == 0)
+    assert np.abs(got - want).max() < 1e-6
+    # seams: the blended map is continuous where the overwrite paste jumps
+    over = torch.zeros((H, W), device=DEV)
+    for t, (y1, _, x1, _) in enumerate(slices):
+        K.resize_paste(src[t], over, (0, 0, S, S), (y1, x1), (2 * S, 2 * S))
+    seam = slices[1][2]                                      # first column of the second tile
+    jump_over = (over[:2 * S - 40, seam] - over[:2 * S - 40, seam - 1]).abs().mean().item()
+    jump_blend = float(np.abs(got[:2 * S - 40, seam] - got[:2 * S - 40, seam - 1]).mean())
+    assert jump_blend < 0.5 * jump_over
