@@ -240,11 +240,12 @@ struct PasteTiles {
     int n;
 };
 
-// One thread = 4 output columns that are 16-byte ALIGNED IN dst (tile origins are arbitrary, e.g. x = 1429) x 8 output
-// rows: 6 source rows x 3-4 source columns are read (round 1: 12 scalar loads and 8 scalar stores per 8 pixels,
-// issue-bound at 1.25 TB/s), the 32 results leave as eight 128-bit stores.  Blocks that a later tile covers
-// completely return before their first load (with make_grid's overlaps that is half of all blocks).
-// grid = (ceil((2S + 3) / 256), 2S / 32, tiles in src), block = (64, 4).
+// One thread = 4 output columns that are 16-byte ALIGNED IN dst (tile origins are arbitrary, e.g. x = 1429) x
+// kPasteRows output rows: kPasteRows/2 + 2 source rows x 3-4 source columns are read (round 1: 12 scalar loads and 8
+// scalar stores per 8 pixels, issue-bound at 1.25 TB/s), the results leave as 128-bit stores.  Blocks that a
+// later tile covers completely return before their first load (with make_grid's overlaps that is half of all blocks).
+// grid = (ceil((2S + 3) / 256), ceil(2S / (4 * kPasteRows)), tiles in src), block = (64, 4).
+constexpr int kPasteRows = 16;
 __global__ void __launch_bounds__(256)
 paste_tiles_x2_kernel(const float* __restrict__ src, int S, PasteTiles tiles, int first_tile, float* __restrict__ dst,
                       int dst_h, int dst_w) {
@@ -256,15 +257,15 @@ paste_tiles_x2_kernel(const float* __restrict__ src, int S, PasteTiles tiles, in
     // aligned quads of dst columns covering [tx0, tx0 + out): quad index q -> columns gq .. gq+3
     const int gq = (tx0 & ~3) + 4 * (blockIdx.x * 64 + (tid & 63));
     if (gq >= tx0 + out || gq + 3 < tx0 || gq >= dst_w) return;
-    const int a = (blockIdx.y * kPasteBY + (tid >> 6) * 8) >> 1;      // output rows 2a .. 2a+7
-    const int gy_lo = ty0 + 2 * a;
-    if (gy_lo >= dst_h || gy_lo + 7 < 0 || 2 * a >= out) return;
+    const int a = (blockIdx.y * (4 * kPasteRows) + (tid >> 6) * kPasteRows) >> 1;      // output rows 2a .. 2a+kPasteRows-1
+    const int gy_lo = ty0 + 2 * a, gy_hi = gy_lo + kPasteRows - 1;
+    if (gy_lo >= dst_h || gy_hi < 0 || 2 * a >= out) return;
     // later tiles (last writer wins): fully covered -> nothing to do; partly covered -> per-pixel test below
     unsigned later = 0;
     for (int l = b + 1; l < tiles.n; ++l) {
         const int lx = tiles.x[l], ly = tiles.y[l];
         const bool cols_all = gq >= lx && gq + 3 < lx + out, cols_any = gq + 3 >= lx && gq < lx + out;
-        const bool rows_all = gy_lo >= ly && gy_lo + 7 < ly + out, rows_any = gy_lo + 7 >= ly && gy_lo < ly + out;
+        const bool rows_all = gy_lo >= ly && gy_hi < ly + out, rows_any = gy_hi >= ly && gy_lo < ly + out;
         if (cols_all && rows_all) return;
         if (cols_any && rows_any) later |= 1u << l;
     }
@@ -283,9 +284,10 @@ paste_tiles_x2_kernel(const float* __restrict__ src, int S, PasteTiles tiles, in
         a1[j] = f;
         a0[j] = 1.f - f;
     }
-    float h[6][4];
+    constexpr int kSrcRows = kPasteRows / 2 + 2;
+    float h[kSrcRows][4];
 #pragma unroll
-    for (int t = 0; t < 6; ++t) {
+    for (int t = 0; t < kSrcRows; ++t) {
         const float* row = sp + (int64_t)min(max(a - 1 + t, 0), S - 1) * S;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -293,7 +295,7 @@ paste_tiles_x2_kernel(const float* __restrict__ src, int S, PasteTiles tiles, in
     }
     const bool cols_inside = gq >= tx0 && gq + 3 < tx0 + out && gq + 3 < dst_w && gq >= 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < kPasteRows; ++k) {
         const int oy = 2 * a + k;
         const int gy = ty0 + oy;
         if (oy >= out || gy < 0 || gy >= dst_h) continue;
@@ -312,7 +314,7 @@ paste_tiles_x2_kernel(const float* __restrict__ src, int S, PasteTiles tiles, in
         }
         float* d = dst + (int64_t)gy * dst_w + gq;
         if (cols_inside && later == 0) {
-            *reinterpret_cast<float4*>(d) = make_float4(o[0], o[1], o[2], o[3]);
+            __stcs(reinterpret_cast<float4*>(d), make_float4(o[0], o[1], o[2], o[3]));
             continue;
         }
 #pragma unroll
@@ -488,7 +490,7 @@ static int paste_tiles_launch(const float* src, int n_src, int first_tile, int n
         tiles.y[b] = b < n_tiles ? ys_host[b] : 0;
         tiles.x[b] = b < n_tiles ? xs_host[b] : 0;
     }
-    dim3 block(64, 4), grid(ceil_div(2 * S + 3, 4 * 64), ceil_div(2 * S, kPasteBY), n_src);
+    dim3 block(64, 4), grid(ceil_div(2 * S + 3, 4 * 64), ceil_div(2 * S, 4 * kPasteRows), n_src);
     paste_tiles_x2_kernel<<<grid, block, 0, as_stream(stream)>>>(src, S, tiles, first_tile, dst, dst_h, dst_w);
     return check_launch("paste_tiles_x2_kernel");
 }
