@@ -381,12 +381,15 @@ def hist_roofline(dev, peak, peak_src):
 
 
 def blend_roofline(dev, peak, peak_src):
-    """The blend of SURVEY.md 8d: TTA merge (de-augment + mean + sigmoid over V*B logit maps) + the x2 bilinear
-    overwrite-paste of the B tiles, at the bench shape (V=8, B=6, S=1024) for the 4 lesion models of one image, back
-    to back as in a step (4 x 201 MB of logits: larger than L2, and L2 is flushed before each repetition).
-    Algorithmic bytes per tile (8d) = V*S^2*4 read + (2S)^2*4 write = 50.3 MB; x 6 tiles per launch pair."""
+    """The blend of SURVEY.md 8d: TTA de-augment + mean + sigmoid over V*B logit maps, x2 bilinear, overwrite-paste of
+    the B tiles -- ONE kernel (tta_blend_x2_kernel) at the bench shape (V=8, B=6, S=1024) for the 4 lesion models of
+    one image, back to back as in a step (4 x 201 MB of logits: larger than L2, and L2 is flushed before each
+    repetition).  Algorithmic bytes per tile (8d) = V*S^2*4 read + (2S)^2*4 write = 50.3 MB, x 6 tiles per launch.
+    `moved` = what the kernel really touches: blocks under a later tile are neither read nor written.  The
+    two-kernel form (tta_merge64 + paste_tiles_x2, the fallback for tile sizes that are not multiples of 64) and
+    the device's pure-write bandwidth (memset) are timed beside it."""
     import torch
-    from eyediseasesegmentation_b200 import kernels as K, ttach_compat as tta
+    from eyediseasesegmentation_b200 import kernels as K, partition, ttach_compat as tta
     from eyediseasesegmentation_b200.util import make_grid
     V, B, M = VIEWS, TILES, len(LESIONS)
     _, deaug = tta.view_maps(tta.aliases.d4_transform(), S, S)
@@ -397,40 +400,65 @@ def blend_roofline(dev, peak, peak_src):
     origins = [(int(x1), int(y1)) for (x1, _, y1, _) in slices]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)        # > L2
 
-    for m in range(M):
-        K.tta_merge(logits[m], deaug, True, out=prob[m])
-        K.paste_tiles_x2(prob[m], preds[m], origins)
-    torch.cuda.synchronize()
-    t_merge, t_all = [], []
-    for _ in range(5):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for m in range(M):
-            K.tta_merge(logits[m], deaug, True, out=prob[m])
-        b.record()
+    def timed(fn):
+        fn()
         torch.cuda.synchronize()
-        t_merge.append(a.elapsed_time(b) / M)
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
+        ts = []
+        for _ in range(5):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) / M)
+        return sorted(ts)[2]
+
+    def fused():
+        for m in range(M):
+            K.tta_blend_x2(logits[m], deaug, preds[m], origins)
+
+    def pair():
         for m in range(M):
             K.tta_merge(logits[m], deaug, True, out=prob[m])
             K.paste_tiles_x2(prob[m], preds[m], origins)
-        b.record()
-        torch.cuda.synchronize()
-        t_all.append(a.elapsed_time(b) / M)
-    ms_merge, ms_all = sorted(t_merge)[2], sorted(t_all)[2]
+
+    def merge_only():
+        for m in range(M):
+            K.tta_merge(logits[m], deaug, True, out=prob[m])
+
+    ms_fused, ms_pair, ms_merge = timed(fused), timed(pair), timed(merge_only)
+    big = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+    M1 = M
+    M = 1
+    ms_write = timed(lambda: big.zero_())
+    M = M1
     bytes_8d = B * (V * S * S * 4 + (2 * S) * (2 * S) * 4)
-    bytes_merge = V * B * S * S * 4 + B * S * S * 4
-    gbs = bytes_8d / (ms_all / 1e3) / 1e9
-    return {"kernel": "tta_merge64_kernel + paste_tiles_x2_kernel (the blend of one image: 6 tiles, two launches)",
+    # blocks (64 x 64 of a tile = 128 x 128 of its window) not completely under a later tile, and owned pixels
+    cells = partition.owned_cells([(y, y + 2 * S, x, x + 2 * S) for (y, x) in origins], (H, W))
+    owned_px = sum(h * w for rects in cells for (_, _, h, w) in rects)
+    live_blocks = 0
+    for t, (y, x) in enumerate(origins):
+        for by in range(0, 2 * S, 128):
+            for bx in range(0, 2 * S, 128):
+                covered = any(y + by >= ly and y + by + 128 <= ly + 2 * S and x + bx >= lx and x + bx + 128 <= lx + 2 * S
+                              for (ly, lx) in origins[t + 1:])
+                live_blocks += 0 if covered else 1
+    moved = live_blocks * 64 * 64 * 4 * V + owned_px * 4
+    gbs = bytes_8d / (ms_fused / 1e3) / 1e9
+    return {"kernel": "tta_blend_x2_kernel (views -> preds: de-augment + mean + sigmoid + x2 bilinear + ownership, one launch "
+                      "per image and lesion model)",
             "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-            "traffic": TRAFFIC["merge"]["bytes"], "traffic_source": TRAFFIC["merge"]["source"],
-            "launch_ms": ms_all, "algorithmic_bytes": bytes_8d, "launches_timed": 2 * M, "peak_source": peak_src,
+            "traffic": moved, "traffic_source": "computed: logits of the blocks not under a later tile + owned pixels written "
+                                                "(ncu: profiles/r02_blend_full.md)",
+            "launch_ms": ms_fused, "algorithmic_bytes": bytes_8d, "launches_timed": M, "peak_source": peak_src,
+            "moved_gbs": moved / (ms_fused / 1e3) / 1e9,
             "l2": "256 MB written before each repetition (flush); 4 x 201 MB of logits per repetition",
-            "merge_only": {"kernel": "tta_merge64_kernel", "ms": ms_merge, "algorithmic_bytes": bytes_merge,
-                           "achieved": bytes_merge / (ms_merge / 1e3) / 1e9, "unit": "GB/s"}}
+            "two_kernel_form": {"kernels": "tta_merge64_kernel + paste_tiles_x2_kernel", "ms": ms_pair,
+                                "achieved": bytes_8d / (ms_pair / 1e3) / 1e9, "unit": "GB/s",
+                                "merge_only_ms": ms_merge,
+                                "merge_only_gbs": (V * B * S * S * 4 + B * S * S * 4) / (ms_merge / 1e3) / 1e9},
+            "pure_write_gbs": (1 << 30) / (ms_write / 1e3) / 1e9}
 
 
 def other_configs(dev):

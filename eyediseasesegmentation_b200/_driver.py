@@ -119,6 +119,17 @@ def shard(items: Sequence, what: str = "images") -> List:
     return list(items)
 
 
+def fused_blend_views(model, transforms, S: int, dst_w: int):
+    """De-augment maps for the one-kernel blend (``eds_tta_blend_x2_f32``) when model, TTA alias, tile size and
+    canvas width qualify, else None (the drivers then merge and paste with two kernels)."""
+    if getattr(model, "forward_tta", None) is None or not tta.is_fusable(transforms):
+        return None
+    if os.environ.get("EDS_FUSED_BLEND", "1") == "0":
+        return None
+    _, deaug = tta.view_maps(transforms, S, S)
+    return deaug if K.tta_blend_supported(len(deaug), S, deaug, dst_w) else None
+
+
 def predict_probs(model, transforms, x: torch.Tensor) -> torch.Tensor:
     """x [B,3,S,S] on the device -> probabilities [B,S,S] (sigmoid of the TTA-mean logits)."""
     fused = getattr(model, "forward_tta", None)
@@ -242,11 +253,16 @@ def tiled_probability_map(model, transforms, image_dev: torch.Tensor, S: int, me
         if x1 < 0 or y1 < 0 or x2 - x1 != 2 * S or y2 - y1 != 2 * S:
             raise ValueError(f"could not broadcast input array from shape ({2 * S},{2 * S}) into shape "
                              f"({max(x2 - max(x1, 0), 0)},{max(y2 - max(y1, 0), 0)}): window larger than the image")
+    deaug = fused_blend_views(model, transforms, S, W) if blend == "overwrite" and len(slices) <= 32 else None
+    origins = [(int(x1), int(y1)) for (x1, _, y1, _) in slices]
     for i in range(0, len(slices), tiles_per_batch):
         group = slices[i:i + tiles_per_batch]
         x = torch.empty((len(group), 3, S, S), dtype=torch.float32, device=image_dev.device)
         for j, (x1, _, y1, _) in enumerate(group):
             K.preprocess_tile(image_dev, int(x1), int(y1), S, mean, std, out=x[j])
+        if deaug is not None:                         # views -> preds in one kernel, no [B,S,S] intermediate
+            K.tta_blend_x2(model.forward_tta(x, transforms, merge=False), deaug, preds, origins, first_tile=i)
+            continue
         prob = predict_probs(model, transforms, x)
         if blend == "gaussian":
             prob = prob.contiguous()
@@ -305,11 +321,17 @@ def partitioned_group(model, transforms, images, gts, S: int, mean, std, hist: t
     mine = [u for j, u in enumerate(units) if (unit_offset + j) % world_size == rank]
     canvases = [torch.zeros((int(im.shape[0]), int(g.shape[1])), dtype=torch.float32, device=dev)
                 for im, g in zip(images, gts)]
+    deaug = fused_blend_views(model, transforms, S, int(gts[0].shape[1])) if all(p.n <= 32 for p in plans) else None
     for batch in partition.batches(mine, tiles_per_batch):
         x = torch.empty((len(batch), 3, S, S), dtype=torch.float32, device=dev)
         for j, (k, t) in enumerate(batch):
             y0, x0 = plans[k].origins[t]
             K.preprocess_tile(images[k], y0, x0, S, mean, std, out=x[j])
+        if deaug is not None:
+            logits = model.forward_tta(x, transforms, merge=False)
+            for j, (k, t) in enumerate(batch):
+                K.tta_blend_x2(logits, deaug, canvases[k], plans[k].origins, first_tile=t, b0=j, n_src=1)
+            continue
         prob = predict_probs(model, transforms, x).contiguous()
         for j, (k, t) in enumerate(batch):
             K.paste_tiles_owned_x2(prob[j:j + 1], t, canvases[k], plans[k].origins)

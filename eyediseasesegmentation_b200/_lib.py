@@ -46,6 +46,8 @@ PROTOTYPES = {
     "eds_resize_paste_f32": [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "eds_paste_tiles_x2_f32": [_vp, _i, _i, C.POINTER(_i), C.POINTER(_i), _vp, _i, _i, _vp],
     "eds_paste_tiles_owned_x2_f32": [_vp, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), _vp, _i, _i, _vp],
+    "eds_tta_blend_supported": [_i, _i, C.POINTER(_i), _i],
+    "eds_tta_blend_x2_f32": [_vp, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _i, C.POINTER(_i), C.POINTER(_i), _vp, _i, _i, _vp],
     "eds_blend_tile_gaussian_x2_f32": [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
     "eds_blend_finalize_f32": [_vp, _vp, _i64, _vp, _vp],
     "eds_preprocess_tile_u8": [_vp, _i, _i, _i, _i, _i, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp, _vp],

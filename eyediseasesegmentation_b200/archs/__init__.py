@@ -160,7 +160,7 @@ class B200SegModel(nn.Module):
             return self.engine(x.device).run(x)
 
     @torch.no_grad()
-    def forward_tta(self, x: torch.Tensor, transforms, apply_sigmoid: bool = False) -> torch.Tensor:
+    def forward_tta(self, x: torch.Tensor, transforms, apply_sigmoid: bool = False, merge: bool = True) -> torch.Tensor:
         """All TTA views in one batched pass: views folded into the stem loader, merged by
         ``eds_tta_merge``.  Returns the mean logits ``[B,1,H,W]`` (what
         ``SegmentationTTAWrapper.forward`` returns) or the probabilities if apply_sigmoid.
@@ -168,7 +168,10 @@ class B200SegModel(nn.Module):
         The ~250 kernel launches of a pass are captured into a CUDA graph the second time a given
         (input shape, views, precision) is seen and replayed afterwards: at the tile-batch sizes of
         the drivers a third of the launches are shorter than their host-side issue cost, and the
-        graph removes those gaps (set EDS_CUDA_GRAPHS=0 to run eagerly)."""
+        graph removes those gaps (set EDS_CUDA_GRAPHS=0 to run eagerly).
+
+        ``merge=False`` returns the per-view logits ``[V,B,H,W]`` (view-major, still augmented) for the fused
+        blend kernel ``eds_tta_blend_x2_f32`` instead of merging them here."""
         from .. import ttach_compat as tta
         from .. import kernels as K
         B, _, H, W = x.shape
@@ -176,14 +179,15 @@ class B200SegModel(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("the B200 networks only run on a CUDA device (no CPU fallback); got a CPU tensor")
         with torch.cuda.device(x.device):
-            return self._forward_tta_on_device(x, aug, deaug, apply_sigmoid)
+            return self._forward_tta_on_device(x, aug, deaug, apply_sigmoid if merge else None)
 
     def _forward_tta_on_device(self, x, aug, deaug, apply_sigmoid):
+        # apply_sigmoid None = no merge: per-view logits
         from .. import kernels as K
         use_graph = (_graphs_enabled() and K.CONV_TRACE is None and K.KERNEL_TRACE is None and not self.engine(x.device).keep_features)
         if not use_graph:
             return self._forward_tta_eager(x, aug, deaug, apply_sigmoid)
-        key = (tuple(x.shape), str(x.device), self.precision, tuple(map(tuple, aug)), bool(apply_sigmoid))
+        key = (tuple(x.shape), str(x.device), self.precision, tuple(map(tuple, aug)), apply_sigmoid)
         entry = self._graphs.get(key)
         if entry is None:                       # first sight: eager (also warms every lazy init)
             self._graphs[key] = "warm"
@@ -202,7 +206,9 @@ class B200SegModel(nn.Module):
         static_x.copy_(x)
         graph.replay()
         K.LAUNCHES[0] += n_kernels
-        return static_y.clone()
+        # per-view logits (merge=False) are consumed by the blend kernel on this stream before the next replay:
+        # the graph's own output buffer is handed out (valid until the next call); merged maps are copied
+        return static_y if apply_sigmoid is None else static_y.clone()
 
     def _forward_tta_eager(self, x, aug, deaug, apply_sigmoid):
         from .. import kernels as K
@@ -210,6 +216,8 @@ class B200SegModel(nn.Module):
         logits = self.engine(x.device).run(x, aug)            # [V*B, classes, H, W]
         if logits.shape[1] != 1 or H != W:
             raise NotImplementedError("fused TTA merge handles square single-class maps")
+        if apply_sigmoid is None:
+            return logits.view(len(aug), B, H, W)
         merged = K.tta_merge(logits.view(len(aug), B, H, W), deaug, apply_sigmoid)
         return merged.view(B, 1, H, W)
 

@@ -226,7 +226,8 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
                 // the store that last read this staging buffer must have finished reading it
                 if (issuer) {
-                    if (p.st_bufs == 2) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(1) : "memory");
+                    if (p.st_bufs == 4) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(3) : "memory");
+                    else if (p.st_bufs == 2) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(1) : "memory");
                     else asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(0) : "memory");
                 }
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
@@ -279,7 +280,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
                         : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
-                if (p.st_bufs == 2) sbuf ^= 1;
+                sbuf = (sbuf + 1) & (p.st_bufs - 1);
             }
             // this warp's TMEM reads of the buffer are complete (tcgen05.wait::ld above)
             tc_fence_before();
@@ -438,7 +439,13 @@ static int igemm_launch(const void* x, int C0, const void* x1, int C1, int N, in
     p.st_ch = (p.block_n % 64 == 0) ? 64 : (p.block_n % 32 == 0 ? 32 : 16);
     p.st_mode = p.st_ch == 64 ? 0 : (p.st_ch == 32 ? 1 : 2);
     p.st_bytes = kTileM * p.st_ch * 2;                                 // 16 / 8 / 4 KB
-    p.st_bufs = k_iters <= 8 ? 2 : 1;      // short reductions are store-bound: overlap the bulk store with the next group
+    // short reductions are store-bound: overlap the bulk stores with the next groups (st_bufs per half in flight)
+    p.st_bufs = k_iters <= 8 ? 2 : 1;
+    {
+        static const int force = getenv("EDS_IGEMM_STBUFS") ? atoi(getenv("EDS_IGEMM_STBUFS")) : 0;
+        const int short_bufs = force ? force : 2;
+        if (k_iters <= 4 && (short_bufs == 1 || short_bufs == 2 || short_bufs == 4)) p.st_bufs = short_bufs;
+    }
     // one persistent CTA per SM: the rest of the shared memory is one TMA ring
     const int ring_budget = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/ - 2 * p.st_bufs * p.st_bytes;
     p.stages = std::max(2, std::min(kMaxStages, ring_budget / stage_bytes));

@@ -330,6 +330,208 @@ paste_tiles_x2_kernel(const float* __restrict__ src, int S, PasteTiles tiles, in
     }
 }
 
+// ---- the blend of SURVEY.md 8d in ONE kernel ------------------------------------------------------------------------
+// logits [V][Bt][S][S] -> de-augment + mean over the views + sigmoid + bilinear x2 + ownership test -> preds[H][W]:
+// tta_merge64_kernel and paste_tiles_x2_kernel fused, bit-identical to running them one after the other, without the
+// [B][S][S] probability intermediate.  One CTA = one 64 x 64 block of a tile's merged map = a 128 x 128 block of its
+// window.  Two things make it cheaper than the pair: (1) a block whose whole window area a LATER tile covers returns
+// before its first load -- with make_grid's overlaps that is half of all blocks, so half of the logits are never read;
+// (2) the merged values go to the paste through shared memory.  The x2 filter needs one merged pixel of halo around
+// the block: 260 pixels re-merged per CTA with scalar loads (+6 % of the reads, all L2 hits).
+constexpr int kBlendP = kMergeTile + 2;          // merged block + halo
+constexpr int kBlendPS = kMergeTile + 4;         // row stride of the shared tile (floats)
+
+__global__ void __launch_bounds__(512, 2)
+tta_blend_x2_kernel(const float* __restrict__ logits, int V, int Bt, int b0, int S, ViewMaps maps, PasteTiles tiles,
+                    int first_tile, float* __restrict__ dst, int dst_h, int dst_w) {
+    extern __shared__ __align__(16) float mtile[];      // [4][64][64] while merging, then the [66][68] merged tile
+    constexpr int ROWS = 2;
+    const int tid = threadIdx.x;
+    const int l16 = tid & 15, rg = tid >> 4;
+    const int b = b0 + blockIdx.z;                      // tile inside the logits batch
+    const int tl = first_tile + blockIdx.z;             // tile inside the image's tile list
+    const int I0 = blockIdx.y * kMergeTile, J0 = blockIdx.x * kMergeTile;
+    const int out = 2 * S;
+    const int ty0 = tiles.y[tl], tx0 = tiles.x[tl];
+    // window area of this block in dst; later tiles that cover it completely / partly
+    const int by0 = ty0 + 2 * I0, bx0 = tx0 + 2 * J0;
+    unsigned later = 0;
+    for (int l = tl + 1; l < tiles.n; ++l) {
+        const int lx = tiles.x[l], ly = tiles.y[l];
+        if (bx0 >= lx && bx0 + 2 * kMergeTile <= lx + out && by0 >= ly && by0 + 2 * kMergeTile <= ly + out) return;
+        if (bx0 + 2 * kMergeTile > lx && bx0 < lx + out && by0 + 2 * kMergeTile > ly && by0 < ly + out) later |= 1u << l;
+    }
+    if (by0 >= dst_h || bx0 >= dst_w || by0 + 2 * kMergeTile <= 0 || bx0 + 2 * kMergeTile <= 0) return;
+
+    // ---- merge of the 64 x 64 block: the body of tta_merge64_kernel<2, 2>
+    constexpr int RSTEP = kMergeTile / ROWS;
+    float4 acc[ROWS];
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        if (g * 4 >= V) break;
+        float4 val[4][ROWS];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int v = g * 4 + u;
+            if (v >= V) continue;
+            const int* m = maps.m[v];
+            const float* src = logits + ((int64_t)v * Bt + b) * S * S;
+            if (m[1] == 0) {
+                const float* p = src + (m[4] > 0 ? J0 + 4 * l16 + m[5] : m[5] - J0 - 4 * l16 - 3);
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r)
+                    val[u][r] = __ldg(reinterpret_cast<const float4*>(p + (int64_t)(m[0] * (I0 + rg + RSTEP * r) + m[2]) * S));
+            } else {
+                const int row0 = m[1] > 0 ? J0 + m[2] : m[2] - J0 - (kMergeTile - 1);
+                const int col0 = m[3] > 0 ? I0 + m[5] : m[5] - I0 - (kMergeTile - 1);
+                const float* p = src + (int64_t)(row0 + rg) * S + col0 + 4 * l16;
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r)
+                    val[u][r] = __ldg(reinterpret_cast<const float4*>(p + (int64_t)(RSTEP * r) * S));
+            }
+        }
+        if (g) __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int v = g * 4 + u;
+            if (v >= V || maps.m[v][1] == 0) continue;
+            const int* m = maps.m[v];
+            float* t = mtile + u * kMergeTile * kMergeTile;
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                const int q = rg + RSTEP * r;
+                const int jl = m[1] > 0 ? q : kMergeTile - 1 - q;
+                const float e[4] = {val[u][r].x, val[u][r].y, val[u][r].z, val[u][r].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int il = m[3] > 0 ? 4 * l16 + k : kMergeTile - 1 - 4 * l16 - k;
+                    t[il * kMergeTile + (jl ^ merge_swz(il))] = e[k];
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int v = g * 4 + u;
+            if (v >= V) continue;
+            const int* m = maps.m[v];
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                float4 x = val[u][r];
+                if (m[1] == 0) {
+                    if (m[4] < 0) x = make_float4(x.w, x.z, x.y, x.x);
+                } else {
+                    const int il = rg + RSTEP * r;
+                    const float4 w = *reinterpret_cast<const float4*>(mtile + u * kMergeTile * kMergeTile +
+                                                                      il * kMergeTile + ((l16 ^ ((il >> 2) & 7)) << 2));
+                    x = (il & 32) ? make_float4(w.z, w.w, w.x, w.y) : w;
+                }
+                if (v == 0) acc[r] = x;
+                else { acc[r].x += x.x; acc[r].y += x.y; acc[r].z += x.z; acc[r].w += x.w; }
+            }
+        }
+    }
+    __syncthreads();                                    // every read of the transposition tiles is done: reuse the space
+    float* P = mtile;                                   // P[(i - I0 + 1) * kBlendPS + (j - J0 + 1)]
+    const float fv = (float)V;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        float4 o = make_float4(acc[r].x / fv, acc[r].y / fv, acc[r].z / fv, acc[r].w / fv);
+        o = make_float4(sigmoidf_acc(o.x), sigmoidf_acc(o.y), sigmoidf_acc(o.z), sigmoidf_acc(o.w));
+        float* pr = P + (rg + RSTEP * r + 1) * kBlendPS + 4 * l16 + 1;
+        pr[0] = o.x; pr[1] = o.y; pr[2] = o.z; pr[3] = o.w;
+    }
+    // halo ring: rows I0-1 and I0+64 (66 pixels each), columns J0-1 and J0+64 (64 each); same sum order, same
+    // division and sigmoid as above, so a halo pixel equals the value its own block computes
+    if (tid < 2 * kBlendP + 2 * kMergeTile) {
+        int li, lj;                                      // position in P
+        if (tid < 2 * kBlendP) { li = tid < kBlendP ? 0 : kBlendP - 1; lj = tid % kBlendP; }
+        else { const int t = tid - 2 * kBlendP; lj = t < kMergeTile ? 0 : kBlendP - 1; li = 1 + t % kMergeTile; }
+        const int i = I0 + li - 1, j = J0 + lj - 1;
+        if (i >= 0 && i < S && j >= 0 && j < S) {
+            float sum = 0.f;
+            for (int v = 0; v < V; ++v) {
+                const int* m = maps.m[v];
+                const float x = __ldg(logits + ((int64_t)v * Bt + b) * S * S + (int64_t)(m[0] * i + m[1] * j + m[2]) * S +
+                                      (m[3] * i + m[4] * j + m[5]));
+                sum = v == 0 ? x : sum + x;
+            }
+            P[li * kBlendPS + lj] = sigmoidf_acc(sum / fv);
+        }
+    }
+    __syncthreads();
+
+    // ---- x2 bilinear + ownership + store: paste_tiles_x2_kernel on the shared tile.  Items = (aligned quad of dst
+    // columns, group of 8 output rows): 33 quads cover the 128 columns whatever the alignment of tx0.
+    const int aq0 = bx0 & ~3;
+    const int n_quads = (bx0 & 3) ? 33 : 32;
+    for (int item = tid; item < n_quads * 16; item += 512) {
+        const int q = item % n_quads, rgo = item / n_quads;
+        const int gq = aq0 + 4 * q;
+        if (gq >= dst_w || gq + 3 < 0) continue;
+        const int a = I0 + rgo * 4;                      // output rows 2a .. 2a+7 of the tile
+        const int gy_lo = ty0 + 2 * a;
+        if (gy_lo >= dst_h || gy_lo + 7 < 0) continue;
+        int lsx[4], lsx1[4];
+        float a0[4], a1[4];
+        bool col_ok[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int oxr = gq + j - tx0;                // column inside the tile's window
+            col_ok[j] = oxr >= 2 * J0 && oxr < 2 * J0 + 2 * kMergeTile && gq + j >= 0 && gq + j < dst_w;
+            const int ox = min(max(oxr, 2 * J0), 2 * J0 + 2 * kMergeTile - 1);
+            int c = (ox >> 1) - ((ox & 1) ? 0 : 1);
+            float f = (ox & 1) ? 0.25f : 0.75f;
+            if (c < 0) { c = 0; f = 0.f; }
+            if (c >= S - 1) { c = S - 1; f = 0.f; }
+            lsx[j] = c - J0 + 1;
+            lsx1[j] = min(c + 1, S - 1) - J0 + 1;
+            a1[j] = f;
+            a0[j] = 1.f - f;
+        }
+        float h[6][4];
+#pragma unroll
+        for (int t = 0; t < 6; ++t) {
+            const float* row = P + (min(max(a - 1 + t, 0), S - 1) - I0 + 1) * kBlendPS;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) h[t][j] = __fadd_rn(__fmul_rn(row[lsx[j]], a0[j]), __fmul_rn(row[lsx1[j]], a1[j]));
+        }
+        const bool quad_inside = col_ok[0] && col_ok[1] && col_ok[2] && col_ok[3];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int oy = 2 * a + k;
+            const int gy = ty0 + oy;
+            if (gy < 0 || gy >= dst_h) continue;
+            const int t0 = (k >> 1) + (k & 1);
+            float b1 = (k & 1) ? 0.25f : 0.75f;
+            if (oy == 0 || oy == out - 1) b1 = 0.f;
+            const float bb0 = 1.f - b1;
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float h0 = (oy == 0) ? h[1][j] : h[t0][j];
+                const float h1 = (oy == out - 1) ? h[t0][j] : h[t0 + 1][j];
+                o[j] = __fadd_rn(__fmul_rn(h0, bb0), __fmul_rn(h1, b1));
+            }
+            float* d = dst + (int64_t)gy * dst_w + gq;
+            if (quad_inside && later == 0) {
+                __stcs(reinterpret_cast<float4*>(d), make_float4(o[0], o[1], o[2], o[3]));
+                continue;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                bool owned = col_ok[j];
+                const int gx = gq + j;
+                for (unsigned mm = later; mm; mm &= mm - 1) {
+                    const int l = __ffs(mm) - 1;
+                    owned = owned && !(gy >= tiles.y[l] && gy < tiles.y[l] + out && gx >= tiles.x[l] && gx < tiles.x[l] + out);
+                }
+                if (owned) d[j] = o[j];
+            }
+        }
+    }
+}
+
 // ---- opt-in: Gaussian overlap-tile blending (north_star "TTA views" bullet; NOT the reference's behaviour -- the
 // reference overwrites, tta.py:213, and that stays the default and the parity mode) -------------------------------
 // acc[gy][gx] += w * v, wsum[gy][gx] += w for ONE tile, v = the same bilinear x2 value the paste kernels write,
@@ -417,32 +619,44 @@ __global__ void preprocess_tile_kernel(const uint8_t* __restrict__ img, int img_
 
 using namespace eds;
 
+static int check_view_maps(const int* view_maps_host, int V, int S, ViewMaps* maps, const char* what) {
+    for (int v = 0; v < V; ++v) {
+        const int* m = view_maps_host + v * 6;
+        // a signed permutation with offsets that keeps [0,S)^2 inside [0,S)^2
+        const bool straight = m[1] == 0 && m[3] == 0 && (m[0] == 1 || m[0] == -1) && (m[4] == 1 || m[4] == -1);
+        const bool swapped = m[0] == 0 && m[4] == 0 && (m[1] == 1 || m[1] == -1) && (m[3] == 1 || m[3] == -1);
+        EDS_REQUIRE(straight || swapped, "%s: view %d map is not a flip/rot90", what, v);
+        for (int corner = 0; corner < 4; ++corner) {
+            const int i = (corner & 1) ? S - 1 : 0, j = (corner & 2) ? S - 1 : 0;
+            const int r = m[0] * i + m[1] * j + m[2], c = m[3] * i + m[4] * j + m[5];
+            EDS_REQUIRE(r >= 0 && r < S && c >= 0 && c < S, "%s: view %d map leaves the tile", what, v);
+        }
+        for (int q = 0; q < 6; ++q) maps->m[v][q] = m[q];
+    }
+    return EDS_OK;
+}
+
+// 16-byte vector loads of the 64 x 64 merge need S % 64 == 0 and column offsets that keep them aligned
+static bool merge_vector_ok(const ViewMaps& maps, int V, int S, const void* a, const void* b) {
+    bool vec = S % kMergeTile == 0 && (((uintptr_t)a | (uintptr_t)b) & 15) == 0;
+    for (int v = 0; v < V && vec; ++v) {
+        const int* m = maps.m[v];
+        const int step = m[1] == 0 ? m[4] : m[3];
+        vec = step > 0 ? m[5] % 4 == 0 : (m[5] + 1) % 4 == 0;
+    }
+    return vec;
+}
+
+
 extern "C" int eds_tta_merge(const float* logits, int V, int B, int S, const int* view_maps_host,
                              int apply_sigmoid, float* prob, void* stream) {
     EDS_REQUIRE(logits && prob && view_maps_host, "tta_merge: null pointer");
     EDS_REQUIRE(V >= 1 && V <= 8, "tta_merge: V=%d not in 1..8", V);
     EDS_REQUIRE(B >= 1 && B <= 65535 && S >= 1, "tta_merge: bad B=%d S=%d", B, S);
     ViewMaps maps;
-    for (int v = 0; v < V; ++v) {
-        const int* m = view_maps_host + v * 6;
-        // a signed permutation with offsets that keeps [0,S)^2 inside [0,S)^2
-        const bool straight = m[1] == 0 && m[3] == 0 && (m[0] == 1 || m[0] == -1) && (m[4] == 1 || m[4] == -1);
-        const bool swapped = m[0] == 0 && m[4] == 0 && (m[1] == 1 || m[1] == -1) && (m[3] == 1 || m[3] == -1);
-        EDS_REQUIRE(straight || swapped, "tta_merge: view %d map is not a flip/rot90", v);
-        for (int corner = 0; corner < 4; ++corner) {
-            const int i = (corner & 1) ? S - 1 : 0, j = (corner & 2) ? S - 1 : 0;
-            const int r = m[0] * i + m[1] * j + m[2], c = m[3] * i + m[4] * j + m[5];
-            EDS_REQUIRE(r >= 0 && r < S && c >= 0 && c < S, "tta_merge: view %d map leaves the tile", v);
-        }
-        for (int q = 0; q < 6; ++q) maps.m[v][q] = m[q];
-    }
+    if (int rc = check_view_maps(view_maps_host, V, S, &maps, "tta_merge")) return rc;
     // 64x64 vector kernel when the tile size and every column offset keep the 16-byte loads aligned
-    bool vec = S % kMergeTile == 0 && (((uintptr_t)logits | (uintptr_t)prob) & 15) == 0;
-    for (int v = 0; v < V && vec; ++v) {
-        const int* m = maps.m[v];
-        const int step = m[1] == 0 ? m[4] : m[3];
-        vec = step > 0 ? m[5] % 4 == 0 : (m[5] + 1) % 4 == 0;
-    }
+    const bool vec = merge_vector_ok(maps, V, S, logits, prob);
     static const bool force_scalar = getenv("EDS_MERGE_SCALAR") && atoi(getenv("EDS_MERGE_SCALAR")) != 0;
     if (vec && !force_scalar) {
         const int smem = 4 * kMergeTile * kMergeTile * (int)sizeof(float);
@@ -504,6 +718,43 @@ extern "C" int eds_paste_tiles_owned_x2_f32(const float* src, int n_src, int fir
                                             const int* ys_host, const int* xs_host, float* dst, int dst_h, int dst_w,
                                             void* stream) {
     return paste_tiles_launch(src, n_src, first_tile, n_tiles, S, ys_host, xs_host, dst, dst_h, dst_w, stream);
+}
+
+extern "C" int eds_tta_blend_supported(int V, int S, const int* view_maps_host, int dst_w) {
+    if (V < 1 || V > 8 || S < kMergeTile || !view_maps_host || dst_w % 4 != 0) return 0;
+    ViewMaps maps;
+    if (check_view_maps(view_maps_host, V, S, &maps, "tta_blend") != EDS_OK) return 0;
+    return merge_vector_ok(maps, V, S, nullptr, nullptr) ? 1 : 0;
+}
+
+extern "C" int eds_tta_blend_x2_f32(const float* logits, int V, int Bt, int b0, int n_src, int S,
+                                    const int* view_maps_host, int first_tile, int n_tiles, const int* ys_host,
+                                    const int* xs_host, float* dst, int dst_h, int dst_w, void* stream) {
+    EDS_REQUIRE(logits && dst && view_maps_host && ys_host && xs_host, "tta_blend: null pointer");
+    EDS_REQUIRE(V >= 1 && V <= 8, "tta_blend: V=%d not in 1..8", V);
+    EDS_REQUIRE(Bt >= 1 && b0 >= 0 && n_src >= 1 && b0 + n_src <= Bt && n_src <= 65535, "tta_blend: tiles %d..%d outside "
+                "the batch of %d", b0, b0 + n_src - 1, Bt);
+    EDS_REQUIRE(n_tiles >= 1 && n_tiles <= kPasteMaxTiles && first_tile >= 0 && first_tile + n_src <= n_tiles,
+                "tta_blend: tiles %d..%d outside the list of %d (max %d)", first_tile, first_tile + n_src - 1, n_tiles,
+                kPasteMaxTiles);
+    ViewMaps maps;
+    if (int rc = check_view_maps(view_maps_host, V, S, &maps, "tta_blend")) return rc;
+    EDS_REQUIRE(dst_w % 4 == 0 && merge_vector_ok(maps, V, S, logits, dst),
+                "tta_blend: needs S %% 64 == 0, dst_w %% 4 == 0 and 16-byte aligned buffers (use eds_tta_merge + "
+                "eds_paste_tiles_x2_f32 otherwise; eds_tta_blend_supported tells)");
+    PasteTiles tiles;
+    tiles.n = n_tiles;
+    for (int b = 0; b < kPasteMaxTiles; ++b) {
+        tiles.y[b] = b < n_tiles ? ys_host[b] : 0;
+        tiles.x[b] = b < n_tiles ? xs_host[b] : 0;
+    }
+    const int smem = 4 * kMergeTile * kMergeTile * (int)sizeof(float);
+    static PerDevice once;
+    if (int rc = smem_opt_in(once, tta_blend_x2_kernel, smem, "tta_blend")) return rc;
+    dim3 grid(S / kMergeTile, S / kMergeTile, n_src);
+    tta_blend_x2_kernel<<<grid, 512, smem, as_stream(stream)>>>(logits, V, Bt, b0, S, maps, tiles, first_tile, dst, dst_h,
+                                                              dst_w);
+    return check_launch("tta_blend_x2_kernel");
 }
 
 extern "C" int eds_blend_tile_gaussian_x2_f32(const float* src, int S, int dst_y, int dst_x, const float* window,

@@ -179,6 +179,27 @@ def paste_tiles_owned_x2(src: torch.Tensor, first_tile: int, dst: torch.Tensor, 
                                                   dst.shape[0], dst.shape[1], _stream()))
 
 
+def tta_blend_supported(V: int, S: int, deaug_maps, dst_w: int) -> bool:
+    flat = _lib.int_array([v for m in deaug_maps for v in m])
+    return bool(_lib.load().eds_tta_blend_supported(int(V), int(S), flat, int(dst_w)))
+
+
+def tta_blend_x2(logits: torch.Tensor, deaug_maps, dst: torch.Tensor, origins, first_tile: int = 0, b0: int = 0,
+                 n_src: Optional[int] = None) -> None:
+    """logits [V,Bt,S,S] fp32 -> de-augment + mean + sigmoid + bilinear x2 + overwrite-paste of tiles b0 .. b0+n_src-1
+    of the batch (= tiles first_tile .. of the image's list ``origins``) into dst [H,W], one launch; only the
+    pixels no later tile of the list covers are written (and only the blocks that own some are read)."""
+    _chk(logits, dst)
+    V, Bt, S, S2 = logits.shape
+    assert S == S2 and logits.dtype == torch.float32 and dst.dtype == torch.float32 and dst.dim() == 2
+    n_src = Bt - b0 if n_src is None else n_src
+    flat = _lib.int_array([v for m in deaug_maps for v in m])
+    ys = _lib.int_array([int(o[0]) for o in origins])
+    xs = _lib.int_array([int(o[1]) for o in origins])
+    check(_lib.lib().eds_tta_blend_x2_f32(_p(logits), V, Bt, b0, n_src, S, flat, first_tile, len(origins), ys, xs,
+                                          _p(dst), dst.shape[0], dst.shape[1], _stream()))
+
+
 def gaussian_window(S2: int, sigma_scale: float = 0.25, device=None) -> torch.Tensor:
     """Separable blend window of the opt-in Gaussian mode: g[t] = exp(-(t - c)^2 / (2 sigma^2)), c = (S2 - 1) / 2,
     sigma = sigma_scale * S2, evaluated in float64 and rounded once to float32."""

@@ -131,6 +131,17 @@ EDS_API int eds_paste_tiles_owned_x2_f32(const float* src, int n_src, int first_
                                  const int* ys_host, const int* xs_host, float* dst, int dst_h, int dst_w,
                                  void* stream);
 
+/* The blend of one batch of tiles in ONE kernel: eds_tta_merge (with sigmoid) followed by
+ * eds_paste_tiles_owned_x2_f32, bit-identical to that pair, without the [B][S][S] intermediate; blocks that a later
+ * tile covers completely are never read.  logits: [V][Bt][S][S]; the n_src tiles b0 .. b0+n_src-1 of that batch are
+ * the tiles first_tile .. first_tile+n_src-1 of the image's list (ys/xs: all n_tiles origins, make_grid order).
+ * Needs S % 64 == 0, dst_w % 4 == 0 and view offsets that keep 16-byte loads aligned (every flip / rot90 of a
+ * square tile does): eds_tta_blend_supported() returns 1 when the arguments qualify. */
+EDS_API int eds_tta_blend_supported(int V, int S, const int* view_maps_host, int dst_w);
+EDS_API int eds_tta_blend_x2_f32(const float* logits, int V, int Bt, int b0, int n_src, int S,
+                         const int* view_maps_host, int first_tile, int n_tiles, const int* ys_host,
+                         const int* xs_host, float* dst, int dst_h, int dst_w, void* stream);
+
 /* OPT-IN blend mode, not the reference's behaviour (the reference overwrites, tta.py:213; overwrite stays the
  * default and the parity mode): Gaussian-weighted accumulation of overlapping tiles.  For ONE tile src [S][S]:
  * acc[y][x] += w * v and wsum[y][x] += w over its 2S x 2S window at (dst_y, dst_x), v = the bilinear x2 value
