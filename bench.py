@@ -171,6 +171,11 @@ def run_b200(args):
     pinned_scores = torch.empty((len(LESIONS), n_set, 2 + 2 * 19 + 2), dtype=torch.float64).pin_memory()
     allreduce_ms = []
 
+    # images whose (image, tile) units are dealt together: the whole set while its canvases fit comfortably (the
+    # units then balance to within one tile per rank and the batches have one shape); the file drivers use
+    # groups of `world` images because they decode and broadcast as they go
+    group_size = args.group if args.group > 0 else (n_set if n_set <= 64 else world)
+
     def run_set(count, host):
         """`count` images of the set (strong scaling: the same images for every N), (image, tile) units over
         the ranks in groups of `world` images.  host=False: inputs resident in HBM, results stay on the device
@@ -178,8 +183,8 @@ def run_b200(args):
         probability maps and the scores go back to pinned host memory (e2e)."""
         hist = torch.zeros((len(LESIONS), count, 2, _lib.PR_BINS), dtype=torch.int32, device=dev)
         strad = torch.zeros((len(LESIONS), count, _lib.PR_NTHRESH, 2), dtype=torch.int32, device=dev)
-        for g in range(0, count, world):
-            group = list(range(g, min(g + world, count)))
+        for g in range(0, count, group_size):
+            group = list(range(g, min(g + group_size, count)))
             if host:
                 imgs = [host_imgs[i].to(dev, non_blocking=True) for i in group]
                 gts = {les: [host_masks[i][les].to(dev, non_blocking=True) for i in group] for les in LESIONS}
@@ -192,8 +197,8 @@ def run_b200(args):
                 if host:
                     for r, i in enumerate(group):
                         if world > 1:
-                            dist.reduce(canvases[r], dst=r, op=dist.ReduceOp.SUM)     # pieces -> the writer rank
-                        if r == rank:
+                            dist.reduce(canvases[r], dst=i % world, op=dist.ReduceOp.SUM)   # pieces -> the writer rank
+                        if i % world == rank:
                             pinned_out[les][(i // world) % 2].copy_(canvases[r], non_blocking=True)
         if world > 1:                              # the path's single data collective: per-image integer histograms
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -223,8 +228,8 @@ def run_b200(args):
         so that no CUDA graph is captured inside a timed region."""
         sizes = set()
         for count in {args.steps, args.warmup}:
-            for g in range(0, count, world):
-                n_units = (min(g + world, count) - g) * TILES
+            for g in range(0, count, group_size):
+                n_units = (min(g + group_size, count) - g) * TILES
                 mine = [u for u in range(n_units) if (g * TILES + u) % world == rank]
                 sizes |= {len(b) for b in partition.batches(mine, args.tiles)}
         for les in LESIONS:
@@ -294,7 +299,7 @@ def run_b200(args):
                              "the set is distinct",
                        "parallelism": f"(image, tile) units round-robin over {world} rank(s); ONE all-reduce of the "
                                       f"per-image integer histograms [4 x {args.steps} x 2 x {_lib.PR_BINS}] int32",
-                       "allreduce_ms": ar_ms, "mean_ap_per_lesion": ap_mean},
+                       "images_per_group": group_size, "allreduce_ms": ar_ms, "mean_ap_per_lesion": ap_mean},
             "e2e": {"value": e2e, "unit": "images/s",
                     "h2d_bytes_per_step": world * (H * W * 3 + len(LESIONS) * H * W),
                     "d2h_bytes_per_step": len(LESIONS) * (H * W * 4 + 42 * 8),
@@ -689,6 +694,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tiles", type=int, default=6, help="tiles per forward batch (x8 views)")
+    ap.add_argument("--group", type=int, default=0, help="images per unit-dealing group (0 = the whole set)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the cfg-1 / cfg-2 / cfg-5 side measurements")
     args = ap.parse_args()

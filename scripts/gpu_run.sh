@@ -1,16 +1,18 @@
-set -x
 cd $GRAFT_REPO_ROOT
-nvidia-smi -L
-python -m pytest tests -m gpu -q -x > gpurun_out/r02_gpu_multi.log 2>&1; tail -6 gpurun_out/r02_gpu_multi.log
-python scripts/dev_hist_probe.py uniform network saturated trained flat > gpurun_out/r02_hist_probe5.log 2>&1; tail -6 gpurun_out/r02_hist_probe5.log
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 6 --warmup 4 > gpurun_out/r02_bench_2gpu.json 2> gpurun_out/r02_bench_2gpu.err; python - <<'P'
+nvidia-smi -L | wc -l
+for n in 8 4 2; do
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 20 --warmup 5 > gpurun_out/r02_scale_${n}gpu.json 2> gpurun_out/r02_scale_${n}gpu.err
+tail -2 gpurun_out/r02_scale_${n}gpu.err
+done
+python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extra > gpurun_out/r02_scale_1gpu.json 2> gpurun_out/r02_scale_1gpu.err
+python - <<'P'
 import json
-d=json.load(open('gpurun_out/r02_bench_2gpu.json'))
-print({k:d[k] for k in ['value','ms_per_step','n_gpus','steps','scaling','gpu_launches']}, d['e2e']['value'], d['config']['allreduce_ms'])
-P
-tail -5 gpurun_out/r02_bench_2gpu.err
-python bench.py --steps 6 --warmup 4 --no-cpu-baseline --no-extra > gpurun_out/r02_bench_1gpu_s6.json 2> gpurun_out/r02_bench_1gpu_s6.err; python - <<'P'
-import json
-d=json.load(open('gpurun_out/r02_bench_1gpu_s6.json'))
-print({k:d[k] for k in ['value','ms_per_step','n_gpus','steps','scaling','gpu_launches']}, d['e2e']['value'], d['roofline_hist']['frac'], d['roofline_blend']['frac'])
+base=None
+for n in (1,2,4,8):
+    try:
+        d=json.load(open(f'gpurun_out/r02_scale_{n}gpu.json'))
+    except Exception as e:
+        print(n, 'failed', e); continue
+    if n==1: base=d['value']
+    print(n, round(d['value'],3), 'e2e', round(d['e2e']['value'],3), 'ms/step', round(d['ms_per_step'],1), 'allreduce_ms', d['config']['allreduce_ms'], 'eff', round(d['value']/(n*base),3) if base else None, d['clocks'])
 P
