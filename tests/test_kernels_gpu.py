@@ -885,8 +885,9 @@ def test_gaussian_blend_mode_matches_numpy_restatement():
     want = np.where(pw > 0, pa / np.where(pw > 0, pw, 1), 0)
     assert (pw == 0).any() and np.array_equal(got == 0, want == 0)
     assert np.abs(got - want).max() < 1e-6
-    # seams: with constant tiles of different levels the overwrite paste jumps by the level difference at a tile
-    # edge, the blended map changes by a small fraction of it per pixel
+    # seams: with constant tiles of different levels the overwrite paste jumps by the whole level difference at a
+    # tile edge; the blended map moves by the entering tile's share of the weight there (the window still has
+    # exp(-2) = 14 % of its peak at the edge, so about a quarter of the difference)
     flat = torch.stack([torch.full((S, S), 0.2 * (t + 1), device=DEV) for t in range(len(slices))])
     over = torch.zeros((H, W), device=DEV)
     acc.zero_()
@@ -898,7 +899,7 @@ def test_gaussian_blend_mode_matches_numpy_restatement():
     seam = slices[1][2]                                      # first column of the second tile
     jump_over = (over[:40, seam] - over[:40, seam - 1]).abs().mean().item()
     jump_blend = (smooth[:40, seam] - smooth[:40, seam - 1]).abs().mean().item()
-    assert jump_over > 0.19 and jump_blend < 0.1 * jump_over
+    assert jump_over > 0.19 and jump_blend < 0.5 * jump_over
 
 
 @pytest.mark.parametrize("alias,S,shape", [("d4_transform", 64, (300, 420)), ("flip_transform", 128, (400, 612)),
