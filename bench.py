@@ -44,8 +44,8 @@ TRAFFIC = {
     "conv": {"bytes": 1116.27e6 + 251.76e6, "source": "profiles/r01_kernels_full.md #0 (conv_igemm 1024->256 @256^2 x8: "
              "1074 MB algorithmic)"},
     "hist": {"bytes": 1653.80e6 + 4.69e6, "source": "profiles/r02_hist_full.md #0 (27 images, 1648.7 MB algorithmic)"},
-    "merge": {"bytes": 201.37e6 + 20.13e6, "source": "profiles/r02_blend_full.md #0 (tta_merge64: 226.5 MB algorithmic; the "
-              "x2 paste reads the merged tiles from L2 and writes 48.8 MB)"},
+    "blend": {"bytes": 108.50e6 + 18.03e6, "source": "profiles/r02_blend_fused_full.md #0 (tta_blend_x2: blocks under a later "
+              "tile are not read; most of the 48.8 MB of stores are still in L2 when the kernel ends)"},
 }
 
 
@@ -454,8 +454,8 @@ def blend_roofline(dev, peak, peak_src):
     return {"kernel": "tta_blend_x2_kernel (views -> preds: de-augment + mean + sigmoid + x2 bilinear + ownership, one launch "
                       "per image and lesion model)",
             "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-            "traffic": moved, "traffic_source": "computed: logits of the blocks not under a later tile + owned pixels written "
-                                                "(ncu: profiles/r02_blend_full.md)",
+            "traffic": TRAFFIC["blend"]["bytes"], "traffic_source": TRAFFIC["blend"]["source"],
+            "moved_bytes": moved, "moved_note": "computed: logits of the blocks not under a later tile + owned pixels written",
             "launch_ms": ms_fused, "algorithmic_bytes": bytes_8d, "launches_timed": M, "peak_source": peak_src,
             "moved_gbs": moved / (ms_fused / 1e3) / 1e9,
             "l2": "256 MB written before each repetition (flush); 4 x 201 MB of logits per repetition",

@@ -10,6 +10,8 @@
 //
 // Data layout: hist [n_images][2][EDS_PR_BINS] u32 (class-major so the positive and
 // negative rows are contiguous for the scan), straddle [n_images][19][2] u32.
+// Kernels: pr_hist_kernel (whole images, one persistent wave, 0.79 of the HBM peak on B200),
+// pr_hist_rects_kernel (the rectangles one rank owns under the (image, tile) partition), pr_scan_kernel.
 #include "common.cuh"
 #include <cmath>
 #include <cstring>

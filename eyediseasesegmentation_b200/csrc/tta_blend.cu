@@ -6,8 +6,11 @@
 //   - cv2.resize(..., INTER_LINEAR) + `preds[x1:x2, y1:y2] = tile` (tta.py:211-213)
 //     and center_crop + GF.resize (tta.py:117-119);
 //   - dataset.read(window) + A.Resize + preprocessing_fn + ToTensorV2 (tta.py:201-204).
-// All three are HBM-bound streaming kernels; the flip / rot90 views are never
-// materialised, they are index maps applied while reading.
+// All are HBM-bound streaming kernels; the flip / rot90 views are never materialised, they are index maps applied
+// while reading.  tta_blend_x2_kernel does merge + sigmoid + x2 + overwrite-paste in one pass (the product path for
+// tile sizes that are multiples of 64); tta_merge*_kernel / paste_tiles_x2_kernel / resize_paste_kernel are the
+// pieces (generic TTA wrapper, ensemble mean, whole-image path, other tile sizes); the Gaussian kernels are an
+// opt-in blend mode with no reference counterpart.
 #include "common.cuh"
 #include <cstdlib>
 

@@ -79,7 +79,8 @@ EDS_API int eds_init(void);
  * (non-zero = positive).  hist: [n_images][2][EDS_PR_BINS] u32 (class 0 = negatives),
  * straddle: [n_images][EDS_PR_NTHRESH][2] u32 = pixels that share the key of
  * threshold k and are strictly above it.  Both are ACCUMULATED into (caller zeroes).
- * `splits` CTAs cooperate on one image (0 = pick). */
+ * splits = 0: one persistent wave of CTAs shares the linear range of all images' pixels (a CTA flushes
+ * where its share crosses an image boundary); splits > 0: exactly that many CTAs per image. */
 EDS_API int eds_pr_hist_f32(const float* prob, const uint8_t* gt, int64_t n_pixels, int n_images,
                     uint32_t* hist, uint32_t* straddle, int splits, void* stream);
 
