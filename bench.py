@@ -70,6 +70,8 @@ def synth_image_device(seed, dev):
     for les in LESIONS:
         coarse = torch.rand((H // 16, W // 16), device=dev, generator=g) < PREVALENCE[les]    # Bernoulli blobs of 16x16 px
         m = coarse.repeat_interleave(16, dim=0).repeat_interleave(16, dim=1) & disc
+        if les == "SE" and seed % 9 == 4:
+            m = torch.zeros_like(m)                # a few images without soft exudates (aucpr.py:22 skips them)
         masks[les] = m.to(torch.uint8).contiguous()
     return img.contiguous(), masks
 

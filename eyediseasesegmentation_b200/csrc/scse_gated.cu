@@ -20,6 +20,7 @@
 // Traffic per decoder block: 2 reads of the sources + 1 write of the concat (was 1 read of the sources,
 // 2 writes + 1 read of the concat, and 2 reads + 1 write of the block output for attention2).
 #include "common.cuh"
+#include <cstdlib>
 
 namespace eds {
 
@@ -356,6 +357,57 @@ concat_gated_kernel(CatSrcs src, int h, int w, int mode, int Ctot, const float* 
     }
 }
 
+// ---- pass B, same-resolution (skip) part: a lean streaming kernel ---------------------------------------------------
+// concat_gated_kernel<T, 1> keeps eight output vectors per thread (128 registers, spills in the bf16 build, two CTAs
+// per SM, ncu: 23 % occupancy and neither DRAM nor issue saturated -- latency-bound).  One thread here = one 8-channel
+// vector of FOUR consecutive pixels of a row: half the registers, twice the resident threads, the same arithmetic in
+// the same order (bit-identical results).  grid.x = N * H rows, grid.y covers (quad, vector) of a row.
+template <typename T>
+__global__ void __launch_bounds__(256, 3)
+concat_skip_kernel(CatSrcs src, int H, int W, int Ctot, const float* __restrict__ cgate1,
+                   const float* __restrict__ sgate1, T* __restrict__ y, int y_stride, int y_coff) {
+    const uint32_t C8a = (uint32_t)src.s[0].C / 8;
+    const uint32_t C8 = (uint32_t)Ctot / 8 - C8a;                  // vectors per pixel of the skip part
+    const uint32_t quads = (uint32_t)(W + 3) / 4;
+    const uint32_t col = blockIdx.y * blockDim.x + threadIdx.x;
+    if (col >= quads * C8) return;
+    const int qx = (int)(col / C8);
+    const int c8 = (int)(col - (uint32_t)qx * C8) + (int)C8a;      // vector inside the concat
+    const int n = (int)(blockIdx.x / (uint32_t)H);
+    const int yy = (int)(blockIdx.x - (uint32_t)n * H);
+    const int x0 = 4 * qx;
+    const int npx = min(4, W - x0);
+    int c = c8 * 8, k = 0;
+    while (k < src.n - 1 && c >= src.s[k].C) { c -= src.s[k].C; ++k; }
+    const GatedSrc sk = src.s[k];
+    const bool gated = sk.cgate != nullptr;
+    float2 cg[4];
+    if (gated) ld8f(sk.cgate + (int64_t)n * sk.C + c, cg);
+    const int64_t p0 = ((int64_t)n * H + yy) * W + x0;             // first pixel of the quad
+    const T* xp = reinterpret_cast<const T*>(sk.x) + p0 * sk.C + c;
+    const float* sg = sk.sgate + p0;                               // only dereferenced when gated
+    float2 o[4][4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        const int dd = min(d, npx - 1);                            // clamped address for a ragged last quad
+        ld_gated<T>(xp + (int64_t)dd * sk.C, cg, sg + dd, gated, o[d]);
+    }
+    if (cgate1) {
+        float2 g1[4];
+        ld8f(cgate1 + (int64_t)n * Ctot + c8 * 8, g1);
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const float2 s1 = f2(__ldg(sgate1 + p0 + min(d, npx - 1)));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o[d][q] = __fmul2_rn(o[d][q], __fadd2_rn(g1[q], s1));
+        }
+    }
+    T* yp = y + p0 * y_stride + (c8 * 8 - y_coff);
+#pragma unroll
+    for (int d = 0; d < 4; ++d)
+        if (d < npx) V8<T>::st(yp + (int64_t)d * y_stride, o[d]);
+}
+
 // y = x * (cgate[n][c] + sgate[n][p]) for an already materialised map (gate = probabilities).
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -478,12 +530,19 @@ static int concat_gated_launch(const eds_gated_src* srcs, int n_srcs, int N, int
     EDS_DISPATCH_DTYPE(dtype, T, (concat_gated_kernel<T, 0><<<grid_a, 256, 0, as_stream(stream)>>>(
                                      cs, h, w, mode, Ctot, cgate, sgate, (T*)y, stride_a, 0)));
     if (c8b > 0) {
-        dim3 grid_b((unsigned)(N * h), (unsigned)ceil_div(wp * c8b, 256));
         void* yb = y_skip ? y_skip : y;
         const int stride_b = y_skip ? Ctot - cs.s[0].C : Ctot;
         const int coff_b = y_skip ? cs.s[0].C : 0;
-        EDS_DISPATCH_DTYPE(dtype, T, (concat_gated_kernel<T, 1><<<grid_b, 256, 0, as_stream(stream)>>>(
-                                         cs, h, w, mode, Ctot, cgate, sgate, (T*)yb, stride_b, coff_b)));
+        static const bool lean_off = getenv("EDS_CONCAT_SKIP_LEAN") && atoi(getenv("EDS_CONCAT_SKIP_LEAN")) == 0;
+        if (!lean_off && (int64_t)N * 2 * h < (1ll << 31)) {
+            dim3 grid_s((unsigned)(N * 2 * h), (unsigned)ceil_div(ceil_div(2 * w, 4) * c8b, 256));
+            EDS_DISPATCH_DTYPE(dtype, T, (concat_skip_kernel<T><<<grid_s, 256, 0, as_stream(stream)>>>(
+                                             cs, 2 * h, 2 * w, Ctot, cgate, sgate, (T*)yb, stride_b, coff_b)));
+        } else {
+            dim3 grid_b((unsigned)(N * h), (unsigned)ceil_div(wp * c8b, 256));
+            EDS_DISPATCH_DTYPE(dtype, T, (concat_gated_kernel<T, 1><<<grid_b, 256, 0, as_stream(stream)>>>(
+                                             cs, h, w, mode, Ctot, cgate, sgate, (T*)yb, stride_b, coff_b)));
+        }
     }
     return check_launch("concat_gated_kernel");
 }
