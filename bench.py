@@ -234,11 +234,15 @@ def run_b200(args):
                 n_units = (min(g + group_size, count) - g) * TILES
                 mine = [u for u in range(n_units) if (g * TILES + u) % world == rank]
                 sizes |= {len(b) for b in partition.batches(mine, args.tiles)}
+        deaug = drv.fused_blend_views(models[LESIONS[0]], tfm, S, W)       # the forward the tile path will call
         for les in LESIONS:
             for b in sorted(sizes):
                 x = torch.zeros((b, 3, S, S), device=dev)
                 for _ in range(3):
-                    drv.predict_probs(models[les], tfm, x)
+                    if deaug is not None:
+                        models[les].forward_tta(x, tfm, merge=False)
+                    else:
+                        drv.predict_probs(models[les], tfm, x)
         if world > 1:                              # lazy NCCL channel set-up of the collectives used below
             w0 = torch.zeros((4, 4), dtype=torch.int32, device=dev)
             partition.allreduce_sum_(w0)
