@@ -305,7 +305,10 @@ def run_b200(args):
                              "the set is distinct",
                        "parallelism": f"(image, tile) units round-robin over {world} rank(s); ONE all-reduce of the "
                                       f"per-image integer histograms [4 x {args.steps} x 2 x {_lib.PR_BINS}] int32",
-                       "images_per_group": group_size, "allreduce_ms": ar_ms, "mean_ap_per_lesion": ap_mean},
+                       "images_per_group": group_size, "allreduce_ms": ar_ms,
+                       "allreduce_ms_note": "device time of the collective on rank 0: transfer (~0.2 ms) + waiting for the "
+                                            "slowest rank",
+                       "mean_ap_per_lesion": ap_mean},
             "e2e": {"value": e2e, "unit": "images/s",
                     "h2d_bytes_per_step": world * (H * W * 3 + len(LESIONS) * H * W),
                     "d2h_bytes_per_step": len(LESIONS) * (H * W * 4 + 42 * 8),
