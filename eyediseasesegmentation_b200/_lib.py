@@ -68,6 +68,8 @@ PROTOTYPES = {
     "eds_se_scale_add_relu": [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
     "eds_upsample2x_concat": [_vp, _i, _i, _i, _i, _i, C.POINTER(_vp), C.POINTER(_i), _i, _vp, _i, _vp],
     "eds_gated_stats": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp],
+    "eds_gated_stats_multi": [_vp, _vp, _vp, _i, _i, _i, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i),
+                              C.POINTER(_vp), _i, _vp],
     "eds_sse_finalize": [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp],
     "eds_concat_gated": [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
     "eds_concat_gated_split": [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp],

@@ -227,27 +227,74 @@ class Engine:
         cgate = K.se_gate(mean, *self.w[name + ".cse"])
         return Gated(x, cgate, K.sse_finalize(None, dot, _lib.UP_NONE, b_sse))
 
-    def _concat_scse(self, name, x, skips):
+    def _concat_scse(self, name, x, skips, skip_names=None):
         """attention1(cat([up2x(x), *skips])): one statistics pass per source at its own resolution,
-        then one pass that writes the gated concat."""
+        then one pass that writes the gated concat.  A skip source that feeds several blocks of the dense
+        decoder is read ONCE for all of them (``_skip_stats``)."""
         w_sse, b_sse = self.w[name + ".sse"]
         srcs = [_parts(x)] + [_parts(s) for s in skips]
         x0 = srcs[0][0]
         N, h, w, _ = x0.shape
         ctot = sum(t[0].shape[3] for t in srcs)
-        mean = torch.empty((N, ctot), dtype=torch.float32, device=x0.device)
+        mean, dot1 = self._consumer_buffers(name, N, ctot, 2 * h, 2 * w, x0.device)
         dot0 = torch.empty((N, h, w), dtype=torch.float32, device=x0.device)
-        dot1 = torch.empty((N, 2 * h, 2 * w), dtype=torch.float32, device=x0.device)
-        off = 0
-        for k, (t, cg, sg) in enumerate(srcs):
+        K.gated_stats(x0, srcs[0][1], srcs[0][2], w_sse[:x0.shape[3]], mean, 0, False, dot0, False)
+        off = x0.shape[3]
+        for k, (t, cg, sg) in enumerate(srcs[1:]):
             c = t.shape[3]
-            K.gated_stats(t, cg, sg, w_sse[off:off + c], mean, off, k == 0, dot0 if k == 0 else dot1, k > 1)
+            key = skip_names[k] if skip_names else None
+            if key is None or key not in self._skip_plan:       # a source with this block as its only consumer
+                K.gated_stats(t, cg, sg, w_sse[off:off + c], mean, off, False, dot1, True)
+            elif key not in self._skip_done:
+                self._skip_done.add(key)
+                cons = []
+                for (cname, coff, cctot) in self._skip_plan[key]:
+                    cm, cd = self._consumer_buffers(cname, N, cctot, 2 * h, 2 * w, x0.device)
+                    cons.append((self.w[cname + ".sse"][0][coff:coff + c], cm, coff, cd))
+                K.gated_stats_multi(t, cg, sg, cons)
             off += c
         cgate = K.se_gate(mean, *self.w[name + ".cse"])
         sgate = K.sse_finalize(dot0, dot1, self.up_mode, b_sse)
         if self._split_ok(srcs):
             return K.concat_gated_split(srcs, self.up_mode, cgate, sgate)
         return K.concat_gated(srcs, self.up_mode, cgate, sgate)
+
+    def _consumer_buffers(self, name, N, ctot, H, W, device):
+        """Zero-initialised (channel means [N,ctot], skip dot map [N,H,W]) of one attention1, created the first time
+        any of its sources is read."""
+        buf = self._stat_bufs.get(name)
+        if buf is None:
+            buf = (torch.zeros((N, ctot), dtype=torch.float32, device=device),
+                   torch.zeros((N, H, W), dtype=torch.float32, device=device))
+            self._stat_bufs[name] = buf
+        return buf
+
+    def _plan_skip_consumers(self, feats):
+        """Static plan of the dense decoder: skip source name -> [(attention1 name, channel offset in that
+        block's concat, channels of that concat)] over the SCSE blocks that read it at its own resolution."""
+        rev = feats[::-1]
+        depth = len(rev) - 1
+        ch = {f"f{len(rev) - i}": int(t.shape[3]) for i, t in enumerate(rev)}     # rev[i] = f(5 - i)
+        for bname, _layer, _in, _skip, out_ch in self.blocks:
+            ch[bname] = int(out_ch)
+        plan = {}
+        for layer_idx in range(depth):
+            for depth_idx in range(depth - layer_idx):
+                li = depth_idx + layer_idx
+                if layer_idx == 0:
+                    bname, xname, snames = f"x_{depth_idx}_{depth_idx}", f"f{len(rev) - depth_idx}", [f"f{len(rev) - depth_idx - 1}"]
+                else:
+                    bname, xname = f"x_{depth_idx}_{li}", f"x_{depth_idx}_{li - 1}"
+                    snames = [f"x_{i}_{li}" for i in range(depth_idx + 1, li + 1)] + [f"f{len(rev) - li - 1}"]
+                p = f"decoder.blocks.{bname}.attention1"
+                if (p + ".sse") not in self.w:
+                    continue
+                ctot = ch[xname] + sum(ch[sname] for sname in snames)
+                off = ch[xname]
+                for sname in snames:
+                    plan.setdefault(sname, []).append((p, off, ctot))
+                    off += ch[sname]
+        return {k: v for k, v in plan.items() if len(v) > 1 and len(v) <= 4}
 
     # ---------------------------------------------------------------- encoders
     def _se_bottleneck(self, p, x, stride):
@@ -329,7 +376,7 @@ class Engine:
             s = K.axial_attention(kq, v, axis, 4, 8, cr // 4, *self.w[f"{p}.{ax}"], relu=False)
         return self._cv(K.mhca_gate(ori, s), p + ".up_sample")
 
-    def _decoder_block(self, name, x, skips: Sequence[torch.Tensor]):
+    def _decoder_block(self, name, x, skips: Sequence[torch.Tensor], skip_names=None):
         p = f"decoder.blocks.{name}"
         if (p + ".down_sample") in self.w:
             x = _plain(x)
@@ -341,7 +388,7 @@ class Engine:
                 cat = K.concat_gated([(x, None, None), (skip, None, None)], self.up_mode)
         else:
             if skips and (p + ".attention1.sse") in self.w:
-                cat = self._concat_scse(p + ".attention1", x, skips)
+                cat = self._concat_scse(p + ".attention1", x, skips, skip_names)
             elif (not skips and self.conv_impl == "tc" and K.FUSED_TAIL and
                   _lib.load().eds_conv3x3_small_supported(x.shape[3], self.w[p + ".conv1"][0].shape[0])):
                 # last block: no skip, no attention1 -- upsampling (and the pending gate of x) is fused into
@@ -366,17 +413,22 @@ class Engine:
     def _decode_dense(self, feats: List[torch.Tensor]):
         rev = feats[::-1]                  # f5, f4, f3, f2, f1
         depth = len(rev) - 1
+        nf = len(rev)
+        self._skip_plan = self._plan_skip_consumers(feats)
         dense = {}
         for layer_idx in range(depth):
             for depth_idx in range(depth - layer_idx):
                 if layer_idx == 0:
                     name = f"x_{depth_idx}_{depth_idx}"
-                    dense[name] = self._decoder_block(name, rev[depth_idx], [rev[depth_idx + 1]])
+                    dense[name] = self._decoder_block(name, rev[depth_idx], [rev[depth_idx + 1]],
+                                                      [f"f{nf - depth_idx - 1}"])
                 else:
                     li = depth_idx + layer_idx
-                    skips = [dense[f"x_{i}_{li}"] for i in range(depth_idx + 1, li + 1)] + [rev[li + 1]]
+                    names = [f"x_{i}_{li}" for i in range(depth_idx + 1, li + 1)]
+                    skips = [dense[n] for n in names] + [rev[li + 1]]
                     name = f"x_{depth_idx}_{li}"
-                    dense[name] = self._decoder_block(name, dense[f"x_{depth_idx}_{li - 1}"], skips)
+                    dense[name] = self._decoder_block(name, dense[f"x_{depth_idx}_{li - 1}"], skips,
+                                                      names + [f"f{nf - li - 1}"])
         return self._decoder_block(f"x_0_{depth}", dense[f"x_0_{depth - 1}"], [])
 
     def _decode_unet(self, feats: List[torch.Tensor]):
@@ -404,6 +456,7 @@ class Engine:
         x = x.contiguous().float()
         if self.keep_features:
             self.features = {}
+        self._stat_bufs, self._skip_done, self._skip_plan = {}, set(), {}
         feats = self._encode(x, aug_maps or IDENTITY_VIEW)
         y = self._decode_unet(feats) if self.arch == "Unet" else self._decode_dense(feats)
         return K.head_conv3x3(_plain(y), *self.w["head"])

@@ -21,6 +21,7 @@
 // 2 writes + 1 read of the concat, and 2 reads + 1 write of the block output for attention2).
 #include "common.cuh"
 #include <cstdlib>
+#include <cstring>
 
 namespace eds {
 
@@ -161,6 +162,124 @@ gated_stats_kernel(const T* __restrict__ x, const float* __restrict__ cgate, con
 #pragma unroll
                 for (int q = 0; q < PPW; ++q) t += s_sum[wi][q * LPP + vl][e];
             atomicAdd(chan_mean + (int64_t)n * mean_stride + c_off + ch, t * inv_p);
+        }
+    }
+}
+
+// ---- pass A for ALL consumers of a skip source at once ------------------------------------------------------------
+// In the dense decoder a block output (or encoder feature) is the same-resolution skip of up to four later blocks,
+// each with its own SCSE attention1.  The channel means of the (gated) source do not depend on the consumer and its
+// per-pixel dot only differs in the weight slice, so ONE read of the source serves every consumer: K dot maps
+// (accumulated into the consumers' dot buffers) and K copies of the channel means (added into the consumers' mean
+// rows).  Round 1 read the source once per consumer.  Same lane layout and reductions as gated_stats_kernel; the
+// gated value v * (cg + s) is formed once per element and dotted with each consumer's weights.
+constexpr int kMaxConsumers = 4;
+#ifndef EDS_GS_MULTI_UNROLL
+#define EDS_GS_MULTI_UNROLL 8
+#endif
+constexpr int kGsMultiUnroll = EDS_GS_MULTI_UNROLL;
+struct StatConsumers {
+    const float* w_sse[kMaxConsumers];    // this source's C-slice of the consumer's sSE weights
+    float* chan_mean[kMaxConsumers];      // consumer's [N][mean_stride] rows (+= at c_off)
+    float* dot[kMaxConsumers];            // consumer's [N][P] map (+=)
+    int mean_stride[kMaxConsumers], c_off[kMaxConsumers];
+    int n;
+};
+
+template <typename T, bool GATED, int LPP, int K>
+__global__ void __launch_bounds__(kGsThreads, 2)
+gated_stats_multi_kernel(const T* __restrict__ x, const float* __restrict__ cgate, const float* __restrict__ sgate,
+                         int P, int C, float inv_p, StatConsumers cons) {
+    constexpr int PPW = 32 / LPP, U = kGsMultiUnroll;                           // pixels in flight per lane group
+    constexpr int NS = ilog2c(LPP) < ilog2c(U) ? ilog2c(LPP) : ilog2c(U);
+    constexpr int MF = U >> NS;
+    constexpr int PLAIN = ilog2c(LPP) - NS;
+    __shared__ float s_sum[kGsThreads / 32][32][8 + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int l = lane % LPP, sub = lane / LPP;
+    const int n = blockIdx.y;
+    const int v8 = blockIdx.z * 32 + l;
+    const bool live = v8 < C / 8;
+    const T* xp = x + (int64_t)n * P * C + (live ? v8 * 8 : 0);
+    const float* sg = GATED ? sgate + (int64_t)n * P : nullptr;
+    float2 w2[K][4], cg2[4], acc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = f2(0.f), cg2[k] = f2(1.f);
+#pragma unroll
+    for (int c = 0; c < K; ++c)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w2[c][k] = f2(0.f);
+    if (live) {
+#pragma unroll
+        for (int c = 0; c < K; ++c) ld8f(cons.w_sse[c] + v8 * 8, w2[c]);
+        if (GATED) ld8f(cgate + (int64_t)n * C + v8 * 8, cg2);
+    }
+    const int per = (P + gridDim.x - 1) / gridDim.x;
+    const int p_begin = blockIdx.x * per;
+    const int p_end = min(P, p_begin + per);
+    constexpr int STEP = (kGsThreads / 32) * PPW * U;
+    for (int pb = p_begin + warp * PPW * U; pb < p_end; pb += STEP) {
+        float2 v[U][4];
+        float sv[U];
+        const bool tail = pb + PPW * U > p_end;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int p = min(pb + u * PPW + sub, p_end - 1);
+            V8<T>::ld(xp + (int64_t)p * C, v[u]);
+            sv[u] = GATED ? __ldg(sg + p) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bool dead = tail && pb + u * PPW + sub >= p_end;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (GATED) v[u][k] = __fmul2_rn(v[u][k], __fadd2_rn(cg2[k], f2(sv[u])));
+                if (dead || !live) v[u][k] = f2(0.f);
+                acc[k] = __fadd2_rn(acc[k], v[u][k]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+            float d[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                float2 a = f2(0.f);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) a = __ffma2_rn(v[u][k], w2[c][k], a);
+                d[u] = a.x + a.y;
+            }
+            int u_sel = 0;
+            GroupReduce<LPP / 2, U>::run(d, l, u_sel);
+            if ((l & ((1 << PLAIN) - 1)) == 0) {
+#pragma unroll
+                for (int q = 0; q < MF; ++q) {
+                    const int p = pb + (u_sel + q) * PPW + sub;
+                    if (p < p_end) {
+                        float* dst = cons.dot[c] + (int64_t)n * P + p;
+                        if (gridDim.z > 1) atomicAdd(dst, d[q]);
+                        else *dst += d[q];
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        s_sum[warp][lane][2 * k] = acc[k].x;
+        s_sum[warp][lane][2 * k + 1] = acc[k].y;
+    }
+    __syncthreads();
+    if (threadIdx.x < LPP * 8) {
+        const int vl = threadIdx.x >> 3, e = threadIdx.x & 7;
+        const int ch = (blockIdx.z * 32 + vl) * 8 + e;
+        if (ch < C) {
+            float t = 0.f;
+            for (int wi = 0; wi < kGsThreads / 32; ++wi)
+#pragma unroll
+                for (int q = 0; q < PPW; ++q) t += s_sum[wi][q * LPP + vl][e];
+#pragma unroll
+            for (int c = 0; c < K; ++c)
+                atomicAdd(cons.chan_mean[c] + (int64_t)n * cons.mean_stride[c] + cons.c_off[c] + ch, t * inv_p);
         }
     }
 }
@@ -478,6 +597,64 @@ extern "C" int eds_gated_stats(const void* x, const float* cgate, const float* s
 #undef EDS_GS_LPP
 #undef EDS_GS_LAUNCH
     return check_launch("gated_stats_kernel");
+}
+
+template <typename T, bool GATED, int LPP>
+static void stats_multi_launch(int K, dim3 grid, cudaStream_t st, const void* x, const float* cgate, const float* sgate,
+                               int P, int C, const StatConsumers& cons) {
+    const float inv_p = 1.0f / (float)P;
+    switch (K) {
+        case 1: gated_stats_multi_kernel<T, GATED, LPP, 1><<<grid, kGsThreads, 0, st>>>((const T*)x, cgate, sgate, P, C, inv_p, cons); break;
+        case 2: gated_stats_multi_kernel<T, GATED, LPP, 2><<<grid, kGsThreads, 0, st>>>((const T*)x, cgate, sgate, P, C, inv_p, cons); break;
+        case 3: gated_stats_multi_kernel<T, GATED, LPP, 3><<<grid, kGsThreads, 0, st>>>((const T*)x, cgate, sgate, P, C, inv_p, cons); break;
+        default: gated_stats_multi_kernel<T, GATED, LPP, 4><<<grid, kGsThreads, 0, st>>>((const T*)x, cgate, sgate, P, C, inv_p, cons); break;
+    }
+}
+
+extern "C" int eds_gated_stats_multi(const void* x, const float* cgate, const float* sgate, int N, int P, int C,
+                                     int n_consumers, const float* const* w_sse, float* const* chan_mean,
+                                     const int* mean_stride, const int* c_off, float* const* dot, int dtype,
+                                     void* stream) {
+    EDS_REQUIRE(x && w_sse && chan_mean && mean_stride && c_off && dot, "gated_stats_multi: null pointer");
+    EDS_REQUIRE((cgate == nullptr) == (sgate == nullptr), "gated_stats_multi: cgate and sgate come together");
+    EDS_REQUIRE(N > 0 && N <= 65535 && P > 0 && C > 0 && C % 8 == 0, "gated_stats_multi: bad shape N=%d P=%d C=%d", N, P, C);
+    EDS_REQUIRE(n_consumers >= 1 && n_consumers <= kMaxConsumers, "gated_stats_multi: n_consumers=%d (1..%d)",
+                n_consumers, kMaxConsumers);
+    StatConsumers cons;
+    memset(&cons, 0, sizeof(cons));
+    cons.n = n_consumers;
+    for (int k = 0; k < n_consumers; ++k) {
+        EDS_REQUIRE(w_sse[k] && chan_mean[k] && dot[k], "gated_stats_multi: consumer %d: null pointer", k);
+        EDS_REQUIRE(mean_stride[k] >= c_off[k] + C && c_off[k] >= 0 && c_off[k] % 8 == 0,
+                    "gated_stats_multi: consumer %d: bad mean layout", k);
+        cons.w_sse[k] = w_sse[k]; cons.chan_mean[k] = chan_mean[k]; cons.dot[k] = dot[k];
+        cons.mean_stride[k] = mean_stride[k]; cons.c_off[k] = c_off[k];
+    }
+    const int c8 = C / 8;
+    int lpp = 32;
+    while (lpp > 1 && lpp / 2 >= c8) lpp /= 2;
+    const int zchunks = ceil_div(c8, 32);
+    EDS_REQUIRE(zchunks <= 65535, "gated_stats_multi: too many channels");
+    int chunks = ceil_div(148 * 12, N * zchunks);
+    const int max_chunks = ceil_div(P, 8 * (32 / lpp) * kGsMultiUnroll);
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    dim3 grid(chunks, N, zchunks);
+    cudaStream_t st = as_stream(stream);
+#define EDS_GSM_LPP(T, G)                                                                                        \
+    switch (lpp) {                                                                                               \
+        case 1: stats_multi_launch<T, G, 1>(n_consumers, grid, st, x, cgate, sgate, P, C, cons); break;          \
+        case 2: stats_multi_launch<T, G, 2>(n_consumers, grid, st, x, cgate, sgate, P, C, cons); break;          \
+        case 4: stats_multi_launch<T, G, 4>(n_consumers, grid, st, x, cgate, sgate, P, C, cons); break;          \
+        case 8: stats_multi_launch<T, G, 8>(n_consumers, grid, st, x, cgate, sgate, P, C, cons); break;          \
+        case 16: stats_multi_launch<T, G, 16>(n_consumers, grid, st, x, cgate, sgate, P, C, cons); break;        \
+        default: stats_multi_launch<T, G, 32>(n_consumers, grid, st, x, cgate, sgate, P, C, cons); break;        \
+    }
+    EDS_DISPATCH_DTYPE(dtype, T, {
+        if (cgate) { EDS_GSM_LPP(T, true) } else { EDS_GSM_LPP(T, false) }
+    });
+#undef EDS_GSM_LPP
+    return check_launch("gated_stats_multi_kernel");
 }
 
 extern "C" int eds_sse_finalize(const float* dot0, const float* dot1, int N, int h, int w, int mode, float b_sse,

@@ -495,6 +495,27 @@ def gated_stats(x: torch.Tensor, cgate: Optional[torch.Tensor], sgate: Optional[
                                      c_off, int(zero_mean), _p(dot), int(accumulate), _dt(x), _stream()))
 
 
+def gated_stats_multi(x: torch.Tensor, cgate: Optional[torch.Tensor], sgate: Optional[torch.Tensor], consumers) -> None:
+    """One read of a same-resolution skip source [N,h,w,C] for ALL its consumers: ``consumers`` is a list (<= 4) of
+    ``(w_sse slice [C] fp32, mean [N,stride] fp32, c_off, dot [N,h,w] fp32)``; the (gated) channel means are ADDED
+    into ``mean[:, c_off:c_off+C]`` and the per-pixel dots ADDED into ``dot`` (the caller zeroes both once)."""
+    _chk(x, cgate, sgate)
+    N, h, w, Cc = x.shape
+    n = len(consumers)
+    assert 1 <= n <= 4
+    for (ws, mean, off, dot) in consumers:
+        _chk(ws, mean, dot)
+        assert ws.numel() == Cc and ws.dtype == torch.float32 and mean.dtype == torch.float32 and mean.shape[0] == N
+        assert dot.shape == (N, h, w) and dot.dtype == torch.float32
+    ws = (C.c_void_p * n)(*[c[0].data_ptr() for c in consumers])
+    means = (C.c_void_p * n)(*[c[1].data_ptr() for c in consumers])
+    strides = (C.c_int * n)(*[c[1].shape[1] for c in consumers])
+    offs = (C.c_int * n)(*[int(c[2]) for c in consumers])
+    dots = (C.c_void_p * n)(*[c[3].data_ptr() for c in consumers])
+    check(_lib.lib().eds_gated_stats_multi(_p(x), _p(cgate), _p(sgate), N, h * w, Cc, n, ws, means, strides, offs, dots,
+                                           _dt(x), _stream()))
+
+
 def sse_finalize(dot0: Optional[torch.Tensor], dot1: Optional[torch.Tensor], mode: int, b_sse: float,
                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """sigmoid(up(dot0) + dot1 + b) -> [N,H,W] fp32 (in place over dot1 by default)."""

@@ -294,6 +294,16 @@ EDS_API int eds_gated_stats(const void* x, const float* cgate, const float* sgat
                             const float* w_sse, float* chan_mean, int mean_stride, int c_off, int zero_mean,
                             float* dot, int accumulate, int dtype, void* stream);
 
+/* The same pass for ALL consumers of a same-resolution skip source at once (dense decoder: a block output is
+ * the skip of up to 4 later blocks; unetplusplusstar.py:239-263).  One read of the source; for consumer k:
+ *   chan_mean[k][n][c_off[k] + c] += mean_p value[n][p][c]      (row stride mean_stride[k]; caller zeroes)
+ *   dot[k][n][p]                  += sum_c w_sse[k][c] * value[n][p][c]              (caller zeroes)
+ * n_consumers <= 4; the pointer arrays are host arrays of device pointers. */
+EDS_API int eds_gated_stats_multi(const void* x, const float* cgate, const float* sgate, int N, int P, int C,
+                                  int n_consumers, const float* const* w_sse, float* const* chan_mean,
+                                  const int* mean_stride, const int* c_off, float* const* dot, int dtype,
+                                  void* stream);
+
 /* sgate[n][p] = sigmoid(up(dot0)[p] + dot1[p] + b_sse) on the output grid (up*h x up*w; mode as in
  * eds_upsample2x_concat; dot0 [N][h][w] or NULL, dot1 [N][up*h][up*w] or NULL; sgate may alias dot1). */
 EDS_API int eds_sse_finalize(const float* dot0, const float* dot1, int N, int h, int w, int mode, float b_sse,

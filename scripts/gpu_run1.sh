@@ -1,4 +1,10 @@
 cd $GRAFT_REPO_ROOT
-EDS_CONCAT_SKIP_LEAN=0 python scripts/dev_concat_probe.py 2>&1 | tail -8
-EDS_CONCAT_SKIP_LEAN=1 python scripts/dev_concat_probe.py 2>&1 | tail -8
-python -m pytest tests/test_kernels_gpu.py -q -x -k "deferred_gate or concat_gated or gaussian" 2>&1 | tail -2
+python -m pytest tests -m gpu -q 2>&1 | tail -3
+python __graft_entry__.py smoke 2>&1 | tail -1
+python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench7.json 2> gpurun_out/r02_bench7.err; tail -2 gpurun_out/r02_bench7.err; python - <<'P'
+import json
+d=json.load(open('gpurun_out/r02_bench7.json'))
+print({k:d[k] for k in ['value','ms_per_step','gpu_launches']}, d['e2e']['value'], 'conv', d['roofline']['frac'], 'hist', d['roofline_hist']['frac'], 'blend', d['roofline_blend']['frac'])
+print(d['time_shares'])
+print(d['other_configs']); print(d['cpu_baseline']['value'], d['cpu_baseline']['tile_seconds'])
+P

@@ -937,3 +937,32 @@ def test_tta_blend_x2_equals_merge_then_paste(alias, S, shape):
         K.tta_blend_x2(sub, deaug, a, origins, first_tile=1)
         K.paste_tiles_owned_x2(K.tta_merge(sub, deaug, True), 1, b, origins)
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("C,gated,n_cons,dtype", [(64, True, 4, torch.bfloat16), (64, False, 3, torch.bfloat16),
+                                                  (256, True, 2, torch.bfloat16), (24, True, 3, torch.float32),
+                                                  (512, False, 1, torch.bfloat16)])
+def test_gated_stats_multi_equals_one_pass_per_consumer(C, gated, n_cons, dtype):
+    """eds_gated_stats_multi (one read of a skip source for all its consumers) against eds_gated_stats run once per
+    consumer: same channel means in every consumer's row, same dot maps (fp32 sums in a different order: 1e-5
+    relative), accumulation on top of what the buffers already hold."""
+    torch.manual_seed(C + n_cons)
+    N, h, w = 3, 19, 23
+    x = (torch.randn(N, h, w, C, device=DEV)).to(dtype)
+    cg = torch.rand(N, C, device=DEV) if gated else None
+    sg = torch.rand(N, h, w, device=DEV) if gated else None
+    cons, want = [], []
+    for k in range(n_cons):
+        stride = C + 16 * (k + 1)
+        off = 8 * k
+        ws = torch.randn(C, device=DEV)
+        mean0 = torch.rand(N, stride, device=DEV)
+        dot0 = torch.randn(N, h, w, device=DEV)
+        m_ref, d_ref = mean0.clone(), dot0.clone()
+        K.gated_stats(x, cg, sg, ws, m_ref, off, False, d_ref, True)
+        want.append((m_ref, d_ref))
+        cons.append((ws, mean0, off, dot0))
+    K.gated_stats_multi(x, cg, sg, cons)
+    for (ws, m, off, d), (m_ref, d_ref) in zip(cons, want):
+        assert (m - m_ref).abs().max().item() < 1e-5 * max(1.0, m_ref.abs().max().item())
+        assert (d - d_ref).abs().max().item() < 2e-5 * max(1.0, d_ref.abs().max().item())
