@@ -336,7 +336,13 @@ def partitioned_group(model, transforms, images, gts, S: int, mean, std, hist: t
         for j, (k, t) in enumerate(batch):
             K.paste_tiles_owned_x2(prob[j:j + 1], t, canvases[k], plans[k].origins)
     for k, p in enumerate(plans):
-        rects = [r for (kk, t) in mine if kk == k for r in p.cells[t]]
+        tiles_here = [t for (kk, t) in mine if kk == k]
+        if len(tiles_here) == p.n and int(gts[k].shape[1]) == int(images[k].shape[1]):
+            # this rank holds every tile of the image (one GPU, or more images than units): the streaming kernel
+            K.pr_hist(canvases[k].view(1, -1), gts[k].view(1, -1), hist[first_row + k:first_row + k + 1],
+                      strad[first_row + k:first_row + k + 1])
+            continue
+        rects = [r for t in tiles_here for r in p.cells[t]]
         if rects:
             K.pr_hist_rects(canvases[k], gts[k], rects, hist[first_row + k], strad[first_row + k])
     return canvases, unit_offset + len(units)
