@@ -1,2 +1,8 @@
 cd $GRAFT_REPO_ROOT
-python scripts/dev_ncu_probe_r02.py && ncu --set full --clock-control none --import-source on -k regex:"conv_igemm|conv3x3_wide|conv3x3_halo|concat_gated|concat_skip|gated_stats|tta_blend|tta_merge64|paste_tiles|pr_hist" -o gpurun_out/r02_kernels python scripts/dev_ncu_probe_r02.py > gpurun_out/r02_kernels_ncu.log 2>&1; tail -2 gpurun_out/r02_kernels_ncu.log; ls -la gpurun_out/r02_kernels.ncu-rep
+python -m pytest tests -m gpu -q 2>&1 | tail -3
+python __graft_entry__.py smoke 2>&1 | tail -1
+python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r02_bench8.json 2> gpurun_out/r02_bench8.err; tail -2 gpurun_out/r02_bench8.err; python - <<'P'
+import json
+d=json.load(open('gpurun_out/r02_bench8.json'))
+print({k:d[k] for k in ['value','ms_per_step','gpu_launches']}, d['e2e']['value'], 'conv', d['roofline']['frac'], 'hist', d['roofline_hist']['frac'], 'blend', d['roofline_blend']['frac'], d['clocks'])
+P
