@@ -21,6 +21,10 @@ from .. import _lib, kernels as K
 from .spec import dense_decoder_blocks
 
 IDENTITY_VIEW = [(1, 0, 0, 0, 1, 0)]
+#: SE bottleneck tail (squeeze, scale, residual, ReLU) in conv3's epilogue on the tensor-core path
+#: (EDS_SE_EPILOGUE=0 keeps conv3 -> channel_mean -> se_gate -> se_scale_add_relu as separate passes)
+SE_IN_EPILOGUE = __import__("os").environ.get("EDS_SE_EPILOGUE", "1") != "0"
+SE_EPILOGUE_MIN_PIXELS = int(__import__("os").environ.get("EDS_SE_EPILOGUE_MIN_PIXELS", str(256 * 256)))
 BN_EPS = 1e-5
 
 
@@ -132,6 +136,10 @@ class Engine:
                     self._conv(sd, p + ".conv1", p + ".conv1", p + ".bn1")
                     self._conv(sd, p + ".conv2", p + ".conv2", p + ".bn2")
                     self._conv(sd, p + ".conv3", p + ".conv3", p + ".bn3")
+                    # fp32 copy of the (rounded) conv3 weights as a [Cout][Cin] matrix: the SE squeeze from the
+                    # channel means of conv3's input (K.affine_rows)
+                    w3 = self.w[p + ".conv3"][0]
+                    self.w[p + ".conv3.f32"] = (w3.float().reshape(w3.shape[0], -1).contiguous(),)
                     if (p + ".downsample.0.weight") in sd:
                         self._conv(sd, p + ".downsample", p + ".downsample.0", p + ".downsample.1")
                     self._se(sd, p + ".se", p + ".se_module.fc1", p + ".se_module.fc2")
@@ -300,8 +308,22 @@ class Engine:
     def _se_bottleneck(self, p, x, stride):
         out = self._cv(x, p + ".conv1", stride=stride, relu=True)
         out = self._cv(out, p + ".conv2", pad=1, relu=True)
-        out = self._cv(out, p + ".conv3")
         res = self._cv(x, p + ".downsample", stride=stride) if (p + ".downsample") in self.w else x
+        if self.conv_impl == "tc" and SE_IN_EPILOGUE:
+            # conv3 (1x1 + folded BN) has no activation, so the channel means its SE module squeezes are an affine
+            # function of the channel means of conv3's INPUT (a quarter of the channels): the gate is known before
+            # conv3 runs and the squeeze never re-reads the 4x wider map.  On the large maps scale + residual + ReLU
+            # then happen on conv3's accumulators (the pre-activation map is never written); on the small ones the
+            # epilogue's residual path costs more than the separate pass it replaces (scripts/dev_se_probe.py: 48
+            # maps, fused vs conv3 + scale: 1.39 vs 1.44 ms at 256^2, 0.76 vs 0.73 at 128^2, 0.42 vs 0.38 at 64^2)
+            w3, b3 = self.w[p + ".conv3"]
+            squeeze = K.affine_rows(K.channel_mean(out), self.w[p + ".conv3.f32"][0], b3)
+            gate = K.se_gate(squeeze, *self.w[p + ".se"])
+            if out.shape[1] * out.shape[2] >= SE_EPILOGUE_MIN_PIXELS:
+                return K.conv1x1_se(out, w3, b3, gate, res)
+            out = self._cv(out, p + ".conv3")
+            return K.se_scale_add_relu(out, gate, res, out=out)
+        out = self._cv(out, p + ".conv3")
         gate = K.se_gate(K.channel_mean(out), *self.w[p + ".se"])
         return K.se_scale_add_relu(out, gate, res, out=out)
 

@@ -41,6 +41,7 @@ struct IgemmParams {
     int k_split;            // channel chunks served by a_map (== k_chunks when there is one input)
     CUtensorMap b_map;
     const float* bias;
+    const float* gate;      // optional [N][Cout]: y = relu((acc + bias) * gate[n][co] + residual)  (SE scale fused)
     const __nv_bfloat16* residual;
     __nv_bfloat16* y;
     int taps, C, block_k, k_chunks, block_n, n_tiles;
@@ -73,7 +74,8 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
     uint8_t* staging = smem + (size_t)p.stages * stage_bytes;          // [2 halves][st_bufs][st_bytes]
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + (size_t)2 * p.st_bufs * p.st_bytes);
+    uint8_t* res_stage = staging + (size_t)2 * p.st_bufs * p.st_bytes; // [2 halves][2][st_bytes] when there is a residual
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(res_stage + (p.residual ? (size_t)4 * p.st_bytes : 0));
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tmem_full_bar = empty_bar + kMaxStages;      // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;          // [2]
@@ -189,7 +191,40 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
         const uint32_t swz = p.st_mode == 0 ? (uint32_t)(m & 7) : (p.st_mode == 1 ? (uint32_t)((m >> 1) & 3) : (uint32_t)((m >> 2) & 1));
         uint8_t* my_stage = staging + (size_t)half * p.st_bufs * p.st_bytes;
         const bool issuer = (warp - 2) % 4 == 0 && lane == 0;      // first warp of the half
-        int t = 0, sbuf = 0;
+        // Residual (skip connection / SE bottleneck tail): the [128 pixels][st_ch] tile of a group is fetched
+        // COOPERATIVELY with cp.async, 16-byte chunk by chunk in row-major order of the staging layout (a warp copies
+        // whole 128-byte pixel rows: coalesced), into one of two buffers of this half, ONE GROUP AHEAD of its use.
+        // (A lane owns one PIXEL: reading its residual directly touched 32 different lines per load instruction and
+        // doubled the time of the SE bottleneck's conv3 once scale + residual + ReLU moved into this epilogue.)
+        uint8_t* my_res = res_stage + (size_t)half * 2 * p.st_bytes;
+        const int hid = (warp - 2) % 4 * 32 + lane;                // thread index inside the half (0..127)
+        auto fetch_residual = [&](int tile_, int grp_, uint8_t* dstbuf) {
+            const int cpr = row_bytes >> 4;                         // 16-byte chunks per staging row: 8 / 4 / 2
+            const int n_tile_ = tile_ % p.n_tiles;
+            int m_tile_ = tile_ / p.n_tiles;
+            const int w0_ = (m_tile_ % p.tiles_w) * p.TW;
+            m_tile_ /= p.tiles_w;
+            const int h0_ = (m_tile_ % p.tiles_h) * p.TH, n0_ = (m_tile_ / p.tiles_h) * p.TN;
+            const int64_t c0_ = (int64_t)n_tile_ * p.block_n + grp_ * p.st_ch;
+#pragma unroll 1
+            for (int qc = hid; qc < kTileM * cpr; qc += 128) {
+                const int rr = qc / cpr, jc = qc - rr * cpr;
+                const int rw = w0_ + (rr & (p.TW - 1)), rh = h0_ + ((rr >> p.tw_log2) & (p.TH - 1));
+                const int rn = n0_ + (rr >> (p.tw_log2 + p.th_log2));
+                if (rw < p.Wo && rh < p.Ho && rn < p.N) {
+                    const uint32_t sw = p.st_mode == 0 ? (uint32_t)(rr & 7)
+                                      : (p.st_mode == 1 ? (uint32_t)((rr >> 1) & 3) : (uint32_t)((rr >> 2) & 1));
+                    const __nv_bfloat16* src = p.residual + (((int64_t)rn * p.Ho + rh) * p.Wo + rw) * p.Cout + c0_ + jc * 8;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(
+                                     dstbuf + (size_t)rr * row_bytes + (((uint32_t)jc ^ sw) << 4))), "l"(src) : "memory");
+                }
+            }
+        };
+        int t = 0, sbuf = 0, gcount = 0;
+        if (p.residual) {                                           // prologue: the first group of this half
+            if ((int)blockIdx.x < p.total_tiles && half < n_groups) fetch_residual(blockIdx.x, half, my_res);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
             const int buf = t & 1;
             const int n_tile = tile % p.n_tiles;
@@ -231,7 +266,20 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
                     else asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(0) : "memory");
                 }
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+                // residual tile: the copy of THIS group was issued one group ago (or in the prologue); issue the
+                // next group's now so that it flies during this group's work
+                const uint8_t* rcur = my_res + (size_t)(gcount & 1) * p.st_bytes;
+                if (p.residual) {
+                    int ntile = tile, ngrp = grp + 2;
+                    if (ngrp >= n_groups) { ntile = tile + gridDim.x; ngrp = half; }
+                    if (ntile < p.total_tiles && ngrp < n_groups) fetch_residual(ntile, ngrp, my_res + (size_t)((gcount + 1) & 1) * p.st_bytes);
+                    asm volatile("cp.async.commit_group;" ::: "memory");          // (possibly empty) keeps the count uniform
+                }
                 tmem_ld_wait();
+                if (p.residual) {
+                    asm volatile("cp.async.wait_group 1;" ::: "memory");           // everything but the prefetch just issued
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");  // ... of every thread of the half
+                }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     if (i >= n16) break;
@@ -245,10 +293,20 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
                         const float4 bb = bv[i][e];
                         v[4 * e] += bb.x; v[4 * e + 1] += bb.y; v[4 * e + 2] += bb.z; v[4 * e + 3] += bb.w;
                     }
-                    if (p.residual && valid) {
+                    if (p.gate && valid) {                     // squeeze-excitation scale of this image's channels
+                        const float4* g4 = reinterpret_cast<const float4*>(p.gate + (int64_t)on * p.Cout + co0 + c);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float4 gg = __ldg(g4 + e);
+                            v[4 * e] *= gg.x; v[4 * e + 1] *= gg.y; v[4 * e + 2] *= gg.z; v[4 * e + 3] *= gg.w;
+                        }
+                    }
+                    if (p.residual) {                          // this lane's own row of the parked residual tile
+                        const uint32_t jr = (uint32_t)c16 >> 3;
+                        const uint8_t* rrow = rcur + (size_t)m * row_bytes;
                         float r0[8], r1[8];
-                        Vec8<__nv_bfloat16>::ld(p.residual + off + c, r0);
-                        Vec8<__nv_bfloat16>::ld(p.residual + off + c + 8, r1);
+                        Vec8<__nv_bfloat16>::ld(reinterpret_cast<const __nv_bfloat16*>(rrow + ((jr ^ swz) << 4)), r0);
+                        Vec8<__nv_bfloat16>::ld(reinterpret_cast<const __nv_bfloat16*>(rrow + (((jr + 1) ^ swz) << 4)), r1);
 #pragma unroll
                         for (int e = 0; e < 8; ++e) { v[e] += r0[e]; v[8 + e] += r1[e]; }
                     }
@@ -281,6 +339,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p) {
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 sbuf = (sbuf + 1) & (p.st_bufs - 1);
+                ++gcount;
             }
             // this warp's TMEM reads of the buffer are complete (tcgen05.wait::ld above)
             tc_fence_before();
@@ -368,7 +427,7 @@ using namespace eds;
 // x: [N][H][W][C0]; x1 (optional): [N][H][W][C1] -- the convolution of their channel concatenation
 static int igemm_launch(const void* x, int C0, const void* x1, int C1, int N, int H, int W, const void* w,
                         const float* bias, int Cout, int R, int S, int stride, int pad, int relu, const void* residual,
-                        void* y, void* stream) {
+                        void* y, void* stream, const float* gate = nullptr) {
     const int C = C0 + C1;
     EDS_REQUIRE(x && w && y, "conv2d_igemm: null pointer");
     EDS_REQUIRE(N > 0 && H > 0 && W > 0, "conv2d_igemm: bad shape N=%d H=%d W=%d", N, H, W);
@@ -390,6 +449,8 @@ static int igemm_launch(const void* x, int C0, const void* x1, int C1, int N, in
     IgemmParams p;
     memset(&p, 0, sizeof(p));
     p.bias = bias;
+    p.gate = gate;
+    EDS_REQUIRE((((uintptr_t)gate) & 15) == 0, "conv2d_igemm: gate must be 16-byte aligned");
     p.residual = (const __nv_bfloat16*)residual;
     p.y = (__nv_bfloat16*)y;
     p.taps = R * S;
@@ -447,11 +508,20 @@ static int igemm_launch(const void* x, int C0, const void* x1, int C1, int N, in
         if (k_iters <= 4 && (short_bufs == 1 || short_bufs == 2 || short_bufs == 4)) p.st_bufs = short_bufs;
     }
     // one persistent CTA per SM: the rest of the shared memory is one TMA ring
-    const int ring_budget = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/ - 2 * p.st_bufs * p.st_bytes;
-    p.stages = std::max(2, std::min(kMaxStages, ring_budget / stage_bytes));
+    const int res_bytes = residual ? 4 * p.st_bytes : 0;               // two residual buffers per epilogue half
+    // one persistent CTA per SM: the rest of the shared memory is one TMA ring of at least two stages (fewer staging
+    // buffers if that is what it takes)
+    int ring_budget = 0;
+    for (;; p.st_bufs >>= 1) {
+        ring_budget = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/ - 2 * p.st_bufs * p.st_bytes - res_bytes;
+        if (ring_budget >= 2 * stage_bytes || p.st_bufs == 1) break;
+    }
+    EDS_REQUIRE(ring_budget >= 2 * stage_bytes, "conv2d_igemm: shared memory budget exhausted (stage %d B)", stage_bytes);
+    p.stages = std::min(kMaxStages, ring_budget / stage_bytes);
     p.tmem_cols = std::max(32, pow2_ceil(2 * p.block_n));
     p.total_tiles = (int)n_ctas;
-    const size_t smem = (size_t)p.stages * stage_bytes + (size_t)2 * p.st_bufs * p.st_bytes + 1024 /*align slack*/ +
+    const size_t smem = (size_t)p.stages * stage_bytes + (size_t)2 * p.st_bufs * p.st_bytes + (size_t)res_bytes +
+                        1024 /*align slack*/ +
                         (2 * kMaxStages + 4) * 8 + 16;
 
     // input tensor maps: one per (row parity, col parity) plane that a tap touches
@@ -515,6 +585,13 @@ extern "C" int eds_conv2d_igemm_bf16(const void* x, int N, int H, int W, int C, 
                                      int Cout, int R, int S, int stride, int pad, int relu, const void* residual,
                                      void* y, void* stream) {
     return igemm_launch(x, C, nullptr, 0, N, H, W, w, bias, Cout, R, S, stride, pad, relu, residual, y, stream);
+}
+
+extern "C" int eds_conv2d_igemm_bf16_gated(const void* x, int N, int H, int W, int C, const void* w, const float* bias,
+                                           const float* gate, int Cout, int R, int S, int stride, int pad, int relu,
+                                           const void* residual, void* y, void* stream) {
+    EDS_REQUIRE(gate, "conv2d_igemm_gated: gate missing");
+    return igemm_launch(x, C, nullptr, 0, N, H, W, w, bias, Cout, R, S, stride, pad, relu, residual, y, stream, gate);
 }
 
 extern "C" int eds_conv2d_igemm_bf16_2src(const void* x0, int C0, const void* x1, int C1, int N, int H, int W,

@@ -346,6 +346,21 @@ static inline int pow2_floor(int v) {
     return p;
 }
 
+// out[n][co] = w[co][:] . m[n][:] + b[co]: one warp per output, lanes along Cin (the SE squeeze of conv3's output
+// from the channel means of its input; N * Cout <= 48 * 1024 dots of length <= 512).
+__global__ void __launch_bounds__(256)
+affine_rows_kernel(const float* __restrict__ m, int Cin, const float* __restrict__ w, const float* __restrict__ b,
+                   int Cout, int total, float* __restrict__ out) {
+    const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (idx >= total) return;
+    const int n = idx / Cout, co = idx - n * Cout;
+    float acc = 0.f;
+    for (int ci = lane; ci < Cin; ci += 32) acc = fmaf(__ldg(w + (int64_t)co * Cin + ci), __ldg(m + (int64_t)n * Cin + ci), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) out[idx] = acc + (b ? b[co] : 0.f);
+}
+
 }  // namespace eds
 
 using namespace eds;
@@ -424,6 +439,14 @@ extern "C" int eds_se_scale_add_relu(const void* x, const float* gate, const voi
     EDS_DISPATCH_DTYPE(dtype, T, (se_scale_add_relu_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
                                      (const T*)x, gate, (const T*)residual, HW, C / 8, total, (T*)y)));
     return check_launch("se_scale_add_relu_kernel");
+}
+
+extern "C" int eds_affine_rows(const float* m, int N, int Cin, const float* w, const float* b, int Cout, float* out,
+                               void* stream) {
+    EDS_REQUIRE(m && w && out && N > 0 && Cin > 0 && Cout > 0, "affine_rows: bad arguments");
+    const int total = N * Cout;
+    affine_rows_kernel<<<ceil_div(total, 8), 256, 0, as_stream(stream)>>>(m, Cin, w, b, Cout, total, out);
+    return check_launch("affine_rows_kernel");
 }
 
 extern "C" int eds_upsample2x_concat(const void* x0, int N, int h, int w, int C0, int mode,

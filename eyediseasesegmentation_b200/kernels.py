@@ -362,6 +362,42 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], strid
     return out
 
 
+def conv1x1_se(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], gate: torch.Tensor,
+               residual: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """SE bottleneck tail in the convolution's epilogue: relu((conv1x1(x) + bias) * gate[n, co] + residual), bf16 on
+    the tcgen05 kernel.  x [N,H,W,C], w [Cout,1,1,C], gate [N,Cout] fp32, residual [N,H,W,Cout]."""
+    _chk(x, w, bias, gate, residual, out)
+    N, H, W_, Cin = x.shape
+    Cout = w.shape[0]
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.shape == (Cout, 1, 1, Cin)
+    assert gate.shape == (N, Cout) and gate.dtype == torch.float32 and residual.shape == (N, H, W_, Cout)
+    if out is None:
+        out = torch.empty((N, H, W_, Cout), dtype=x.dtype, device=x.device)
+    trace = CONV_TRACE
+    if trace is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    _TAG[0] = "conv_igemm 1x1 (tcgen05)"
+    check(_lib.lib().eds_conv2d_igemm_bf16_gated(_p(x), N, H, W_, Cin, _p(w), _p(bias), _p(gate), Cout, 1, 1, 1, 0, 1,
+                                                 _p(residual), _p(out), _stream()))
+    if trace is not None:
+        ev1.record()
+        trace.append((2.0 * N * H * W_ * Cout * Cin, ev0, ev1, (N, H, W_, Cin, Cout, 1, 1)))
+    return out
+
+
+def affine_rows(m: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], out: Optional[torch.Tensor] = None):
+    """m [N,Cin] fp32, w [Cout,Cin] fp32 -> [N,Cout] = m @ w.T + b."""
+    _chk(m, w, b, out)
+    N, Cin = m.shape
+    Cout = w.shape[0]
+    assert w.shape == (Cout, Cin) and m.dtype == torch.float32 and w.dtype == torch.float32
+    if out is None:
+        out = torch.empty((N, Cout), dtype=torch.float32, device=m.device)
+    check(_lib.lib().eds_affine_rows(_p(m), N, Cin, _p(w), _p(b), Cout, _p(out), _stream()))
+    return out
+
+
 def conv3x3_small(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = True,
                   up_mode: int = _lib.UP_NONE, cgate: Optional[torch.Tensor] = None,
                   sgate: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:

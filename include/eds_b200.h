@@ -189,6 +189,19 @@ EDS_API int eds_conv2d_igemm_bf16(const void* x, int N, int H, int W, int C, con
                           const float* bias, int Cout, int R, int S, int stride, int pad,
                           int relu, const void* residual, void* y, void* stream);
 
+/* The same with a squeeze-excitation scale in the epilogue: y = relu((conv + bias) * gate[n][co] + residual),
+ * gate [N][Cout] fp32.  The SE bottleneck's conv3 has no activation, so the channel means its SE module squeezes
+ * are an affine function of the channel means of conv3's INPUT (eds_affine_rows): the gate is known before conv3
+ * runs, and `x * se(x) + residual -> ReLU` (Cadene SENet bottleneck) happens on the accumulators
+ * instead of in three more passes over the 4x wider map. */
+EDS_API int eds_conv2d_igemm_bf16_gated(const void* x, int N, int H, int W, int C, const void* w,
+                                const float* bias, const float* gate, int Cout, int R, int S, int stride,
+                                int pad, int relu, const void* residual, void* y, void* stream);
+
+/* out[n][co] = sum_ci w[co][ci] * m[n][ci] + b[co]   (fp32; w [Cout][Cin] row-major, b may be NULL). */
+EDS_API int eds_affine_rows(const float* m, int N, int Cin, const float* w, const float* b, int Cout, float* out,
+                    void* stream);
+
 /* Same contract on CUDA cores with fp32 accumulate for either storage type; used for
  * the fp32 parity mode and as the cross-check of the tensor-core kernel.  w has the
  * activation dtype. */

@@ -966,3 +966,27 @@ def test_gated_stats_multi_equals_one_pass_per_consumer(C, gated, n_cons, dtype)
     for (ws, m, off, d), (m_ref, d_ref) in zip(cons, want):
         assert (m - m_ref).abs().max().item() < 1e-5 * max(1.0, m_ref.abs().max().item())
         assert (d - d_ref).abs().max().item() < 2e-5 * max(1.0, d_ref.abs().max().item())
+
+
+@pytest.mark.parametrize("N,H,Cin,Cout", [(3, 40, 64, 256), (2, 19, 128, 512), (5, 8, 256, 1024)])
+def test_se_tail_in_conv3_epilogue(N, H, Cin, Cout):
+    """SE bottleneck tail fused into conv3 (Cadene SENet bottleneck, SURVEY A.1: conv3 + BN, no activation, then
+    x * se(x) + residual -> ReLU): (1) the squeeze -- channel means of conv3's OUTPUT -- equals the affine map of the
+    channel means of its INPUT (eds_affine_rows), because conv3 is linear; (2) eds_conv2d_igemm_bf16_gated =
+    relu((conv + bias) * gate + residual) against fp32 PyTorch and against the unfused kernel sequence."""
+    x = rnd(N, H, H, Cin, seed=31).bfloat16()
+    w = (rnd(Cout, 1, 1, Cin, seed=32) / math.sqrt(Cin)).bfloat16()
+    b = rnd(Cout, seed=33) * 0.1
+    res = rnd(N, H, H, Cout, seed=34).bfloat16()
+    y3 = K.conv2d(x, w, b, 1, 0, False, None, impl="tc")                         # what round 1 wrote to HBM
+    squeeze = K.affine_rows(K.channel_mean(x), w.float().reshape(Cout, Cin).contiguous(), b)
+    ref_sq = torch.einsum("nhwc,oc->no", x.float(), w.float().reshape(Cout, Cin)) / (H * H) + b
+    assert (squeeze - ref_sq).abs().max().item() < 1e-4
+    assert (squeeze - K.channel_mean(y3)).abs().max().item() < 5e-3             # y3 is bf16-rounded per element
+    gate = torch.rand(N, Cout, device=DEV)
+    got = K.conv1x1_se(x, w, b, gate, res).float()
+    ref = F.relu((torch.einsum("nhwc,oc->nhwo", x.float(), w.float().reshape(Cout, Cin)) + b) * gate.view(N, 1, 1, Cout)
+                 + res.float())
+    assert rel_err(got, ref) < 4e-3
+    unfused = K.se_scale_add_relu(y3, gate, res).float()
+    assert rel_err(got, unfused) < 6e-3
