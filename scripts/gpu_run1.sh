@@ -1,9 +1,10 @@
 cd $GRAFT_REPO_ROOT
-python -m pytest tests/test_kernels_gpu.py tests/test_parity_gpu.py tests/test_golden_gpu.py tests/test_configs_gpu.py -q -x 2>&1 | tail -4
-python bench.py --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench9.json 2> gpurun_out/r02_bench9.err; tail -2 gpurun_out/r02_bench9.err; python - <<'P'
+python -m pytest tests -m gpu -q 2>&1 | tail -3
+python __graft_entry__.py smoke 2>&1 | tail -1
+python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench10.json 2> gpurun_out/r02_bench10.err; tail -2 gpurun_out/r02_bench10.err; python - <<'P'
 import json
-d=json.load(open('gpurun_out/r02_bench9.json'))
-print({k:d[k] for k in ['value','ms_per_step','gpu_launches']}, d['e2e']['value'], 'conv', d['roofline']['frac'], d['clocks'])
+d=json.load(open('gpurun_out/r02_bench10.json'))
+print({k:d[k] for k in ['value','ms_per_step','gpu_launches']}, d['e2e']['value'], 'conv', d['roofline']['frac'], 'hist', d['roofline_hist']['frac'], 'blend', d['roofline_blend']['frac'], d['clocks'])
 print(d['time_shares'])
-print(d['other_configs']['cfg2_uppse50_bf16_16x1024_flip'])
+print(d['other_configs'])
 P
