@@ -172,6 +172,7 @@ def run_b200(args):
     pinned_out = {les: [torch.empty((H, W), dtype=torch.float32).pin_memory() for _ in range(2)] for les in LESIONS}
     pinned_scores = torch.empty((len(LESIONS), n_set, 2 + 2 * 19 + 2), dtype=torch.float64).pin_memory()
     allreduce_ms = []
+    up_stream, down_stream = torch.cuda.Stream(), torch.cuda.Stream()
 
     # images whose (image, tile) units are dealt together: the whole set while its canvases fit comfortably (the
     # units then balance to within one tile per rank and the batches have one shape); the file drivers use
@@ -185,12 +186,31 @@ def run_b200(args):
         probability maps and the scores go back to pinned host memory (e2e)."""
         hist = torch.zeros((len(LESIONS), count, 2, _lib.PR_BINS), dtype=torch.int32, device=dev)
         strad = torch.zeros((len(LESIONS), count, _lib.PR_NTHRESH, 2), dtype=torch.int32, device=dev)
-        for g in range(0, count, group_size):
-            group = list(range(g, min(g + group_size, count)))
-            if host:
+        main = torch.cuda.current_stream()
+        # host mode: groups of max(N, 4) images so that the upload of group g+1 (copy stream) and the download of
+        # finished maps (another copy stream) overlap the compute of group g; the units of a group still balance
+        gs = group_size if not host else max(world, 4)
+        starts = list(range(0, count, gs))
+
+        def upload(g):
+            group = list(range(g, min(g + gs, count)))
+            with torch.cuda.stream(up_stream):
                 imgs = [host_imgs[i].to(dev, non_blocking=True) for i in group]
                 gts = {les: [host_masks[i][les].to(dev, non_blocking=True) for i in group] for les in LESIONS}
+                ev = torch.cuda.Event()
+                ev.record(up_stream)
+            return group, imgs, gts, ev
+
+        pending = upload(starts[0]) if host else None
+        for gi, g in enumerate(starts):
+            if host:
+                group, imgs, gts, ev = pending
+                main.wait_event(ev)
+                for t_ in imgs + [m for les in LESIONS for m in gts[les]]:
+                    t_.record_stream(main)
+                pending = upload(starts[gi + 1]) if gi + 1 < len(starts) else None
             else:
+                group = list(range(g, min(g + gs, count)))
                 imgs = [dev_imgs[i] for i in group]
                 gts = {les: [dev_masks[i][les] for i in group] for les in LESIONS}
             for li, les in enumerate(LESIONS):
@@ -200,8 +220,14 @@ def run_b200(args):
                     for r, i in enumerate(group):
                         if world > 1:
                             dist.reduce(canvases[r], dst=i % world, op=dist.ReduceOp.SUM)   # pieces -> the writer rank
-                        if i % world == rank:
-                            pinned_out[les][(i // world) % 2].copy_(canvases[r], non_blocking=True)
+                    down_stream.wait_stream(main)
+                    with torch.cuda.stream(down_stream):
+                        for r, i in enumerate(group):
+                            if i % world == rank:
+                                pinned_out[les][(i // world) % 2].copy_(canvases[r], non_blocking=True)
+                                canvases[r].record_stream(down_stream)
+        if host:
+            main.wait_stream(down_stream)
         if world > 1:                              # the path's single data collective: per-image integer histograms
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a0.record()
@@ -230,10 +256,11 @@ def run_b200(args):
         so that no CUDA graph is captured inside a timed region."""
         sizes = set()
         for count in {args.steps, args.warmup}:
-            for g in range(0, count, group_size):
-                n_units = (min(g + group_size, count) - g) * TILES
-                mine = [u for u in range(n_units) if (g * TILES + u) % world == rank]
-                sizes |= {len(b) for b in partition.batches(mine, args.tiles)}
+            for gs in {group_size, max(world, 4)}:          # resident run / host run (see run_set)
+                for g in range(0, count, gs):
+                    n_units = (min(g + gs, count) - g) * TILES
+                    mine = [u for u in range(n_units) if (g * TILES + u) % world == rank]
+                    sizes |= {len(b) for b in partition.batches(mine, args.tiles)}
         deaug = drv.fused_blend_views(models[LESIONS[0]], tfm, S, W)       # the forward the tile path will call
         for les in LESIONS:
             for b in sorted(sizes):
@@ -312,9 +339,10 @@ def run_b200(args):
             "e2e": {"value": e2e, "unit": "images/s",
                     "h2d_bytes_per_step": world * (H * W * 3 + len(LESIONS) * H * W),
                     "d2h_bytes_per_step": len(LESIONS) * (H * W * 4 + 42 * 8),
-                    "what": "each rank uploads the group's images + masks from pinned host memory; the owned pieces of "
-                            "the probability maps are summed onto one rank per image (NCCL) and copied to pinned host "
-                            "memory with the scores"},
+                    "what": "groups of max(N, 4) images: each rank uploads the group's images + masks from pinned host "
+                            "memory (copy stream, one group ahead); the owned pieces of the probability maps are summed "
+                            "onto one rank per image (NCCL) and copied to pinned host memory (second copy stream) with "
+                            "the scores"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_hist": hist_roof,
             "roofline_blend": blend_roof, "time_shares": shares,
         }
