@@ -703,7 +703,7 @@ def run_reference(args):
     tiles, scores = [], []
     t_start = time.perf_counter()
     for _ in range(max(1, args.steps)):
-        tiles.append(cpu_tile_sample(threads))
+        tiles.append(cpu_tile_sample(threads, views=args.ref_views) * (VIEWS / args.ref_views))
         scores.append(cpu_score_sample())
         if time.perf_counter() - t_start > 150:
             break
@@ -734,6 +734,8 @@ def main():
     ap.add_argument("--group", type=int, default=0, help="images per unit-dealing group (0 = the whole set)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the cfg-1 / cfg-2 / cfg-5 side measurements")
+    ap.add_argument("--ref-views", type=int, default=VIEWS, choices=[1, VIEWS],
+                    help="--impl reference: TTA views per sampled tile (8 = the workload; 1 only for quick contract tests)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
