@@ -63,6 +63,7 @@ def _dt(t: torch.Tensor) -> int:
 
 
 def _chk(*tensors: Optional[torch.Tensor]) -> None:
+    cur = -1
     for t in tensors:
         if t is None:
             continue
@@ -70,6 +71,12 @@ def _chk(*tensors: Optional[torch.Tensor]) -> None:
             raise ValueError("libeds_b200 kernels need CUDA tensors (there is no CPU path)")
         if not t.is_contiguous():
             raise ValueError("tensor must be contiguous")
+        if cur < 0:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            # the launch goes to the CURRENT device's stream: a tensor of another GPU would be dereferenced there
+            raise ValueError(f"tensor lives on cuda:{t.device.index} but the current device is cuda:{cur}; wrap the call "
+                             "in `with torch.cuda.device(tensor.device):` (B200SegModel.forward does)")
 
 
 def _p(t: Optional[torch.Tensor]) -> Optional[int]:
