@@ -41,7 +41,7 @@ WORKLOAD = ("cfg4: fixed set of `steps` distinct 2848x4288 images x 4 lesion mod
             "random init), 6 tiles of 1024^2 x 8 D4 views each, sigmoid + x2 paste + PR histogram/scan")
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu --set full captures
 TRAFFIC = {
-    "conv": {"bytes": 1116.27e6 + 251.76e6, "source": "profiles/r01_kernels_full.md #0 (conv_igemm 1024->256 @256^2 x8: "
+    "conv": {"bytes": 1115.83e6 + 252.90e6, "source": "profiles/r02_kernels_full.md #0 (conv_igemm 1024->256 @256^2 x8: "
              "1074 MB algorithmic)"},
     "hist": {"bytes": 1653.80e6 + 4.69e6, "source": "profiles/r02_hist_full.md #0 (27 images, 1648.7 MB algorithmic)"},
     "blend": {"bytes": 108.50e6 + 18.03e6, "source": "profiles/r02_blend_fused_full.md #0 (tta_blend_x2: blocks under a later "
