@@ -1,7 +1,7 @@
 cd $GRAFT_REPO_ROOT
-for i in 1 2; do
-EDS_SE_EPILOGUE=0 python scripts/dev_pass_probe.py 2>&1 | tail -1
-EDS_SE_EPILOGUE=1 EDS_SE_EPILOGUE_MIN_PIXELS=999999999 python scripts/dev_pass_probe.py 2>&1 | tail -1
-EDS_SE_EPILOGUE=1 python scripts/dev_pass_probe.py 2>&1 | tail -1
-EDS_SE_EPILOGUE=1 EDS_SE_EPILOGUE_MIN_PIXELS=1 python scripts/dev_pass_probe.py 2>&1 | tail -1
-done
+EDS_TAG=plain python scripts/dev_concat_probe.py 2>&1 | tail -8
+cp eyediseasesegmentation_b200/libeds_b200.so /tmp/plain.so; cp eyediseasesegmentation_b200/libeds_stream.so eyediseasesegmentation_b200/libeds_b200.so
+EDS_TAG=stream python scripts/dev_concat_probe.py 2>&1 | tail -8
+python scripts/dev_pass_probe.py 2>&1 | tail -1
+cp /tmp/plain.so eyediseasesegmentation_b200/libeds_b200.so
+python scripts/dev_pass_probe.py 2>&1 | tail -1
