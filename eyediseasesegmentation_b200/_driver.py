@@ -372,11 +372,23 @@ def partitioned_producer(model, transforms, keys, load, S: int, mean, std, tiles
         kept = {}
         unit_offset = 0
         starts = list(range(0, n, ws))
-        mine = prefetched([(lambda g=g: load(keys[g + rank]) if g + rank < n else None) for g in starts])
+        def guarded(g):
+            # a decode error on one rank must reach every rank BEFORE the next collective, or the others hang in it
+            try:
+                return load(keys[g + rank]) if g + rank < n else None
+            except Exception as e:                      # noqa: BLE001 -- re-raised on every rank below
+                return e
+
+        mine = prefetched([(lambda g=g: guarded(g)) for g in starts])
         for g, loaded in zip(starts, mine):
             group = list(range(g, min(g + ws, n)))
             shapes = [None] * ws
-            dist.all_gather_object(shapes, None if loaded is None else tuple(loaded[0].shape[:2]))
+            failed = isinstance(loaded, Exception)
+            dist.all_gather_object(shapes, ("error", f"rank {rank}: {loaded!r}") if failed else
+                                   (None if loaded is None else tuple(loaded[0].shape[:2])))
+            errors = [s_[1] for s_ in shapes if isinstance(s_, tuple) and s_ and s_[0] == "error"]
+            if errors:
+                raise RuntimeError("image loading failed: " + "; ".join(errors))
             images, gts = [], []
             for r, i in enumerate(group):
                 H, W = shapes[r]
