@@ -389,3 +389,30 @@ def test_two_rank_tile_partition_histograms_sum_to_single_process(tmp_path):
         assert p.returncode == 0, err[-2000:]
         res = json.loads([ln for ln in out.splitlines() if ln.startswith("RESULT")][0][6:])
         assert res["ok"] and res["total"] == 150 * 210 * 2 + 140 * 130
+
+
+def test_skip_consumer_plan_of_the_dense_decoder():
+    """Engine._plan_skip_consumers (host logic of eds_gated_stats_multi): which SCSE attention1 blocks read a skip
+    source at its own resolution, and at which channel offset of their concat -- derived from the block list and
+    checked here against the concat order of unetplusplusstar.py:239-263 ([x_up, dense skips by depth, encoder
+    feature]); MHCA blocks (x_0_0, x_0_1, x_1_1) take no statistics and sources with one consumer are left out."""
+    from eyediseasesegmentation_b200.archs.engine import Engine
+    from eyediseasesegmentation_b200.archs.spec import dense_decoder_blocks
+    eng = Engine.__new__(Engine)
+    eng.blocks = dense_decoder_blocks((3, 64, 256, 512, 1024, 2048))
+    scse = ["x_2_2", "x_3_3", "x_1_2", "x_2_3", "x_0_2", "x_1_3", "x_0_3", "x_0_4"]
+    eng.w = {f"decoder.blocks.{n}.attention1.sse": 1 for n in scse}
+    feats = [torch.empty(1, 1, 1, c) for c in (64, 256, 512, 1024, 2048)]
+    plan = eng._plan_skip_consumers(feats)
+    a1 = lambda n: f"decoder.blocks.{n}.attention1"      # noqa: E731
+    assert plan["f1"] == [(a1("x_3_3"), 256, 320), (a1("x_2_3"), 320, 384), (a1("x_1_3"), 384, 448), (a1("x_0_3"), 256, 320)]
+    assert plan["x_3_3"] == [(a1("x_2_3"), 256, 384), (a1("x_1_3"), 320, 448), (a1("x_0_3"), 192, 320)]
+    assert plan["x_2_3"] == [(a1("x_1_3"), 256, 448), (a1("x_0_3"), 128, 320)]
+    assert plan["f2"] == [(a1("x_2_2"), 512, 768), (a1("x_1_2"), 768, 1024), (a1("x_0_2"), 640, 896)]
+    assert plan["x_2_2"] == [(a1("x_1_2"), 512, 1024), (a1("x_0_2"), 384, 896)]
+    assert set(plan) == {"f1", "f2", "x_3_3", "x_2_3", "x_2_2"}          # x_1_3, x_1_2, f3, f4: one SCSE consumer or none
+    # every offset + source width stays inside the consumer's concat, offsets are multiples of 8 (vector loads)
+    ch = {"f1": 64, "f2": 256, "x_3_3": 64, "x_2_3": 64, "x_2_2": 256}
+    for src, cons in plan.items():
+        for (_, off, ctot) in cons:
+            assert off % 8 == 0 and off + ch[src] <= ctot
