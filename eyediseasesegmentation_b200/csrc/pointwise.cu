@@ -300,24 +300,20 @@ head_conv3x3_kernel(const T* __restrict__ x, int N, int H, int W, int C, const f
         for (int k = 0; k < classes; ++k) {
             float acc = bias ? bias[k] : 0.f;
             for (int c = 0; c < C; c += 8) {
-                float v[9][8];
+                float2 v[9][4];
 #pragma unroll
-                for (int q = 0; q < 9; ++q) Vec8<T>::ld(xp[q] + c, v[q]);
+                for (int q = 0; q < 9; ++q) V8<T>::ld(xp[q] + c, v[q]);
 #pragma unroll
                 for (int q = 0; q < 9; ++q) {
-                    // 8 weights per two 128-bit shared loads (one scalar load per multiply made this
-                    // kernel LDS-bound)
+                    // 8 weights per two 128-bit shared loads (one scalar load per multiply made this kernel
+                    // LDS-bound); the products run on the packed fp32 pipe, two per instruction
                     const float4* wp = reinterpret_cast<const float4*>(s_w + (k * 9 + q) * C + c);
                     const float4 w0 = wp[0], w1 = wp[1];
-                    float d = v[q][0] * w0.x;
-                    d = fmaf(v[q][1], w0.y, d);
-                    d = fmaf(v[q][2], w0.z, d);
-                    d = fmaf(v[q][3], w0.w, d);
-                    d = fmaf(v[q][4], w1.x, d);
-                    d = fmaf(v[q][5], w1.y, d);
-                    d = fmaf(v[q][6], w1.z, d);
-                    d = fmaf(v[q][7], w1.w, d);
-                    acc = fmaf(valid[q], d, acc);
+                    float2 d = __fmul2_rn(v[q][0], make_float2(w0.x, w0.y));
+                    d = __ffma2_rn(v[q][1], make_float2(w0.z, w0.w), d);
+                    d = __ffma2_rn(v[q][2], make_float2(w1.x, w1.y), d);
+                    d = __ffma2_rn(v[q][3], make_float2(w1.z, w1.w), d);
+                    acc = fmaf(valid[q], d.x + d.y, acc);
                 }
             }
             logits[(((int64_t)n * classes + k) * H + oy) * W + ox] = acc;
