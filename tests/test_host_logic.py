@@ -416,3 +416,19 @@ def test_skip_consumer_plan_of_the_dense_decoder():
     for src, cons in plan.items():
         for (_, off, ctot) in cons:
             assert off % 8 == 0 and off + ch[src] <= ctot
+
+
+def test_fused_blend_eligibility_is_a_host_decision():
+    """eds_tta_blend_supported needs no GPU: the one-kernel blend is taken for flip / rot90 views of a square tile
+    whose size is a multiple of 64 and a canvas whose rows are 16-byte aligned; everything else falls back to
+    eds_tta_merge + paste (``_driver.fused_blend_views``)."""
+    from eyediseasesegmentation_b200 import kernels as K, _driver as drv
+    for alias, n in (("d4_transform", 8), ("flip_transform", 4), ("hflip_transform", 2)):
+        _, deaug = tta.view_maps(getattr(tta.aliases, alias)(), 1024, 1024)
+        assert len(deaug) == n
+        assert K.tta_blend_supported(n, 1024, deaug, 4288)
+        assert not K.tta_blend_supported(n, 1024, deaug, 4290)           # canvas rows not 16-byte aligned
+    _, deaug96 = tta.view_maps(tta.aliases.d4_transform(), 96, 96)
+    assert not K.tta_blend_supported(8, 96, deaug96, 4288)               # tile size not a multiple of 64
+    assert drv.fused_blend_views(torch.nn.Identity(), tta.aliases.d4_transform(), 1024, 4288) is None   # no forward_tta
+    assert drv.tile_blend_mode(None) == "overwrite"
