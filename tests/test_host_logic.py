@@ -432,3 +432,90 @@ def test_fused_blend_eligibility_is_a_host_decision():
     assert not K.tta_blend_supported(8, 96, deaug96, 4288)               # tile size not a multiple of 64
     assert drv.fused_blend_views(torch.nn.Identity(), tta.aliases.d4_transform(), 1024, 4288) is None   # no forward_tta
     assert drv.tile_blend_mode(None) == "overwrite"
+
+
+_GROUP_WORKER = r"""
+import os, sys, json
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, 'tests'))
+import cv2, numpy as np, torch, torch.distributed as dist
+from eyediseasesegmentation_b200 import _driver as drv, kernels as K, partition, _lib, ttach_compat as tta
+from oracle import pipeline, scoring
+rank = int(sys.argv[1])
+dist.init_process_group('gloo', init_method='tcp://127.0.0.1:{port}', rank=rank, world_size=2)
+
+# ---- numpy stand-ins for the CUDA entry points the driver calls (same arithmetic as the kernels' contracts) so that
+# ---- the REAL _driver.partitioned_group runs on CPU tensors: units, batches, ownership, canvases, histogram rows
+def preprocess_tile(img, y0, x0, S, mean, std, out=None):
+    win = img.numpy()[y0:y0 + 2 * S, x0:x0 + 2 * S]
+    small = cv2.resize(win, (S, S), interpolation=cv2.INTER_LINEAR)
+    out.copy_(torch.from_numpy(pipeline.preprocess(small, mean, std).transpose(2, 0, 1)).float())
+    return out
+def paste_tiles_owned_x2(src, first_tile, dst, origins):
+    S = src.shape[1]
+    H, W = dst.shape
+    cells = partition.owned_cells([(y, y + 2 * S, x, x + 2 * S) for (y, x) in origins], (H, W))
+    for j in range(src.shape[0]):
+        t = first_tile + j
+        up = cv2.resize(src[j].numpy(), (2 * S, 2 * S), interpolation=cv2.INTER_LINEAR)
+        for (y, x, h, w) in cells[t]:
+            dst[y:y + h, x:x + w] = torch.from_numpy(up[y - origins[t][0]:y - origins[t][0] + h, x - origins[t][1]:x - origins[t][1] + w])
+def _bin(prob, gt, hist):
+    key = scoring.score_key(prob).ravel()
+    for cls in (0, 1):
+        hist[cls] += torch.from_numpy(np.bincount(key[gt.ravel() == cls], minlength=_lib.PR_BINS).astype(np.int32))
+def pr_hist_rects(prob, gt, rects, hist, strad):
+    for (y, x, h, w) in rects:
+        _bin(prob.numpy()[y:y + h, x:x + w], gt.numpy()[y:y + h, x:x + w], hist)
+def pr_hist(prob, gt, hist=None, strad=None, splits=0):
+    _bin(prob.numpy(), gt.numpy(), hist[0])
+    return hist, strad
+K.preprocess_tile, K.paste_tiles_owned_x2, K.pr_hist_rects, K.pr_hist = preprocess_tile, paste_tiles_owned_x2, pr_hist_rects, pr_hist
+
+class Pointwise(torch.nn.Module):
+    def forward(self, x):
+        return x[:, 0:1] * 0.7 - x[:, 1:2] * 0.3 + x[:, 2:3] * 0.1
+model, tfm = Pointwise(), tta.aliases.d4_transform()
+S = 64
+mean, std = pipeline.DATASET_STATS['IDRiD']
+rng = np.random.default_rng(8)
+shapes = [(300, 420), (280, 302), (330, 290)]
+images = [torch.from_numpy(rng.integers(0, 256, size=s + (3,), dtype=np.uint8)) for s in shapes]
+gts = [torch.from_numpy((rng.random(s) < 0.2).astype(np.uint8)) for s in shapes]
+hist = torch.zeros((len(shapes), 2, _lib.PR_BINS), dtype=torch.int32)
+strad = torch.zeros((len(shapes), _lib.PR_NTHRESH, 2), dtype=torch.int32)
+canvases, nxt = drv.partitioned_group(model, tfm, images, gts, S, mean, std, hist, strad, 0, rank, 2, tiles_per_batch=4)
+partition.allreduce_sum_(hist)
+for c in canvases:
+    dist.all_reduce(c)
+ok_units = nxt == sum(drv.tile_plan(s[0], s[1], S).n for s in shapes)
+ok_map, ok_hist = True, True
+for k, s in enumerate(shapes):
+    want = pipeline.tiled_probability_map(images[k].numpy(), model, S, mean, std, 'd4')
+    ok_map &= bool(np.abs(canvases[k].numpy() - want).max() < 1e-6)
+    full = torch.zeros((2, _lib.PR_BINS), dtype=torch.int32)
+    _bin(canvases[k].numpy(), gts[k].numpy(), full)
+    ok_hist &= bool(torch.equal(hist[k], full))
+mine = len([u for u in range(nxt) if u % 2 == rank])
+print('RESULT' + json.dumps(dict(ok_units=bool(ok_units), ok_map=ok_map, ok_hist=ok_hist, mine=mine, total=int(nxt))))
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_partitioned_group_on_cpu_equals_the_oracle_pipeline(tmp_path):
+    """The REAL _driver.partitioned_group under gloo, world size 2, with numpy stand-ins for the five CUDA entry
+    points it calls: the two ranks' canvases sum to oracle/pipeline.py's single-process map (the reference's tile
+    loop restated), the all-reduced integer histograms equal the histogram of that map bin for bin, and the
+    (image, tile) units split evenly."""
+    import json
+    port = 29120 + os.getpid() % 300
+    code = _GROUP_WORKER.format(root=ROOT, port=port)
+    procs = [subprocess.Popen([sys.executable, "-c", code, str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                              text=True) for r in range(2)]
+    seen = []
+    for p in procs:
+        out, err = p.communicate(timeout=600)
+        assert p.returncode == 0, err[-3000:]
+        res = json.loads([ln for ln in out.splitlines() if ln.startswith("RESULT")][0][6:])
+        assert res["ok_units"] and res["ok_map"] and res["ok_hist"], res
+        seen.append(res["mine"])
+    assert sum(seen) == res["total"] and abs(seen[0] - seen[1]) <= 1
