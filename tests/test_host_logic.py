@@ -519,3 +519,83 @@ def test_two_rank_partitioned_group_on_cpu_equals_the_oracle_pipeline(tmp_path):
         assert res["ok_units"] and res["ok_map"] and res["ok_hist"], res
         seen.append(res["mine"])
     assert sum(seen) == res["total"] and abs(seen[0] - seen[1]) <= 1
+
+
+_PRODUCER_WORKER = _GROUP_WORKER.split("class Pointwise")[0] + r"""
+def pr_scan(hist, strad):
+    # totals exact, AP / ROC read off the bins as sklearn does on key-quantised scores
+    from sklearn.metrics import average_precision_score, roc_auc_score
+    n = hist.shape[0]
+    ap, roc = np.full(n, np.nan), np.full(n, np.nan)
+    counts = torch.zeros((n, _lib.PR_NTHRESH, 2), dtype=torch.int64)
+    totals = torch.zeros((n, 2), dtype=torch.int64)
+    for i in range(n):
+        neg, pos = hist[i, 0].numpy().astype(np.int64), hist[i, 1].numpy().astype(np.int64)
+        totals[i, 0], totals[i, 1] = int(pos.sum()), int(neg.sum())
+        if pos.sum() and neg.sum():
+            keys = np.arange(_lib.PR_BINS)
+            y = np.concatenate([np.ones(_lib.PR_BINS), np.zeros(_lib.PR_BINS)])
+            s = np.concatenate([keys, keys]); w = np.concatenate([pos, neg]).astype(float)
+            ap[i] = average_precision_score(y, s, sample_weight=w)
+            roc[i] = roc_auc_score(y, s, sample_weight=w)
+    return torch.from_numpy(ap), torch.from_numpy(roc), counts, totals
+K.pr_scan = pr_scan
+drv.device = lambda: torch.device('cpu')
+_reduce = dist.reduce
+class Pointwise(torch.nn.Module):
+    def forward(self, x):
+        return x[:, 0:1] * 0.7 - x[:, 1:2] * 0.3 + x[:, 2:3] * 0.1
+model, tfm = Pointwise(), tta.aliases.d4_transform()
+S = 64
+mean, std = pipeline.DATASET_STATS['IDRiD']
+rng = np.random.default_rng(8)
+shapes = [(300, 420), (280, 302), (330, 290)]          # three images, two ranks: a ragged last group
+data = {{f'img{{i}}': (rng.integers(0, 256, size=s + (3,), dtype=np.uint8), (rng.random(s) < 0.2).astype(np.uint8))
+        for i, s in enumerate(shapes)}}
+if {empty_last}:
+    data['img2'][1][:] = 0                              # an image without positives
+loads = []
+def load(key):
+    loads.append(key)
+    return data[key]
+produce = drv.partitioned_producer(model, tfm, sorted(data), load, S, mean, std, tiles_per_batch=4)
+items = list(produce())
+from eyediseasesegmentation_b200 import aucpr
+auc = aucpr.get_auc(items, dict())
+want = {{k: pipeline.tiled_probability_map(v[0], model, S, mean, std, 'd4') for k, v in data.items()}}
+ok = True
+held = []
+for (pred, gt, name) in items:
+    assert pred._eds_scores.replicated
+    if np.asarray(pred).size:
+        held.append(name)
+        ok &= bool(np.abs(np.asarray(pred) - want[name]).max() < 1e-6) and bool(np.array_equal(gt, data[name][1]))
+    else:
+        ok &= gt is None
+ref = scoring.get_auc([(scoring.score_key(want[k]).astype(np.float64), data[k][1], k) for k in sorted(data)])
+print('RESULT' + json.dumps(dict(ok=bool(ok), names=[n for _, _, n in items], held=held, loads=loads, auc=auc, ref=ref)))
+dist.destroy_process_group()
+"""
+
+
+@pytest.mark.parametrize("empty_last", [False, True])
+def test_two_rank_partitioned_producer_on_cpu(tmp_path, empty_last):
+    """_driver.partitioned_producer (the generator behind tta_patches under torchrun) on two gloo ranks with numpy
+    stand-ins for the CUDA entry points: each rank decodes only its images of a group, every rank yields EVERY image
+    with the global (replicated) scores, the full-resolution map lives on exactly one rank and equals the oracle's
+    tile loop, and get_auc returns the same global mean on both ranks without summing over ranks again."""
+    import json
+    port = 29420 + os.getpid() % 300 + (7 if empty_last else 0)
+    code = _PRODUCER_WORKER.format(root=ROOT, port=port, empty_last=empty_last)
+    procs = [subprocess.Popen([sys.executable, "-c", code, str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                              text=True) for r in range(2)]
+    results = []
+    for p in procs:
+        out, err = p.communicate(timeout=600)
+        assert p.returncode == 0, err[-3000:]
+        results.append(json.loads([ln for ln in out.splitlines() if ln.startswith("RESULT")][0][6:]))
+    for r in results:
+        assert r["ok"] and r["names"] == ["img0", "img1", "img2"]
+        assert abs(r["auc"] - r["ref"]) < 1e-9 and abs(r["auc"] - results[0]["auc"]) < 1e-15
+    assert sorted(results[0]["held"] + results[1]["held"]) == ["img0", "img1", "img2"]
+    assert results[0]["loads"] == ["img0", "img2"] and results[1]["loads"] == ["img1"]
