@@ -6,9 +6,9 @@
                              TTA net -> sigmoid -> cv2 bilinear x2 -> overwrite paste)
   whole_image_probability    src/main/tta.py:108-121 (center crop + cv2 resize to full size)
   ensemble_probability       ensemble.py:86-100 (per-model sigmoid of the D4-mean logits, summed in
-                             model order, divided by the model count).  ensemble.py itself cannot be
-                             imported here (smp / ttach / catalyst / albumentations at module scope), so
-                             this function is a restatement only: parity unpinned for that driver
+                             model order, divided by the model count).  Pinned by tests/golden/ensemble.npz,
+                             written by the reference's own ensemble.py (ref_loader.load_ensemble runs it
+                             with the absent third-party packages restated): tests/test_oracle.py
 
 ``net`` is any callable ``[B,3,S,S] float32 tensor -> logits [B,1,S,S]`` (the oracle nets, or
 the reference modules in the build container).  cv2 is the same library the reference calls.

@@ -156,6 +156,179 @@ def load_pad_img():
     return _load("refdata", "pad_img", os.path.join(REFERENCE_ROOT, "src", "data", "augment_vessel", "pad_img.py"))
 
 
+def build_reference_module(ref, name, cfg):
+    """The reference module behind a registry name, built the way ``archs.get_model(..., training=False)`` builds
+    it (archs/__init__.py:101-130)."""
+    cfg = dict(cfg)
+    if name == "unetplusplusstar":
+        return ref.unetplusplusstar.UnetPlusPlusStar(**cfg)
+    if name == "unetplusplus_deepsup":
+        cfg["deep_supervision"] = False          # archs/__init__.py:118-119 (training=False)
+        return ref.deep_supunetplusplus.UnetPlusPlus(**cfg)
+    if name == "Unet":
+        return ref.smp.Unet(**cfg)
+    raise KeyError(name)
+
+
+def load_ensemble():
+    """The reference's top-level ``ensemble.py`` executed UNMODIFIED, together with the reference's own
+    ``src/data/lesion_dataset.py`` (TestSegmentation), ``src/data/data_transform.py`` (NormalTransform),
+    ``base_utils.get_datapath`` / ``save_output`` and ``aucpr.py``.
+
+    Third-party packages that are not installed are restated: ``ttach`` by
+    ``oracle.nets.tta_mean_logits``, the five ``albumentations`` classes the path touches (Compose, Lambda,
+    LongestMaxSize, PadIfNeeded, ToTensorV2) with cv2, ``catalyst.dl.utils.get_device`` = cpu.
+
+    ``ensemble.py`` is stale against the rest of the reference in four places (listed in the product's
+    ``ensemble.py`` docstring); they are bridged here by ADAPTERS around the reference's own functions, not by
+    editing it: ``TestSegmentation(images, masks, transform=)`` -> ``TestSegmentation(images, False, masks, ...)``;
+    ``get_preprocessing_fn(dataset_name=)`` -> ``grayscale=False``; ``get_auc(gts, preds, config)`` /
+    ``plot_aucpr_curve(gts, preds, outdir, config)`` -> the ``(pred, gt, name)`` generator form of aucpr.py:17,45
+    (first two thresholds returned).  Returns ``(module, captured)``: ``captured`` collects what the adapters saw
+    (``preds``, ``gts``, ``auc``, ``thresholds``, ``masks`` by file name)."""
+    import cv2
+    import numpy as np
+    import torch
+    from . import nets
+
+    ref = load()
+    captured = {"masks": {}}
+
+    class SegmentationTTAWrapper(torch.nn.Module):
+        def __init__(self, model, transforms, merge_mode="mean"):
+            super().__init__()
+            assert merge_mode == "mean"
+            self.model, self.kind = model, transforms
+
+        def forward(self, x):
+            return nets.tta_mean_logits(self.model, x, self.kind)
+
+    _module("ttach", SegmentationTTAWrapper=SegmentationTTAWrapper,
+            aliases=types.SimpleNamespace(d4_transform=lambda: "d4"))
+    _module("pytorch_toolbelt.inference")
+    _module("pytorch_toolbelt.inference.tiles", ImageSlicer=object, TileMerger=object)
+    _module("pytorch_toolbelt.utils", fs=None, image_to_tensor=None)
+    _module("pytorch_toolbelt.utils.torch_utils", to_numpy=None, image_to_tensor=None, tensor_from_rgb_image=None)
+    _module("iglovikov_helper_functions")
+    _module("iglovikov_helper_functions.utils")
+    _module("iglovikov_helper_functions.utils.image_utils", pad=None)
+    dl_utils = _module("catalyst.dl.utils", get_device=lambda: torch.device("cpu"))
+    _module("catalyst.dl", utils=dl_utils)
+
+    # ---- albumentations 1.0 (3P), the classes this path touches
+    def longest_max_size(img, max_size, interpolation):
+        h, w = img.shape[:2]
+        scale = max_size / float(max(h, w))
+        if scale == 1.0:
+            return img
+        return cv2.resize(img, (int(round(w * scale)), int(round(h * scale))), interpolation=interpolation)
+
+    class LongestMaxSize:
+        def __init__(self, max_size=1024, **_):
+            self.max_size = max_size
+
+        def __call__(self, **d):
+            d["image"] = longest_max_size(d["image"], self.max_size, cv2.INTER_LINEAR)
+            if "mask" in d:
+                d["mask"] = longest_max_size(d["mask"], self.max_size, cv2.INTER_NEAREST)
+            return d
+
+    class PadIfNeeded:
+        def __init__(self, min_height, min_width, border_mode=cv2.BORDER_CONSTANT, value=0, **_):
+            assert border_mode == cv2.BORDER_CONSTANT and value == 0
+            self.h, self.w = min_height, min_width
+
+        def _pad(self, a):
+            h, w = a.shape[:2]
+            top = int((self.h - h) / 2.0) if h < self.h else 0
+            left = int((self.w - w) / 2.0) if w < self.w else 0
+            out = np.zeros((max(self.h, h), max(self.w, w)) + a.shape[2:], dtype=a.dtype)
+            out[top:top + h, left:left + w] = a
+            return out
+
+        def __call__(self, **d):
+            d["image"] = self._pad(d["image"])
+            if "mask" in d:
+                d["mask"] = self._pad(d["mask"])
+            return d
+
+    class Lambda:
+        def __init__(self, image=None, **_):
+            self.fn = image
+
+        def __call__(self, **d):
+            d["image"] = self.fn(d["image"])
+            return d
+
+    class ToTensorV2:
+        def __call__(self, **d):
+            d["image"] = torch.from_numpy(np.ascontiguousarray(d["image"].transpose(2, 0, 1)))
+            if "mask" in d:
+                d["mask"] = torch.from_numpy(np.ascontiguousarray(d["mask"]))
+            return d
+
+    class Compose:
+        def __init__(self, transforms, **_):
+            self.transforms = list(transforms)
+
+        def __call__(self, **d):
+            d = dict(d)
+            for t in self.transforms:
+                d = t(**d)
+            return d
+
+    alb = _module("albumentations", Compose=Compose, Lambda=Lambda, LongestMaxSize=LongestMaxSize, PadIfNeeded=PadIfNeeded)
+    _module("albumentations.pytorch", ToTensorV2=ToTensorV2)
+    _module("albumentations.pytorch.transforms", ToTensorV2=ToTensorV2)
+    alb.pytorch = sys.modules["albumentations.pytorch"]
+    _module("albumentations.augmentations")
+    _module("albumentations.augmentations.geometric")
+    _module("albumentations.augmentations.geometric.functional", longest_max_size=longest_max_size)
+    _module("albumentations.augmentations.geometric.resize", RandomScale=object)
+
+    # ---- the reference's own data classes
+    data_dir = os.path.join(REFERENCE_ROOT, "src", "data")
+    _module("refdatapkg")
+    lesion_dataset = _load("refdatapkg", "lesion_dataset", os.path.join(data_dir, "lesion_dataset.py"))
+    data_transform = _load("refdatapkg", "data_transform", os.path.join(data_dir, "data_transform.py"))
+
+    class TestSegmentation(lesion_dataset.TestSegmentation):        # adapter: the call of ensemble.py:78
+        def __init__(self, images, masks=None, transform=None):
+            super().__init__(images, False, masks, transform=transform)
+
+    TestSegmentation.__test__ = False                               # not a pytest class
+
+    def _items(gts, preds):
+        return [(np.asarray(p), np.asarray(g).reshape(np.asarray(p).shape), str(i)) for i, (g, p) in enumerate(zip(gts, preds))]
+
+    def get_auc(gt_masks, tta_predictions, config):                 # adapter: ensemble.py:102 -> aucpr.py:17
+        captured["preds"], captured["gts"] = list(tta_predictions), list(gt_masks)
+        captured["auc"] = float(ref.aucpr.get_auc(_items(gt_masks, tta_predictions), config))
+        return captured["auc"]
+
+    def plot_aucpr_curve(gt_masks, tta_predictions, outdir, config):  # adapter: ensemble.py:105 -> aucpr.py:45
+        th = ref.aucpr.plot_aucpr_curve(_items(gt_masks, tta_predictions), outdir, config)
+        captured["thresholds"] = [float(t) for t in th]
+        return th[0], th[1]
+
+    def save_output(mask, out_path):                                # the reference's own writer, observed
+        captured["masks"][os.path.basename(str(out_path))] = np.array(mask)
+        return ref.base_utils.save_output(mask, out_path)
+
+    archs = _module("src.main.archs",
+                    get_model=lambda model_name, params, training=False: build_reference_module(ref, model_name, params),
+                    get_preprocessing_fn=lambda dataset_name, grayscale=False: get_preprocessing_fn(dataset_name, grayscale))
+    _module("src")
+    _module("src.main", archs=archs)
+    _module("src.main.aucpr", get_auc=get_auc, plot_aucpr_curve=plot_aucpr_curve)
+    _module("src.main.util", get_datapath=ref.base_utils.get_datapath, save_output=save_output)
+    _module("src.data", NormalTransform=data_transform.NormalTransform, TestSegmentation=TestSegmentation)
+    _module("refroot")
+    sys.modules.pop("refroot.ensemble", None)
+    mod = _load("refroot", "ensemble", os.path.join(REFERENCE_ROOT, "ensemble.py"))
+    return mod, captured
+
+
 def get_preprocessing_fn(dataset_name, grayscale=False):
     """archs/__init__.py cannot be imported (it imports every architecture); its
     get_preprocessing_fn (lines 61-99) is executed from source text instead."""

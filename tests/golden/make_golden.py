@@ -26,15 +26,7 @@ import helpers  # noqa: E402
 
 
 def reference_module(ref, name, cfg):
-    cfg = dict(cfg)
-    if name == "unetplusplusstar":
-        return ref.unetplusplusstar.UnetPlusPlusStar(**cfg)
-    if name == "unetplusplus_deepsup":
-        cfg["deep_supervision"] = False          # archs/__init__.py:118-119 (training=False)
-        return ref.deep_supunetplusplus.UnetPlusPlus(**cfg)
-    if name == "Unet":
-        return ref.smp.Unet(**cfg)
-    raise KeyError(name)
+    return ref_loader.build_reference_module(ref, name, cfg)
 
 
 def pad_fixture_only():
@@ -50,9 +42,33 @@ def pad_fixture_only():
     print("pad_img.npz written:", sorted(arrays))
 
 
+def ensemble_fixture_only():
+    """The reference's own top-level ensemble.py (predict + get_best_model, unmodified; see
+    oracle/ref_loader.load_ensemble for the third-party restatements and the four adapters) on two member models and
+    three seeded 64 x 64 images: per-image ensemble probability maps, AUC-PR, thresholds and the written masks."""
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        first = helpers.run_reference_ensemble(tmp)               # random labels: only to learn the probabilities
+    # labels for the committed case: the top 30 % of each probability map with 5 % of the 8 x 8 blocks flipped, so
+    # that precision / recall move over the threshold list and the written masks have content
+    rng = np.random.default_rng(3)
+    gts = []
+    for pred in first["preds"]:
+        flips = np.kron(rng.random((pred.shape[0] // 8, pred.shape[1] // 8)) < 0.05, np.ones((8, 8))).astype(bool)
+        gts.append(((pred > np.quantile(pred, 0.7)) ^ flips).astype(np.uint8))
+    with tempfile.TemporaryDirectory() as tmp:
+        out = helpers.run_reference_ensemble(tmp, gts=np.stack(gts))
+    assert np.array_equal(out["gts"], np.stack(gts)) and np.array_equal(out["preds"], first["preds"])
+    np.savez_compressed(os.path.join(HERE, "ensemble.npz"), **out)
+    print("ensemble.npz written:", {k: getattr(v, "shape", v) for k, v in out.items()}, "auc", float(out["auc"]),
+          "thresholds", out["thresholds"].tolist())
+
+
 def main():
-    if len(sys.argv) > 1 and sys.argv[1] == "pad":     # only the fixture added in round 2
+    if len(sys.argv) > 1 and sys.argv[1] == "pad":     # only the fixtures added in round 2
         return pad_fixture_only()
+    if len(sys.argv) > 1 and sys.argv[1] == "ensemble":
+        return ensemble_fixture_only()
     ref = ref_loader.load()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
 
@@ -110,6 +126,8 @@ def main():
     json.dump(stat, open(os.path.join(HERE, "stat_result.json"), "w"), indent=1)
     # 6. vessel padding: the reference's own pad_img.pad, file to file, on tiny seeded images / labels
     pad_fixture_only()
+    # 7. the reference's ensemble.py end to end
+    ensemble_fixture_only()
     print("golden fixtures written to", HERE)
 
 

@@ -192,3 +192,93 @@ def read_pad_outputs(directory):
     import cv2
     import os
     return {f: cv2.imread(os.path.join(directory, f), cv2.IMREAD_UNCHANGED) for f in sorted(os.listdir(directory))}
+
+
+# ------------------------------------------------------------------ ensemble (reference ensemble.py)
+ENSEMBLE_S = 64
+ENSEMBLE_SPECS = [("unetplusplus_deepsup", dict(encoder_name="resnet34", encoder_weights=None, classes=1)),
+                  ("Unet", dict(encoder_name="resnet34", encoder_weights=None, classes=1))]
+ENSEMBLE_IMG_DIR = "data/raw/IDRiD/1. Original Images/b. Testing Set"                   # ensemble.py:65
+ENSEMBLE_MASK_DIR = "data/raw/IDRiD/2. All Segmentation Groundtruths/b. Testing Set"    # ensemble.py:66
+
+
+def ensemble_state_dicts():
+    """The two member models of the ensemble fixture: deterministic product-initialised weights, segmentation head
+    scaled up so that the probabilities spread over (0, 1)."""
+    out = []
+    for i, (name, cfg) in enumerate(ENSEMBLE_SPECS):
+        sd = {k: v.clone() for k, v in build_product_model(name, cfg, seed=1999 + i).state_dict().items()}
+        sd["segmentation_head.0.weight"] *= 8.0
+        out.append(sd)
+    return out
+
+
+def ensemble_oracle_nets(state_dicts):
+    return [lambda t, sd=state_dicts[0]: nets.unetplusplus_forward(sd, t),
+            lambda t, sd=state_dicts[1]: nets.unet_forward(sd, t)]
+
+
+def make_ensemble_case(root, gts=None, n_images=3, seed=11):
+    """Under ``root``: the IDRiD test folders at the paths ensemble.py hard-codes (S x S JPEG images + 'EX' label
+    TIFFs) and one log directory per member model (config.json + checkpoints/best.pth).  ``gts`` [n, S, S] {0,1}:
+    the label maps to write (the committed fixture's, which were derived from the ensemble's own probabilities so
+    that the PR curve and the masks are not degenerate); random blocks without it.  -> (config, logdirs)"""
+    import json
+    import numpy as np
+    from pathlib import Path
+    from PIL import Image
+    root = Path(root)
+    S = ENSEMBLE_S
+    img_dir = root / ENSEMBLE_IMG_DIR
+    mask_dir = root / ENSEMBLE_MASK_DIR / "3. Hard Exudates"
+    img_dir.mkdir(parents=True)
+    mask_dir.mkdir(parents=True)
+    rng = np.random.default_rng(seed)
+    for i in range(n_images):
+        Image.fromarray(rng.integers(0, 256, size=(S, S, 3), dtype=np.uint8)).save(img_dir / f"IDRiD_{55 + i}.jpg", quality=95)
+        gt = (np.kron(rng.random((S // 8, S // 8)) < 0.25, np.ones((8, 8))) * 255).astype(np.uint8)
+        if gts is not None:
+            gt = (np.asarray(gts[i]) > 0).astype(np.uint8) * 255
+        Image.fromarray(gt, "L").save(mask_dir / f"IDRiD_{55 + i}_EX.tif")
+    logdirs = []
+    for i, ((name, cfg), sd) in enumerate(zip(ENSEMBLE_SPECS, ensemble_state_dicts())):
+        logdir = root / "models" / "IDRiD" / "EX" / f"run{i}"
+        (logdir / "checkpoints").mkdir(parents=True)
+        torch.save({"model_state_dict": sd}, logdir / "checkpoints" / "best.pth")
+        with open(logdir / "config.json", "w") as j:
+            json.dump({"model_name": name, "model_params": cfg}, j)
+        logdirs.append(logdir)
+    config = {"lesion_type": "EX", "dataset_name": "IDRiD", "scale_size": S, "out_dir": str(root / "outputs")}
+    return config, logdirs
+
+
+def run_reference_ensemble(root, gts=None):
+    """Runs the reference's own ensemble.predict (oracle/ref_loader.load_ensemble) on make_ensemble_case(root) with
+    the working directory at ``root`` (its dataset paths are relative).  -> dict of arrays, file-name order."""
+    import os
+    import numpy as np
+    from pathlib import Path
+    from PIL import Image
+    from oracle import ref_loader
+    config, logdirs = make_ensemble_case(root, gts=gts)
+    ens, cap = ref_loader.load_ensemble()
+    # in-process loading: ensemble.py:80 asks for two worker processes, and fork() from a multi-threaded test process
+    # can deadlock; the loader only feeds images (still shuffled), the arithmetic under test is untouched
+    real_loader = torch.utils.data.DataLoader
+    ens.DataLoader = lambda ds, **kw: real_loader(ds, **{**kw, "num_workers": 0, "pin_memory": False})
+    cwd = os.getcwd()
+    os.chdir(root)
+    try:
+        # the file names come back from the reference's save loop (shuffled loader order, ensemble.py:80)
+        ens.predict(config, [Path(os.path.relpath(d, root)) for d in logdirs], "ensemble_1")
+    finally:
+        os.chdir(cwd)
+    names = list(cap["masks"])                       # save order == prediction order (ensemble.py:112)
+    order = sorted(range(len(names)), key=lambda i: names[i])
+    img_dir = Path(root) / ENSEMBLE_IMG_DIR
+    return {"names": np.array([names[i] for i in order]),
+            "images": np.stack([np.asarray(Image.open(img_dir / names[i]).convert("RGB")) for i in order]),
+            "gts": np.stack([np.asarray(cap["gts"][i]).reshape(ENSEMBLE_S, ENSEMBLE_S) for i in order]).astype(np.uint8),
+            "preds": np.stack([cap["preds"][i] for i in order]).astype(np.float32),
+            "masks": np.stack([cap["masks"][names[i]] for i in order]).astype(np.uint8),
+            "auc": np.float64(cap["auc"]), "thresholds": np.array(cap["thresholds"], dtype=np.float64)}

@@ -226,3 +226,28 @@ def test_gaussian_tile_blend_driver_matches_oracle_restatement(monkeypatch):
                                     blend="gaussian").cpu().numpy()
     assert np.abs(got - want).max() < 1e-4
     assert np.abs(want - plain).max() > 1e-3                 # the mode does something
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 1e-3)])
+def test_ensemble_predict_reproduces_the_reference_ensemble_script(tmp_path, monkeypatch, precision, tol):
+    """tests/golden/ensemble.npz holds what the reference's own ensemble.py (run unmodified, make_golden.py) produced
+    on helpers.make_ensemble_case: the product's ensemble.predict, started in the same folder layout (the dataset
+    paths ensemble.py:65-66 hard-codes, relative to the working directory), must return its AUC-PR and write its
+    masks."""
+    from PIL import Image
+    from eyediseasesegmentation_b200 import ensemble as eds_ensemble
+    g = np.load(os.path.join(GOLDEN, "ensemble.npz"))
+    monkeypatch.setenv("EDS_PRECISION", precision)
+    config, logdirs = helpers.make_ensemble_case(tmp_path, gts=g["gts"])
+    monkeypatch.chdir(tmp_path)
+    got_auc = eds_ensemble.predict(config, [os.path.relpath(d, tmp_path) for d in logdirs], "ensemble_1")
+    assert abs(got_auc - float(g["auc"])) < tol                 # BASELINE: AUC-PR within 1e-3 (bf16)
+    written = tmp_path / "outputs" / "IDRiD" / "tta" / "EX" / "ensemble_1"
+    assert sorted(p.name for p in written.iterdir()) == [str(n) for n in g["names"]]
+    t1 = float(g["thresholds"][0])
+    for name, want, pred in zip(g["names"], g["masks"], g["preds"]):
+        got = np.asarray(Image.open(written / str(name)).convert("L")) > 127
+        undecided = np.abs(pred - t1) < (1e-3 if precision == "fp32" else 2e-2)
+        assert got.shape == want.shape
+        # pixels a rounding difference cannot flip; the masks travel through the reference's JPEG writer
+        assert np.mean(got[~undecided] != want.astype(bool)[~undecided]) < 2e-3, name

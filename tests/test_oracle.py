@@ -249,3 +249,42 @@ def test_pad_img_matches_reference_function(tmp_path):
         assert sorted(want) == sorted(got)
         for k in want:
             assert np.array_equal(want[k], got[k]), (k, is_mask)
+
+
+# ------------------------------------------------------------------ ensemble.py
+def _golden_ensemble():
+    return np.load(os.path.join(GOLDEN, "ensemble.npz"))
+
+
+def test_ensemble_oracle_matches_the_reference_ensemble_script():
+    """tests/golden/ensemble.npz was written by the reference's OWN ensemble.py (get_best_model + predict, run
+    unmodified by make_golden.py through ref_loader.load_ensemble).  oracle.pipeline.ensemble_probability + the
+    oracle scoring must reproduce its per-image probability maps, AUC-PR, threshold and masks."""
+    g = _golden_ensemble()
+    nets_list = helpers.ensemble_oracle_nets(helpers.ensemble_state_dicts())
+    mean, std = pipeline.DATASET_STATS["IDRiD"]
+    items = []
+    for img, gt, want, name in zip(g["images"], g["gts"], g["preds"], g["names"]):
+        x = torch.from_numpy(pipeline.preprocess(img, mean, std).transpose(2, 0, 1)).float()[None]
+        pred = pipeline.ensemble_probability(nets_list, x)
+        assert pred.dtype == np.float32 and pred.shape == want.shape
+        assert np.abs(pred - want).max() < 2e-6, name          # exact here; a few ulp for another host CPU
+        items.append((pred, gt, str(name)))
+    assert abs(scoring.get_auc(items) - float(g["auc"])) < 1e-6
+    t1 = scoring.pr_curve(items)["thresholds"][0]
+    assert t1 == float(g["thresholds"][0])
+    for (pred, _, name), want_mask in zip(items, g["masks"]):
+        decided = np.abs(pred - t1) > 1e-5                      # pixels a last-ulp difference cannot flip
+        assert np.array_equal((pred > t1)[decided], want_mask.astype(bool)[decided]), name
+
+
+@pytest.mark.skipif(not HAS_REF, reason="needs /root/reference (build container)")
+def test_reference_ensemble_script_reproduces_its_fixture(tmp_path):
+    """The committed fixture is what the reference's ensemble.py produces today (regeneration check)."""
+    g = _golden_ensemble()
+    out = helpers.run_reference_ensemble(tmp_path, gts=g["gts"])
+    assert list(out["names"]) == list(g["names"])
+    assert np.array_equal(out["images"], g["images"]) and np.array_equal(out["gts"], g["gts"])
+    assert np.abs(out["preds"] - g["preds"]).max() < 2e-6
+    assert np.array_equal(out["masks"], g["masks"])
+    assert abs(float(out["auc"]) - float(g["auc"])) < 1e-9 and list(out["thresholds"]) == list(g["thresholds"])
