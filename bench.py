@@ -615,29 +615,30 @@ def from_files(dev, n_images=4):
 _CPU_STATE = {}
 
 
-def _cpu_setup(threads):
+def _cpu_setup(threads, size=S):
     import torch
     from oracle import nets
     import helpers
     if "sd" not in _CPU_STATE:
         torch.set_num_threads(threads)
-        model = helpers.build_product_model("unetplusplusstar", star_cfg(32), seed=1999)
+        # the proposed network ties its attention length to the input size: base_dim = size / 32 (32 <-> 1024^2)
+        model = helpers.build_product_model("unetplusplusstar", star_cfg(size // 32), seed=1999)
         _CPU_STATE["sd"] = model.state_dict()
-        _CPU_STATE["x"] = torch.randn(1, 3, S, S, generator=torch.Generator().manual_seed(0))
+        _CPU_STATE["x"] = torch.randn(1, 3, size, size, generator=torch.Generator().manual_seed(0))
     return _CPU_STATE["sd"], _CPU_STATE["x"]
 
 
-def cpu_tile_sample(threads, views=VIEWS):
+def cpu_tile_sample(threads, views=VIEWS, size=S):
     """One REAL unit of the workload on the host cores with the oracle (the reference's PyTorch path restated,
     oracle/nets.py + sklearn): ONE 1024^2 tile through all `views` D4 views of the proposed network with the TTA mean
     and the sigmoid (tta.py:209-210) -> seconds."""
     import torch
     from oracle import nets
-    sd, x = _cpu_setup(threads)
+    sd, x = _cpu_setup(threads, size)
     kind = "d4" if views == 8 else "none"
     t0 = time.perf_counter()
     with torch.no_grad():
-        torch.sigmoid(nets.tta_mean_logits(lambda t: nets.unetplusplusstar_forward(sd, t, 32), x, kind))
+        torch.sigmoid(nets.tta_mean_logits(lambda t: nets.unetplusplusstar_forward(sd, t, size // 32), x, kind))
     return time.perf_counter() - t0
 
 
@@ -699,11 +700,11 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     for _ in range(args.warmup):
-        cpu_tile_sample(threads, views=1)
+        cpu_tile_sample(threads, views=1, size=args.ref_size)
     tiles, scores = [], []
     t_start = time.perf_counter()
     for _ in range(max(1, args.steps)):
-        tiles.append(cpu_tile_sample(threads, views=args.ref_views) * (VIEWS / args.ref_views))
+        tiles.append(cpu_tile_sample(threads, views=args.ref_views, size=args.ref_size) * (VIEWS / args.ref_views))
         scores.append(cpu_score_sample())
         if time.perf_counter() - t_start > 150:
             break
@@ -734,6 +735,9 @@ def main():
     ap.add_argument("--group", type=int, default=0, help="images per unit-dealing group (0 = the whole set)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the cfg-1 / cfg-2 / cfg-5 side measurements")
+    ap.add_argument("--ref-size", type=int, default=S,
+                    help="--impl reference: tile edge of the sampled forward (1024 = the workload; smaller only for "
+                         "quick contract tests, the printed value is then not a measurement)")
     ap.add_argument("--ref-views", type=int, default=VIEWS, choices=[1, VIEWS],
                     help="--impl reference: TTA views per sampled tile (8 = the workload; 1 only for quick contract tests)")
     args = ap.parse_args()

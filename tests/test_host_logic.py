@@ -244,7 +244,8 @@ def test_bench_reference_arm_prints_one_contract_line():
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0", "--ref-views", "1"], capture_output=True, text=True, timeout=600)
+                          "--warmup", "0", "--ref-views", "1", "--ref-size", "256"], capture_output=True, text=True,
+                         timeout=600)
     assert res.returncode == 0, res.stderr[-2000:]
     lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, res.stdout
