@@ -124,6 +124,26 @@ def test_oracle_nets_bit_exact_against_reference_modules():
 
 
 @pytest.mark.skipif(not HAS_REF, reason="/root/reference is only present in the build container")
+def test_survey_known_answers_of_the_reference_network():
+    """SURVEY.md 8c known answers: the reference's own constructor under torch.manual_seed(1999) (pipeline.py:36),
+    proposed network, base_dim 8, x = randn(1,3,256,256) from seed 7 -> logit statistics, two probe pixels, and
+    the statistics of the D4-TTA mean (the oracle's restatement of ttach on the reference's weights)."""
+    ref = ref_loader.load()
+    torch.manual_seed(1999)
+    m = ref.unetplusplusstar.UnetPlusPlusStar(**helpers.star_cfg(8)).eval()
+    x = helpers.golden_input(1, 256, seed=7)
+    sd = m.state_dict()
+    with torch.no_grad():
+        y = nets.unetplusplusstar_forward(sd, x, 8)
+        assert torch.equal(y, m(x))
+        t = nets.tta_mean_logits(lambda z: nets.unetplusplusstar_forward(sd, z, 8), x, "d4")
+    assert y.mean().item() == pytest.approx(-0.551582, abs=2e-6) and y.std().item() == pytest.approx(0.139031, abs=2e-6)
+    assert y[0, 0, 0, 0].item() == pytest.approx(0.006472, abs=2e-6)
+    assert y[0, 0, 128, 128].item() == pytest.approx(-0.619326, abs=2e-6)
+    assert t.mean().item() == pytest.approx(-0.553268, abs=2e-6) and t.std().item() == pytest.approx(0.089578, abs=2e-6)
+
+
+@pytest.mark.skipif(not HAS_REF, reason="/root/reference is only present in the build container")
 def test_oracle_scoring_against_reference_aucpr(tmp_path):
     ref = ref_loader.load()
     cfg = {"out_dir": str(tmp_path), "dataset_name": "IDRiD", "lesion_type": "EX"}
