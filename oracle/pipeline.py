@@ -10,6 +10,10 @@
                              written by the reference's own ensemble.py (ref_loader.load_ensemble runs it
                              with the absent third-party packages restated): tests/test_oracle.py
 
+Pinned: tests/golden/tta_patches.npz and tta_whole.npz were written by the reference's own tta.py (run unmodified
+through oracle/ref_loader.load_tta by tests/golden/make_golden.py); tests/test_oracle.py holds
+tiled_probability_map and whole_image_probability to them (2e-6, exact in the build container).
+
 ``net`` is any callable ``[B,3,S,S] float32 tensor -> logits [B,1,S,S]`` (the oracle nets, or
 the reference modules in the build container).  cv2 is the same library the reference calls.
 """

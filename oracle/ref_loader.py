@@ -6,9 +6,12 @@ with them timm / smp / pytorch_toolbelt / catalyst, none of which are installed)
 individual files are loaded inside synthetic packages after registering the third-party
 restatements of ``oracle/shims.py`` in ``sys.modules``.
 
+``load_tta()`` / ``load_ensemble()`` go one level up and execute the reference's DRIVER files
+(src/main/tta.py, ensemble.py) unmodified, with its own dataset / transform / tiling / scoring code.
+
 Used by tests/golden/make_golden.py (to generate the committed fixtures) and by
-tests/test_oracle.py (to pin ``oracle/nets.py`` and ``oracle/scoring.py`` against the
-reference's own code).  Never imported by the product package.
+tests/test_oracle.py (to pin ``oracle/nets.py``, ``oracle/scoring.py`` and ``oracle/pipeline.py``
+against the reference's own code).  Never imported by the product package.
 """
 from __future__ import annotations
 
@@ -170,29 +173,15 @@ def build_reference_module(ref, name, cfg):
     raise KeyError(name)
 
 
-def load_ensemble():
-    """The reference's top-level ``ensemble.py`` executed UNMODIFIED, together with the reference's own
-    ``src/data/lesion_dataset.py`` (TestSegmentation), ``src/data/data_transform.py`` (NormalTransform),
-    ``base_utils.get_datapath`` / ``save_output`` and ``aucpr.py``.
-
-    Third-party packages that are not installed are restated (SURVEY.md appendix B): ``ttach`` by
-    ``oracle.nets.tta_mean_logits``, the five ``albumentations`` classes the path touches (Compose, Lambda,
-    LongestMaxSize, PadIfNeeded, ToTensorV2) with cv2, ``catalyst.dl.utils.get_device`` = cpu.
-
-    ``ensemble.py`` is stale against the rest of the reference in four places (listed in the product's
-    ``ensemble.py`` docstring); they are bridged here by ADAPTERS around the reference's own functions, not by
-    editing it: ``TestSegmentation(images, masks, transform=)`` -> ``TestSegmentation(images, False, masks, ...)``;
-    ``get_preprocessing_fn(dataset_name=)`` -> ``grayscale=False``; ``get_auc(gts, preds, config)`` /
-    ``plot_aucpr_curve(gts, preds, outdir, config)`` -> the ``(pred, gt, name)`` generator form of aucpr.py:17,45
-    (first two thresholds returned).  Returns ``(module, captured)``: ``captured`` collects what the adapters saw
-    (``preds``, ``gts``, ``auc``, ``thresholds``, ``masks`` by file name)."""
+def _install_inference_stubs():
+    """Third-party packages the reference's inference drivers import and this image lacks, restated:
+    ttach 0.0.3 (views + mean merge = oracle.nets.tta_mean_logits), the albumentations 1.0 classes / functions the
+    drivers touch (cv2 underneath, as in albumentations), rasterio's windowed read (PIL decode + slice),
+    catalyst.dl.utils.get_device (= cpu)."""
     import cv2
     import numpy as np
     import torch
     from . import nets
-
-    ref = load()
-    captured = {"masks": {}}
 
     class SegmentationTTAWrapper(torch.nn.Module):
         def __init__(self, model, transforms, merge_mode="mean"):
@@ -204,7 +193,8 @@ def load_ensemble():
             return nets.tta_mean_logits(self.model, x, self.kind)
 
     _module("ttach", SegmentationTTAWrapper=SegmentationTTAWrapper,
-            aliases=types.SimpleNamespace(d4_transform=lambda: "d4"))
+            aliases=types.SimpleNamespace(d4_transform=lambda: "d4", flip_transform=lambda: "flip",
+                                          hflip_transform=lambda: "hflip"))
     _module("pytorch_toolbelt.inference")
     _module("pytorch_toolbelt.inference.tiles", ImageSlicer=object, TileMerger=object)
     _module("pytorch_toolbelt.utils", fs=None, image_to_tensor=None)
@@ -215,7 +205,7 @@ def load_ensemble():
     dl_utils = _module("catalyst.dl.utils", get_device=lambda: torch.device("cpu"))
     _module("catalyst.dl", utils=dl_utils)
 
-    # ---- albumentations 1.0 (3P), the classes this path touches
+    # ---- albumentations 1.0 (3P), the classes / functions this path touches
     def longest_max_size(img, max_size, interpolation):
         h, w = img.shape[:2]
         scale = max_size / float(max(h, w))
@@ -223,34 +213,51 @@ def load_ensemble():
             return img
         return cv2.resize(img, (int(round(w * scale)), int(round(h * scale))), interpolation=interpolation)
 
-    class LongestMaxSize:
+    def resize(img, height, width, interpolation=cv2.INTER_LINEAR):
+        if img.shape[:2] == (height, width):
+            return img
+        return cv2.resize(img, (width, height), interpolation=interpolation)
+
+    def center_crop(img, crop_height, crop_width):
+        h, w = img.shape[:2]
+        if h < crop_height or w < crop_width:
+            raise ValueError("Requested crop size is larger than the image size")
+        y1, x1 = (h - crop_height) // 2, (w - crop_width) // 2
+        return img[y1:y1 + crop_height, x1:x1 + crop_width]
+
+    class _Dual:
+        def __call__(self, **d):
+            d["image"] = self.apply(d["image"], cv2.INTER_LINEAR)
+            if "mask" in d:
+                d["mask"] = self.apply(d["mask"], cv2.INTER_NEAREST)
+            return d
+
+    class LongestMaxSize(_Dual):
         def __init__(self, max_size=1024, **_):
             self.max_size = max_size
 
-        def __call__(self, **d):
-            d["image"] = longest_max_size(d["image"], self.max_size, cv2.INTER_LINEAR)
-            if "mask" in d:
-                d["mask"] = longest_max_size(d["mask"], self.max_size, cv2.INTER_NEAREST)
-            return d
+        def apply(self, a, interpolation):
+            return longest_max_size(a, self.max_size, interpolation)
 
-    class PadIfNeeded:
+    class Resize(_Dual):
+        def __init__(self, height, width, **_):
+            self.h, self.w = height, width
+
+        def apply(self, a, interpolation):
+            return resize(a, self.h, self.w, interpolation)
+
+    class PadIfNeeded(_Dual):
         def __init__(self, min_height, min_width, border_mode=cv2.BORDER_CONSTANT, value=0, **_):
             assert border_mode == cv2.BORDER_CONSTANT and value == 0
             self.h, self.w = min_height, min_width
 
-        def _pad(self, a):
+        def apply(self, a, interpolation):
             h, w = a.shape[:2]
             top = int((self.h - h) / 2.0) if h < self.h else 0
             left = int((self.w - w) / 2.0) if w < self.w else 0
             out = np.zeros((max(self.h, h), max(self.w, w)) + a.shape[2:], dtype=a.dtype)
             out[top:top + h, left:left + w] = a
             return out
-
-        def __call__(self, **d):
-            d["image"] = self._pad(d["image"])
-            if "mask" in d:
-                d["mask"] = self._pad(d["mask"])
-            return d
 
     class Lambda:
         def __init__(self, image=None, **_):
@@ -277,20 +284,78 @@ def load_ensemble():
                 d = t(**d)
             return d
 
-    alb = _module("albumentations", Compose=Compose, Lambda=Lambda, LongestMaxSize=LongestMaxSize, PadIfNeeded=PadIfNeeded)
+    alb = _module("albumentations", Compose=Compose, Lambda=Lambda, LongestMaxSize=LongestMaxSize,
+                  PadIfNeeded=PadIfNeeded, Resize=Resize)
     _module("albumentations.pytorch", ToTensorV2=ToTensorV2)
     _module("albumentations.pytorch.transforms", ToTensorV2=ToTensorV2)
     alb.pytorch = sys.modules["albumentations.pytorch"]
     _module("albumentations.augmentations")
+    _module("albumentations.augmentations.crops")
+    _module("albumentations.augmentations.crops.functional", center_crop=center_crop)
     _module("albumentations.augmentations.geometric")
-    _module("albumentations.augmentations.geometric.functional", longest_max_size=longest_max_size)
+    _module("albumentations.augmentations.geometric.functional", longest_max_size=longest_max_size, resize=resize)
     _module("albumentations.augmentations.geometric.resize", RandomScale=object)
 
-    # ---- the reference's own data classes
+    # ---- rasterio 1.2 (3P): tta.py:196,201 open a JPEG and read RGB windows
+    class Window:
+        def __init__(self, rows, cols):
+            self.rows, self.cols = rows, cols
+
+        @classmethod
+        def from_slices(cls, rows, cols):
+            return cls(tuple(int(v) for v in rows), tuple(int(v) for v in cols))
+
+    class _Dataset:
+        def __init__(self, path):
+            from PIL import Image
+            self._a = np.asarray(Image.open(path).convert("RGB"))
+            self.shape = self._a.shape[:2]
+
+        def read(self, indexes, window=None):
+            a = self._a if window is None else self._a[window.rows[0]:window.rows[1], window.cols[0]:window.cols[1]]
+            return np.stack([a[..., i - 1] for i in indexes])
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *exc):
+            return False
+
+    _module("rasterio", open=lambda path, *a, **k: _Dataset(path), Affine=lambda *a: a)
+    _module("rasterio.windows", Window=Window)
+
+
+def _reference_data_classes():
+    """The reference's own src/data/lesion_dataset.py and data_transform.py, loaded by path."""
     data_dir = os.path.join(REFERENCE_ROOT, "src", "data")
     _module("refdatapkg")
-    lesion_dataset = _load("refdatapkg", "lesion_dataset", os.path.join(data_dir, "lesion_dataset.py"))
-    data_transform = _load("refdatapkg", "data_transform", os.path.join(data_dir, "data_transform.py"))
+    return (_load("refdatapkg", "lesion_dataset", os.path.join(data_dir, "lesion_dataset.py")),
+            _load("refdatapkg", "data_transform", os.path.join(data_dir, "data_transform.py")))
+
+
+def load_ensemble():
+    """The reference's top-level ``ensemble.py`` executed UNMODIFIED, together with the reference's own
+    ``src/data/lesion_dataset.py`` (TestSegmentation), ``src/data/data_transform.py`` (NormalTransform),
+    ``base_utils.get_datapath`` / ``save_output`` and ``aucpr.py``.
+
+    Third-party packages that are not installed are restated (SURVEY.md appendix B): ``ttach`` by
+    ``oracle.nets.tta_mean_logits``, the five ``albumentations`` classes the path touches (Compose, Lambda,
+    LongestMaxSize, PadIfNeeded, ToTensorV2) with cv2, ``catalyst.dl.utils.get_device`` = cpu.
+
+    ``ensemble.py`` is stale against the rest of the reference in four places (listed in the product's
+    ``ensemble.py`` docstring); they are bridged here by ADAPTERS around the reference's own functions, not by
+    editing it: ``TestSegmentation(images, masks, transform=)`` -> ``TestSegmentation(images, False, masks, ...)``;
+    ``get_preprocessing_fn(dataset_name=)`` -> ``grayscale=False``; ``get_auc(gts, preds, config)`` /
+    ``plot_aucpr_curve(gts, preds, outdir, config)`` -> the ``(pred, gt, name)`` generator form of aucpr.py:17,45
+    (first two thresholds returned).  Returns ``(module, captured)``: ``captured`` collects what the adapters saw
+    (``preds``, ``gts``, ``auc``, ``thresholds``, ``masks`` by file name)."""
+    import numpy as np
+
+    ref = load()
+    _install_inference_stubs()
+    captured = {"masks": {}}
+
+    lesion_dataset, data_transform = _reference_data_classes()
 
     class TestSegmentation(lesion_dataset.TestSegmentation):        # adapter: the call of ensemble.py:78
         def __init__(self, images, masks=None, transform=None):
@@ -326,6 +391,83 @@ def load_ensemble():
     _module("refroot")
     sys.modules.pop("refroot.ensemble", None)
     mod = _load("refroot", "ensemble", os.path.join(REFERENCE_ROOT, "ensemble.py"))
+    return mod, captured
+
+
+def load_tta():
+    """The reference's lesion inference drivers, ``src/main/tta.py`` (``test_tta``, ``tta_patches``), executed
+    UNMODIFIED together with the reference's own ``TestSegmentation`` / ``NormalTransform`` / ``base_utils``
+    (``make_grid``, ``multigen``, ``get_datapath``, ``save_output``) / ``aucpr.py`` and
+    ``archs.get_preprocessing_fn``; ``archs.get_model`` builds the reference's own modules
+    (``build_reference_module``).  Third-party packages: see ``_install_inference_stubs``.
+
+    Two things stand between that file and a CPU-only container and are handled OUTSIDE it: its loader asks for
+    worker processes and pinned memory, and ``test_tta`` sends the batch ``.to('cuda')`` (tta.py:111); the module's
+    ``DataLoader`` name is therefore bound to an in-process loader whose image batches ignore ``.to``.
+
+    Returns ``(module, captured)``; ``captured[call]`` = the ``(pred, gt, name)`` items each scoring call received,
+    ``captured["auc"]``, ``captured["thresholds"]``, ``captured["masks"]`` (file name -> array handed to
+    ``save_output``)."""
+    import numpy as np
+    import torch
+
+    ref = load()
+    _install_inference_stubs()
+    lesion_dataset, data_transform = _reference_data_classes()
+    captured = {"masks": {}}
+    bu = ref.base_utils
+
+    def get_auc(generator, config):
+        items = [(np.array(p), np.array(g), str(n)) for p, g, n in generator]
+        captured["items"] = items
+        captured["auc"] = float(ref.aucpr.get_auc(items, config))
+        return captured["auc"]
+
+    def plot_aucpr_curve(generator, exp_name, config):
+        th = ref.aucpr.plot_aucpr_curve(list(generator), exp_name, config)
+        captured["thresholds"] = [float(t) for t in th]
+        return th
+
+    def save_output(mask, out_path):
+        captured["masks"][os.path.basename(str(out_path))] = np.array(mask)
+        return bu.save_output(mask, out_path)
+
+    archs = _module("refsrc.main.archs",
+                    get_model=lambda model_name, params, training=False: build_reference_module(ref, model_name, params),
+                    get_preprocessing_fn=get_preprocessing_fn)
+    sys.modules["refsrc.main"].archs = archs
+    # observed (not replaced) scoring / writer: the wrappers call the reference's functions
+    _module("refsrc.main.aucpr", get_auc=get_auc, plot_aucpr_curve=plot_aucpr_curve)
+    _module("refsrc.main.util", lesion_dict=bu.lesion_dict, get_datapath=bu.get_datapath, make_grid=bu.make_grid,
+            multigen=bu.multigen, save_output=save_output)
+    _module("refsrc.data", NormalTransform=data_transform.NormalTransform,
+            TestSegmentation=lesion_dataset.TestSegmentation)
+    sys.modules.pop("refsrc.main.tta", None)
+    mod = _load("refsrc.main", "tta", os.path.join(REFERENCE_ROOT, "src", "main", "tta.py"))
+
+    class _HostTensor(torch.Tensor):
+        def to(self, *args, **kwargs):           # tta.py:111 `.to('cuda')` on a CPU-only box
+            return self.as_subclass(torch.Tensor)
+
+    real_loader = torch.utils.data.DataLoader
+
+    def loader(ds, **kw):
+        kw.update(num_workers=0, pin_memory=False)
+        for batch in real_loader(ds, **kw):
+            batch["image"] = batch["image"].as_subclass(_HostTensor)
+            yield batch
+
+    class _Loader:
+        def __init__(self, ds, **kw):
+            self.ds, self.kw = ds, kw
+
+        def __iter__(self):
+            return loader(self.ds, **self.kw)
+
+        def __len__(self):
+            return -(-len(self.ds) // self.kw.get("batch_size", 1))
+
+    mod.DataLoader = _Loader
     return mod, captured
 
 

@@ -64,7 +64,40 @@ def ensemble_fixture_only():
           "thresholds", out["thresholds"].tolist())
 
 
+def tta_fixtures_only():
+    """The reference's own src/main/tta.py -- tta_patches (sliding window, D4) and test_tta (whole image, hflip) -- run
+    unmodified (oracle/ref_loader.load_tta) from JPEG / TIFF files to scores and masks.  Two passes: the first, on
+    random labels, only learns the probability maps; the committed case uses labels derived from them (top 30 % of
+    each map with 5 % of the 8 x 8 blocks flipped; one image without positives for aucpr.py:22) so that the PR
+    curve, the chosen threshold and the written masks are not degenerate."""
+    import tempfile
+    for case in ("patches", "whole"):
+        with tempfile.TemporaryDirectory() as tmp:
+            first = helpers.run_reference_tta(tmp, case)
+        n = len(first["names"])
+        rng = np.random.default_rng(17)
+        gts = []
+        for i in range(n):
+            pred = first[f"pred{i}"]
+            top = np.zeros(pred.size, dtype=bool)
+            top[np.argsort(pred.ravel(), kind="stable")[-int(0.3 * pred.size):]] = True
+            h, w = pred.shape
+            flips = np.kron(rng.random((h // 8 + 1, w // 8 + 1)) < 0.05, np.ones((8, 8)))[:h, :w].astype(bool)
+            gts.append((top.reshape(pred.shape) ^ flips).astype(np.uint8))
+        if case == "patches":
+            gts[-1][:] = 0
+        with tempfile.TemporaryDirectory() as tmp:
+            out = helpers.run_reference_tta(tmp, case, jpegs=[first[f"jpeg{i}"] for i in range(n)], gts=gts)
+        for i in range(n):
+            assert np.array_equal(out[f"pred{i}"], first[f"pred{i}"]) and np.array_equal(out[f"label{i}"], gts[i])
+        np.savez_compressed(os.path.join(HERE, f"tta_{case}.npz"), **out)
+        print(f"tta_{case}.npz written: auc", float(out["auc"]), "thresholds", out["thresholds"].tolist(),
+              "mask means", [float(out[f"mask{i}"].mean()) for i in range(n)])
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "tta":
+        return tta_fixtures_only()
     if len(sys.argv) > 1 and sys.argv[1] == "pad":     # only the fixtures added in round 2
         return pad_fixture_only()
     if len(sys.argv) > 1 and sys.argv[1] == "ensemble":
@@ -128,6 +161,8 @@ def main():
     pad_fixture_only()
     # 7. the reference's ensemble.py end to end
     ensemble_fixture_only()
+    # 8. the reference's tta.py drivers end to end
+    tta_fixtures_only()
     print("golden fixtures written to", HERE)
 
 

@@ -282,3 +282,96 @@ def run_reference_ensemble(root, gts=None):
             "preds": np.stack([cap["preds"][i] for i in order]).astype(np.float32),
             "masks": np.stack([cap["masks"][names[i]] for i in order]).astype(np.uint8),
             "auc": np.float64(cap["auc"]), "thresholds": np.array(cap["thresholds"], dtype=np.float64)}
+
+
+# ------------------------------------------------------------------ tta.py drivers (reference tta_patches / test_tta)
+TTA_CASES = {
+    # name: registry name, params, scale_size, TTA alias, original image shapes, data_type
+    "patches": ("unetplusplus_deepsup", dict(encoder_name="resnet34", encoder_weights=None, classes=1), 64, "d4",
+                [(150, 200), (140, 131), (128, 170)]),
+    "whole": ("Unet", dict(encoder_name="resnet34", encoder_weights=None, classes=1), 1024, "hflip",
+              [(89, 134), (89, 134)]),
+}
+
+
+def tta_case_state_dict(case):
+    name, cfg = TTA_CASES[case][:2]
+    sd = {k: v.clone() for k, v in build_product_model(name, cfg, seed=2001).state_dict().items()}
+    # fixed head calibration (measured once on the case's first image): logits ~ mean 0, std 2, so that the
+    # probabilities of the random-init network spread over the threshold list
+    scale, bias = {"patches": (5.0, -5.9), "whole": (1.0, 3.6)}[case]
+    sd["segmentation_head.0.weight"] *= scale
+    sd["segmentation_head.0.bias"] += bias
+    return sd
+
+
+def tta_case_oracle_net(case, sd):
+    if TTA_CASES[case][0] == "Unet":
+        return lambda t: nets.unet_forward(sd, t)
+    return lambda t: nets.unetplusplus_forward(sd, t)
+
+
+def make_tta_case(root, case, jpegs=None, gts=None, seed=31):
+    """Under ``root``: ``images/IDRiD_NN.jpg``, ``masks/3. Hard Exudates/IDRiD_NN_EX.tif`` and the log directory of one
+    model.  ``jpegs`` (list of uint8 byte arrays) / ``gts`` ([H,W] {0,1} arrays): the committed fixture's files, written
+    back verbatim (a re-encoded JPEG would not be the same image); seeded noise discs / random blocks without them.
+    -> (logdir, config, args)"""
+    import io
+    import json
+    import numpy as np
+    from pathlib import Path
+    from PIL import Image
+    name, cfg, S, alias, shapes = TTA_CASES[case]
+    root = Path(root)
+    img_dir, mask_root = root / "images", root / "masks"
+    mask_dir = mask_root / "3. Hard Exudates"
+    img_dir.mkdir(parents=True)
+    mask_dir.mkdir(parents=True)
+    rng = np.random.default_rng(seed)
+    for i, (h, w) in enumerate(shapes):
+        if jpegs is not None:
+            (img_dir / f"IDRiD_{i:02d}.jpg").write_bytes(bytes(np.asarray(jpegs[i], dtype=np.uint8)))
+        else:
+            img = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+            yy, xx = np.mgrid[:h, :w]
+            img[(yy - h / 2) ** 2 + (xx - w / 2) ** 2 > (0.55 * min(h, w)) ** 2] = 0
+            buf = io.BytesIO()
+            Image.fromarray(img).save(buf, format="JPEG", quality=95)
+            (img_dir / f"IDRiD_{i:02d}.jpg").write_bytes(buf.getvalue())
+        gt = (np.kron(rng.random((h // 8 + 1, w // 8 + 1)) < 0.2, np.ones((8, 8)))[:h, :w] * 255).astype(np.uint8)
+        if gts is not None:
+            gt = (np.asarray(gts[i]) > 0).astype(np.uint8) * 255
+        Image.fromarray(gt, "L").save(mask_dir / f"IDRiD_{i:02d}_EX.tif")
+    logdir = root / "models" / "IDRiD" / "EX" / f"{case}_exp"
+    (logdir / "checkpoints").mkdir(parents=True)
+    torch.save({"model_state_dict": tta_case_state_dict(case)}, logdir / "checkpoints" / "best.pth")
+    config = {"dataset_name": "IDRiD", "lesion_type": "EX", "gray": False, "scale_size": S, "val_batch_size": 2,
+              "model_name": name, "model_params": dict(cfg), "test_img_path": img_dir, "test_mask_path": mask_root,
+              "out_dir": str(root / "outputs"), "data_type": "tile" if case == "patches" else "all"}
+    args = {"best": "true", "tta": alias, "createprob": "false", "optim_thres": 0}
+    return logdir, config, args
+
+
+def run_reference_tta(root, case, jpegs=None, gts=None):
+    """Runs the reference's own tta.tta_patches / tta.test_tta (oracle/ref_loader.load_tta) on make_tta_case.
+    -> dict of arrays (per image, in file-name order: JPEG bytes, label map as stored, probability map and label map
+    as scored, the mask handed to save_output) + auc + thresholds."""
+    import copy
+    import numpy as np
+    from pathlib import Path
+    from oracle import ref_loader
+    logdir, config, args = make_tta_case(root, case, jpegs=jpegs, gts=gts)
+    mod, cap = ref_loader.load_tta()
+    (mod.tta_patches if case == "patches" else mod.test_tta)(str(logdir), copy.deepcopy(config), dict(args))
+    key = (lambda n: n.replace("_EX.tif", ".jpg"))
+    items = sorted(cap["items"], key=lambda it: key(it[2]))
+    out = {"auc": np.float64(cap["auc"]), "thresholds": np.array(cap["thresholds"], dtype=np.float64),
+           "names": np.array([key(n) for _, _, n in items])}
+    for i, (pred, gt, n) in enumerate(items):
+        out[f"jpeg{i}"] = np.frombuffer((Path(config["test_img_path"]) / key(n)).read_bytes(), dtype=np.uint8)
+        out[f"label{i}"] = (np.asarray(__import__("PIL.Image", fromlist=["Image"]).open(
+            Path(config["test_mask_path"]) / "3. Hard Exudates" / key(n).replace(".jpg", "_EX.tif")).convert("L")) > 0).astype(np.uint8)
+        out[f"pred{i}"] = pred.astype(np.float32)
+        out[f"gt{i}"] = gt
+        out[f"mask{i}"] = np.asarray(cap["masks"][key(n)])
+    return out

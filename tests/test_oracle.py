@@ -308,3 +308,92 @@ def test_reference_ensemble_script_reproduces_its_fixture(tmp_path):
     assert np.abs(out["preds"] - g["preds"]).max() < 2e-6
     assert np.array_equal(out["masks"], g["masks"])
     assert abs(float(out["auc"]) - float(g["auc"])) < 1e-9 and list(out["thresholds"]) == list(g["thresholds"])
+
+
+# ------------------------------------------------------------------ tta.py drivers
+def _golden_tta(case):
+    g = np.load(os.path.join(GOLDEN, f"tta_{case}.npz"))
+    return g, len(g["names"])
+
+
+def _decode(jpeg_bytes):
+    import io
+    from PIL import Image
+    return np.asarray(Image.open(io.BytesIO(bytes(jpeg_bytes))).convert("RGB")).astype("uint8")
+
+
+def _check_scores_and_masks(g, items, mask_dtype):
+    assert abs(scoring.get_auc(items) - float(g["auc"])) < 1e-6
+    th = scoring.pr_curve(items)["thresholds"]
+    assert list(th) == list(g["thresholds"])
+    for i, (pred, _, name) in enumerate(items):
+        want = g[f"mask{i}"]
+        assert want.dtype == mask_dtype                         # tta.py:226 writes float32, tta.py:138 uint8
+        decided = np.abs(pred - th[2]) > 1e-5                   # pixels a last-ulp difference cannot flip
+        assert np.array_equal((pred > th[2])[decided], want.astype(bool)[decided]), name
+
+
+def test_tiled_pipeline_oracle_matches_the_reference_tta_patches():
+    """tests/golden/tta_patches.npz was written by the reference's OWN tta.tta_patches (tta.py:150-238, run
+    unmodified by make_golden.py through ref_loader.load_tta: windowed read, A.Resize, preprocessing, D4 TTA of the
+    reference's UNet++ module, sigmoid, cv2 x2 resize, overwrite paste, get_auc, plot_aucpr_curve, the third
+    threshold, the float32 masks).  oracle.pipeline.tiled_probability_map + oracle.scoring must reproduce its
+    probability maps, scores, thresholds and masks from the same JPEG bytes."""
+    g, n = _golden_tta("patches")
+    _, _, S, alias, shapes = helpers.TTA_CASES["patches"]
+    net = helpers.tta_case_oracle_net("patches", helpers.tta_case_state_dict("patches"))
+    mean, std = pipeline.DATASET_STATS["IDRiD"]
+    items = []
+    for i in range(n):
+        image = _decode(g[f"jpeg{i}"])
+        assert image.shape[:2] == shapes[i]
+        pred = pipeline.tiled_probability_map(image, net, S, mean, std, alias)
+        assert np.abs(pred - g[f"pred{i}"]).max() < 2e-6, i     # exact here; a few ulp for another host CPU
+        assert np.array_equal(g[f"gt{i}"], g[f"label{i}"])      # tta.py:192-194: labels scored as stored (> 0)
+        items.append((pred, g[f"gt{i}"], str(g["names"][i])))
+    assert items[-1][1].sum() == 0                              # the image aucpr.py:22 skips
+    _check_scores_and_masks(g, items, np.float32)
+
+
+def test_whole_image_oracle_matches_the_reference_test_tta():
+    """tests/golden/tta_whole.npz: the reference's OWN tta.test_tta (tta.py:56-148) on two 89 x 134 images through
+    its TestSegmentation / NormalTransform (LongestMaxSize(1024) + centred pad), smp.Unet(resnet34) under hflip TTA,
+    sigmoid, centre crop + cv2 resize of prediction AND mask back to the original size, scoring, uint8 masks."""
+    import cv2
+    g, n = _golden_tta("whole")
+    _, _, S, alias, shapes = helpers.TTA_CASES["whole"]
+    net = helpers.tta_case_oracle_net("whole", helpers.tta_case_state_dict("whole"))
+    mean, std = pipeline.DATASET_STATS["IDRiD"]
+    items = []
+    for i in range(n):
+        image = _decode(g[f"jpeg{i}"])
+        H0, W0 = image.shape[:2]
+        scale = S / max(H0, W0)
+        nh, nw = int(round(H0 * scale)), int(round(W0 * scale))
+        top, left = int((S - nh) / 2.0), int((S - nw) / 2.0)
+        padded = np.zeros((S, S, 3), dtype=np.uint8)
+        padded[top:top + nh, left:left + nw] = cv2.resize(image, (nw, nh), interpolation=cv2.INTER_LINEAR)
+        x = torch.from_numpy(pipeline.preprocess(padded, mean, std).transpose(2, 0, 1)).float()[None]
+        with torch.no_grad():
+            prob = torch.sigmoid(nets.tta_mean_logits(net, x, alias)[0, 0]).numpy()
+        pred = pipeline.whole_image_probability(prob, (nh, nw), (H0, W0))
+        assert np.abs(pred - g[f"pred{i}"]).max() < 2e-6, i
+        mp = np.zeros((S, S), dtype=np.uint8)                   # lesion_dataset.py:126-128 + the same transform
+        mp[top:top + nh, left:left + nw] = cv2.resize(g[f"label{i}"], (nw, nh), interpolation=cv2.INTER_NEAREST)
+        gt = pipeline.whole_image_probability(mp, (nh, nw), (H0, W0))
+        assert np.array_equal(gt, g[f"gt{i}"])
+        items.append((pred, gt, str(g["names"][i])))
+    _check_scores_and_masks(g, items, np.uint8)
+
+
+@pytest.mark.skipif(not HAS_REF, reason="needs /root/reference (build container)")
+def test_reference_tta_patches_reproduces_its_fixture(tmp_path):
+    """The committed sliding-window fixture is what the reference's tta.py produces today (regeneration check)."""
+    g, n = _golden_tta("patches")
+    out = helpers.run_reference_tta(tmp_path, "patches", jpegs=[g[f"jpeg{i}"] for i in range(n)],
+                                    gts=[g[f"label{i}"] for i in range(n)])
+    assert list(out["names"]) == list(g["names"]) and list(out["thresholds"]) == list(g["thresholds"])
+    assert abs(float(out["auc"]) - float(g["auc"])) < 1e-9
+    for i in range(n):
+        assert np.abs(out[f"pred{i}"] - g[f"pred{i}"]).max() < 2e-6
+        assert np.array_equal(out[f"mask{i}"], g[f"mask{i}"]) and np.array_equal(out[f"gt{i}"], g[f"gt{i}"])
