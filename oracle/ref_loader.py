@@ -394,8 +394,9 @@ def load_ensemble():
     return mod, captured
 
 
-def load_tta():
-    """The reference's lesion inference drivers, ``src/main/tta.py`` (``test_tta``, ``tta_patches``), executed
+def load_tta(which="tta"):
+    """The reference's inference drivers, ``src/main/tta.py`` (lesions; ``which="tta_vessel"``: its vessel twin
+    ``src/main/tta_vessel.py``, scored on ROC) -- ``test_tta``, ``tta_patches`` --, executed
     UNMODIFIED together with the reference's own ``TestSegmentation`` / ``NormalTransform`` / ``base_utils``
     (``make_grid``, ``multigen``, ``get_datapath``, ``save_output``) / ``aucpr.py`` and
     ``archs.get_preprocessing_fn``; ``archs.get_model`` builds the reference's own modules
@@ -428,6 +429,17 @@ def load_tta():
         captured["thresholds"] = [float(t) for t in th]
         return th
 
+    def get_aucroc(generator, config):
+        items = [(np.array(p), np.array(g), str(n)) for p, g, n in generator]
+        captured["items"] = items
+        captured["auc"] = float(ref.aucpr.get_aucroc(items, config))
+        return captured["auc"]
+
+    def plot_aucroc_curve(generator, exp_name, config):
+        t = ref.aucpr.plot_aucroc_curve(list(generator), exp_name, config)
+        captured["thresholds"] = [float(t)]
+        return t
+
     def save_output(mask, out_path):
         captured["masks"][os.path.basename(str(out_path))] = np.array(mask)
         return bu.save_output(mask, out_path)
@@ -437,13 +449,15 @@ def load_tta():
                     get_preprocessing_fn=get_preprocessing_fn)
     sys.modules["refsrc.main"].archs = archs
     # observed (not replaced) scoring / writer: the wrappers call the reference's functions
-    _module("refsrc.main.aucpr", get_auc=get_auc, plot_aucpr_curve=plot_aucpr_curve)
+    _module("refsrc.main.aucpr", get_auc=get_auc, plot_aucpr_curve=plot_aucpr_curve, get_aucroc=get_aucroc,
+            plot_aucroc_curve=plot_aucroc_curve)
     _module("refsrc.main.util", lesion_dict=bu.lesion_dict, get_datapath=bu.get_datapath, make_grid=bu.make_grid,
             multigen=bu.multigen, save_output=save_output)
     _module("refsrc.data", NormalTransform=data_transform.NormalTransform,
             TestSegmentation=lesion_dataset.TestSegmentation)
-    sys.modules.pop("refsrc.main.tta", None)
-    mod = _load("refsrc.main", "tta", os.path.join(REFERENCE_ROOT, "src", "main", "tta.py"))
+    assert which in ("tta", "tta_vessel")
+    sys.modules.pop("refsrc.main." + which, None)
+    mod = _load("refsrc.main", which, os.path.join(REFERENCE_ROOT, "src", "main", which + ".py"))
 
     class _HostTensor(torch.Tensor):
         def to(self, *args, **kwargs):           # tta.py:111 `.to('cuda')` on a CPU-only box

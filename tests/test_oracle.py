@@ -397,3 +397,32 @@ def test_reference_tta_patches_reproduces_its_fixture(tmp_path):
     for i in range(n):
         assert np.abs(out[f"pred{i}"] - g[f"pred{i}"]).max() < 2e-6
         assert np.array_equal(out[f"mask{i}"], g[f"mask{i}"]) and np.array_equal(out[f"gt{i}"], g[f"gt{i}"])
+
+
+def test_vessel_oracle_matches_the_reference_tta_vessel():
+    """tests/golden/tta_vessel.npz: the reference's OWN tta_vessel.test_tta (tta_vessel.py:55-136) on two pre-padded
+    256 x 256 images -- its TestSegmentation (labels read with > 50), dataset-independent statistics
+    (get_preprocessing_fn(None)), the reference's proposed network (base_dim 8) under D4 TTA, sigmoid, get_aucroc,
+    plot_aucroc_curve's threshold, uint8 masks.  The oracle must reproduce all of it from the same JPEG bytes."""
+    g, n = _golden_tta("vessel")
+    _, _, S, alias, _ = helpers.TTA_CASES["vessel"]
+    net = helpers.tta_case_oracle_net("vessel", helpers.tta_case_state_dict("vessel"))
+    mean, std = pipeline.DATASET_STATS["IDRiD"]                 # tta_vessel.py:73 passes dataset_name=None
+    items = []
+    for i in range(n):
+        image = _decode(g[f"jpeg{i}"])
+        gt = (_decode(g[f"maskjpeg{i}"])[..., 0] > 50).astype(np.uint8)
+        assert image.shape[:2] == (S, S) and np.array_equal(gt, g[f"gt{i}"])
+        x = torch.from_numpy(pipeline.preprocess(image, mean, std).transpose(2, 0, 1)).float()[None]
+        with torch.no_grad():
+            pred = torch.sigmoid(nets.tta_mean_logits(net, x, alias)[0, 0]).numpy()
+        assert np.abs(pred - g[f"pred{i}"]).max() < 2e-6, i
+        items.append((pred, gt, str(g["names"][i])))
+    assert abs(scoring.get_aucroc(items) - float(g["auc"])) < 1e-6
+    t = scoring.roc_curve(items)["threshold"]
+    assert [t] == list(g["thresholds"])
+    for i, (pred, _, name) in enumerate(items):
+        want = g[f"mask{i}"]
+        assert want.dtype == np.uint8
+        decided = np.abs(pred - t) > 1e-5
+        assert np.array_equal((pred > t)[decided], want.astype(bool)[decided]), name
