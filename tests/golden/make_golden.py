@@ -66,13 +66,14 @@ def ensemble_fixture_only():
 
 def tta_fixtures_only():
     """The reference's own src/main/tta.py -- tta_patches (sliding window, D4) and test_tta (whole image, hflip) -- and
-    src/main/tta_vessel.py -- test_tta (pre-padded squares, proposed network, D4, ROC scoring) -- run unmodified
+    src/main/tta_vessel.py -- test_tta (pre-padded squares, proposed network, D4, ROC scoring) and tta_patches (sliding
+    window over unpadded images, DRIVE statistics, ROC scoring) -- run unmodified
     (oracle/ref_loader.load_tta) from JPEG / TIFF files to scores and masks.  Two passes: the first, on
     random labels, only learns the probability maps; the committed case uses labels derived from them (top 30 % of
     each map with 5 % of the 8 x 8 blocks flipped; one image without positives for aucpr.py:22) so that the PR
     curve, the chosen threshold and the written masks are not degenerate."""
     import tempfile
-    for case in ("patches", "whole", "vessel"):
+    for case in ("patches", "whole", "vessel", "vpatches"):
         with tempfile.TemporaryDirectory() as tmp:
             first = helpers.run_reference_tta(tmp, case)
         n = len(first["names"])
@@ -91,7 +92,7 @@ def tta_fixtures_only():
             out = helpers.run_reference_tta(tmp, case, jpegs=[first[f"jpeg{i}"] for i in range(n)], gts=gts)
         for i in range(n):
             assert np.array_equal(out[f"pred{i}"], first[f"pred{i}"])
-            assert np.array_equal(out[f"gt{i}" if case == "vessel" else f"label{i}"], gts[i])
+            assert np.array_equal(out[f"gt{i}" if case in helpers.VESSEL_CASES else f"label{i}"], gts[i])
         np.savez_compressed(os.path.join(HERE, f"tta_{case}.npz"), **out)
         print(f"tta_{case}.npz written: auc", float(out["auc"]), "thresholds", out["thresholds"].tolist(),
               "mask means", [float(out[f"mask{i}"].mean()) for i in range(n)])

@@ -293,7 +293,11 @@ TTA_CASES = {
               [(89, 134), (89, 134)]),
     # tta_vessel.test_tta: whole pre-padded squares through the proposed network (base_dim 8 <-> 256^2), ROC scoring
     "vessel": ("unetplusplusstar", star_cfg(8), 256, "d4", [(256, 256), (256, 256)]),
+    # tta_vessel.tta_patches: sliding window over unpadded vessel images, DRIVE statistics, ROC scoring
+    "vpatches": ("unetplusplus_deepsup", dict(encoder_name="resnet34", encoder_weights=None, classes=1), 64, "d4",
+                 [(150, 180), (131, 140)]),
 }
+VESSEL_CASES = ("vessel", "vpatches")
 
 
 def tta_case_state_dict(case):
@@ -301,13 +305,14 @@ def tta_case_state_dict(case):
     sd = {k: v.clone() for k, v in build_product_model(name, cfg, seed=2001).state_dict().items()}
     # fixed head calibration (measured once on the case's first image): logits ~ mean 0, std 2, so that the
     # probabilities of the random-init network spread over the threshold list
-    scale, bias = {"patches": (5.0, -5.9), "whole": (1.0, 3.6), "vessel": VESSEL_HEAD}[case]
+    scale, bias = {"patches": (5.0, -5.9), "whole": (1.0, 3.6), "vessel": VESSEL_HEAD, "vpatches": VPATCHES_HEAD}[case]
     sd["segmentation_head.0.weight"] *= scale
     sd["segmentation_head.0.bias"] += bias
     return sd
 
 
 VESSEL_HEAD = (12.0, 8.0)
+VPATCHES_HEAD = (6.0, -4.75)
 
 
 def tta_case_oracle_net(case, sd):
@@ -319,14 +324,14 @@ def tta_case_oracle_net(case, sd):
     return lambda t: nets.unetplusplus_forward(sd, t)
 
 
-def _make_vessel_case(root, jpegs, gts, mask_jpegs, seed):
+def _make_vessel_case(root, case, jpegs, gts, mask_jpegs, seed):
     """tta_vessel layout: images and labels are both ``NN_test.jpg`` (get_datapath globs *.jpg for 'Vessel_*'), the
     labels are read with ``> 50`` (lesion_dataset.py:127), the checkpoint is ``last.pth``."""
     import io
     import numpy as np
     from pathlib import Path
     from PIL import Image
-    name, cfg, S, alias, shapes = TTA_CASES["vessel"]
+    name, cfg, S, alias, shapes = TTA_CASES[case]
     root = Path(root)
     img_dir, mask_dir = root / "vimages", root / "vmasks"
     img_dir.mkdir(parents=True)
@@ -342,19 +347,20 @@ def _make_vessel_case(root, jpegs, gts, mask_jpegs, seed):
         img = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
         yy, xx = np.mgrid[:h, :w]
         img[(yy - h / 2) ** 2 + (xx - w / 2) ** 2 > (0.48 * min(h, w)) ** 2] = 0
-        gt = (np.kron(rng.random((h // 8, w // 8)) < 0.15, np.ones((8, 8))) * 255).astype(np.uint8)
+        gt = (np.kron(rng.random((h // 8 + 1, w // 8 + 1)) < 0.15, np.ones((8, 8)))[:h, :w] * 255).astype(np.uint8)
         if gts is not None:
             gt = (np.asarray(gts[i]) > 0).astype(np.uint8) * 255
         (img_dir / f"{i:02d}_test.jpg").write_bytes(bytes(np.asarray(jpegs[i], dtype=np.uint8)) if jpegs is not None
                                                     else jpeg(img, 95))
         (mask_dir / f"{i:02d}_test.jpg").write_bytes(bytes(np.asarray(mask_jpegs[i], dtype=np.uint8))
                                                      if mask_jpegs is not None else jpeg(gt, 100))
-    logdir = root / "models" / "DRIVE" / "Vessel_DRIVE" / "vessel_exp"
+    logdir = root / "models" / "DRIVE" / "Vessel_DRIVE" / f"{case}_exp"
     (logdir / "checkpoints").mkdir(parents=True)
-    torch.save({"model_state_dict": tta_case_state_dict("vessel")}, logdir / "checkpoints" / "last.pth")
+    torch.save({"model_state_dict": tta_case_state_dict(case)}, logdir / "checkpoints" / "last.pth")
     config = {"dataset_name": "DRIVE", "lesion_type": "Vessel_DRIVE", "gray": False, "scale_size": S,
               "val_batch_size": 1, "model_name": name, "model_params": dict(cfg), "test_img_path": img_dir,
-              "test_mask_path": mask_dir, "out_dir": str(root / "outputs"), "data_type": "all"}
+              "test_mask_path": mask_dir, "out_dir": str(root / "outputs"),
+              "data_type": "all" if case == "vessel" else "tile"}
     return logdir, config, {"best": "false", "tta": alias}
 
 
@@ -368,8 +374,8 @@ def make_tta_case(root, case, jpegs=None, gts=None, seed=31, mask_jpegs=None):
     import numpy as np
     from pathlib import Path
     from PIL import Image
-    if case == "vessel":
-        return _make_vessel_case(root, jpegs, gts, mask_jpegs, seed)
+    if case in VESSEL_CASES:
+        return _make_vessel_case(root, case, jpegs, gts, mask_jpegs, seed)
     name, cfg, S, alias, shapes = TTA_CASES[case]
     root = Path(root)
     img_dir, mask_root = root / "images", root / "masks"
@@ -410,15 +416,15 @@ def run_reference_tta(root, case, jpegs=None, gts=None, mask_jpegs=None):
     from pathlib import Path
     from oracle import ref_loader
     logdir, config, args = make_tta_case(root, case, jpegs=jpegs, gts=gts, mask_jpegs=mask_jpegs)
-    mod, cap = ref_loader.load_tta("tta_vessel" if case == "vessel" else "tta")
-    (mod.tta_patches if case == "patches" else mod.test_tta)(str(logdir), copy.deepcopy(config), dict(args))
+    mod, cap = ref_loader.load_tta("tta_vessel" if case in VESSEL_CASES else "tta")
+    (mod.tta_patches if case in ("patches", "vpatches") else mod.test_tta)(str(logdir), copy.deepcopy(config), dict(args))
     key = (lambda n: n.replace("_EX.tif", ".jpg"))
     items = sorted(cap["items"], key=lambda it: key(it[2]))
     out = {"auc": np.float64(cap["auc"]), "thresholds": np.array(cap["thresholds"], dtype=np.float64),
            "names": np.array([key(n) for _, _, n in items])}
     for i, (pred, gt, n) in enumerate(items):
         out[f"jpeg{i}"] = np.frombuffer((Path(config["test_img_path"]) / key(n)).read_bytes(), dtype=np.uint8)
-        if case == "vessel":
+        if case in VESSEL_CASES:
             out[f"maskjpeg{i}"] = np.frombuffer((Path(config["test_mask_path"]) / key(n)).read_bytes(), dtype=np.uint8)
         else:
             out[f"label{i}"] = (np.asarray(__import__("PIL.Image", fromlist=["Image"]).open(

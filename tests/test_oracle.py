@@ -426,3 +426,29 @@ def test_vessel_oracle_matches_the_reference_tta_vessel():
         assert want.dtype == np.uint8
         decided = np.abs(pred - t) > 1e-5
         assert np.array_equal((pred > t)[decided], want.astype(bool)[decided]), name
+
+
+def test_vessel_tiled_oracle_matches_the_reference_tta_vessel_patches():
+    """tests/golden/tta_vpatches.npz: the reference's OWN tta_vessel.tta_patches (tta_vessel.py:138-229) on two
+    unpadded images -- PIL read, make_grid windows of 2S, A.Resize, DRIVE statistics, D4 TTA, sigmoid, cv2 x2 resize,
+    overwrite paste, labels read with > 50, get_aucroc, plot_aucroc_curve's threshold, float32 masks."""
+    g, n = _golden_tta("vpatches")
+    _, _, S, alias, shapes = helpers.TTA_CASES["vpatches"]
+    net = helpers.tta_case_oracle_net("vpatches", helpers.tta_case_state_dict("vpatches"))
+    mean, std = pipeline.DATASET_STATS["DRIVE"]
+    items = []
+    for i in range(n):
+        image = _decode(g[f"jpeg{i}"])
+        gt = (_decode(g[f"maskjpeg{i}"])[..., 0] > 50).astype(np.uint8)
+        assert image.shape[:2] == shapes[i] and np.array_equal(gt, g[f"gt{i}"])
+        pred = pipeline.tiled_probability_map(image, net, S, mean, std, alias)
+        assert np.abs(pred - g[f"pred{i}"]).max() < 2e-6, i
+        items.append((pred, gt, str(g["names"][i])))
+    assert abs(scoring.get_aucroc(items) - float(g["auc"])) < 1e-6
+    t = scoring.roc_curve(items)["threshold"]
+    assert [t] == list(g["thresholds"])
+    for i, (pred, _, name) in enumerate(items):
+        want = g[f"mask{i}"]
+        assert want.dtype == np.float32                         # tta_vessel.py:217
+        decided = np.abs(pred - t) > 1e-5
+        assert np.array_equal((pred > t)[decided], want.astype(bool)[decided]), name
